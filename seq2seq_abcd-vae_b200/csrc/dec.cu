@@ -1,0 +1,782 @@
+// Decoder recurrence with self-feedback: RNN_Variational_Decoder._forward_unidirectional
+// (ABCD-VAE/modules/model.py:165-196) and its backward.  Step t feeds the Gaussian sample drawn from step
+// t-1's emission parameters back into the cell (model.py:177-180), so nothing can be hoisted out of the
+// time loop: the per-step chain is  cell([x_t | h_{t-1}]) -> 2 emission MLPs -> reparameterised sample.
+//
+// One persistent cluster kernel per direction of time (forward / BPTT).  Per step, three phases separated by
+// hardware cluster barriers; every weight slice stays resident in shared memory (see rnn_common.cuh):
+//   fwd  P1 gates+cell (K = Fp+H)      P2 MLP hidden layers (K = H)        P3 mean/log-var/sample/NLL (K = 2M)
+//   bwd  B3 d(hidden pre-act) (K=2Fp)  B2 dh + gate gradients (K = 2M)     B1 [dh_prev | dx] (K = 4H)
+// The offset predictor (model.py:191-195) does not feed the recurrence and runs as plain GEMMs over all
+// frames, as do all weight gradients.
+#include "rnn_common.cuh"
+#include "sgemm.cuh"
+#include "enc.cuh"
+
+using namespace rnn;
+
+namespace {
+
+constexpr int DEC_KC = 64;
+constexpr int DEC_LDA = DEC_KC + 4;
+constexpr float LOG_2PI = 1.8378770664093453f;
+
+__host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
+__host__ __device__ inline int xcols_per_cta(int F) { return (F + CL - 1) / CL; }
+
+struct DecK {
+    int cell, F, Fp, n_tiles, B, T_max;
+    int ld_eps, ld_gt;
+    const int* batch_sizes; const int* offsets; const int* lengths;
+    // parameters
+    const float* w_ih; const float* w_hh; const float* b_ih; const float* b_hh;
+    const float* em_w1[2]; const float* em_b1[2]; const float* em_w2[2]; const float* em_b2[2];
+    // activations (see DecWs)
+    float* Hall; float* Call; float* Xall; float* Gs; float* Hid; float* Mean; float* Lv;
+    const float* eps; const float* gt;
+    float* nll_partial;   // [gridDim.x]
+    // backward only
+    float* dML; float* dHidPre; float* dG; const float* dHoff; float* dHC0;
+};
+
+// -------------------------------------------------------------------------------------------------
+// forward
+// -------------------------------------------------------------------------------------------------
+template <int CELL>
+__global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
+    extern __shared__ __align__(16) float smem[];
+    const int H = ABCD_H, M = ABCD_M;
+    const int F = p.F, Fp = p.Fp;
+    const int XC = xcols_per_cta(F);
+    const int ncg3 = (XC + 1) / 2, NC3 = ncg3 * 4;
+    float* Wg = smem;                         // [Fp+H][U*4]
+    float* W1 = Wg + (Fp + H) * (U * 4);      // [H][2U]
+    float* W3 = W1 + H * (2 * U);             // [2M][NC3]
+    float* stage0 = W3 + 2 * M * NC3;
+    float* stage1 = stage0 + ROWS * DEC_LDA;
+    float* red = stage1 + ROWS * DEC_LDA;     // 40 floats
+    const Stage st{stage0, stage1, DEC_LDA, DEC_KC};
+
+    const int tid = threadIdx.x;
+    const int rank = (int)cluster_ctarank();
+    const int tile = blockIdx.x / CL;
+    const int u0 = rank * U;
+    const int xc0 = rank * XC;
+    const int xc1 = min(F, xc0 + XC);
+
+    // ---- resident weights ----
+    for (int idx = tid; idx < (Fp + H) * (U * 4); idx += NTHREADS) {
+        int col = idx % (U * 4), k = idx / (U * 4);
+        int u = col >> 2, s = col & 3;
+        float v = 0.f;
+        if (k < Fp) {
+            int gate = CELL == 0 ? s : (s == 3 ? -1 : s);
+            if (k < F && gate >= 0) v = p.w_ih[(long)(gate * H + u0 + u) * F + k];
+        } else {
+            int gate = CELL == 0 ? s : (s == 0 ? 0 : s == 1 ? 1 : s == 3 ? 2 : -1);
+            if (gate >= 0) v = p.w_hh[(long)(gate * H + u0 + u) * H + (k - Fp)];
+        }
+        Wg[idx] = v;
+    }
+    for (int idx = tid; idx < H * 2 * U; idx += NTHREADS) {
+        int col = idx % (2 * U), k = idx / (2 * U);
+        int which = col / U, u = col % U;
+        W1[idx] = p.em_w1[which][(long)(u0 + u) * H + k];
+    }
+    for (int idx = tid; idx < 2 * M * NC3; idx += NTHREADS) {
+        int col = idx % NC3, k = idx / NC3;
+        int q = col >> 2, j = col & 3;           // j: 0,1 -> mean cols; 2,3 -> log-var cols
+        int which = j >> 1;
+        int c = xc0 + 2 * q + (j & 1);
+        float v = 0.f;
+        bool in_block = which == 0 ? (k < M) : (k >= M);
+        if (in_block && c < xc1) v = p.em_w2[which][(long)c * M + (which == 0 ? k : k - M)];
+        W3[idx] = v;
+    }
+
+    // ---- per-thread constants for the three phases ----
+    const ThreadMap tm1 = make_map(tid, U, 1);
+    const int unit = u0 + tm1.cg;
+    float bias1[4];
+    if (CELL == 0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) bias1[g] = p.b_ih[g * H + unit] + p.b_hh[g * H + unit];
+    } else {
+        bias1[0] = p.b_ih[unit] + p.b_hh[unit];
+        bias1[1] = p.b_ih[H + unit] + p.b_hh[H + unit];
+        bias1[2] = p.b_ih[2 * H + unit];
+        bias1[3] = p.b_hh[2 * H + unit];
+    }
+    const int KS2 = pick_ks(2 * U / 4);
+    const ThreadMap tm2 = make_map(tid, 2 * U / 4, KS2);
+    float bias2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int col = tm2.cg * 4 + j;
+        bias2[j] = p.em_b1[col / U][u0 + col % U];
+    }
+    const int KS3 = pick_ks(ncg3);
+    const ThreadMap tm3 = make_map(tid, ncg3, KS3);
+    float bias3[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int c = xc0 + 2 * tm3.cg + (j & 1);
+        bias3[j] = (tm3.active && c < xc1) ? p.em_b2[j >> 1][c] : 0.f;
+    }
+
+    // recurrent state of (row, unit) pairs owned by this thread
+    float creg[RT], hreg[RT];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+        int b = tile + p.n_tiles * (tm1.rg + i * RG);
+        creg[i] = 0.f; hreg[i] = 0.f;
+        if (b < p.B) {
+            hreg[i] = p.Hall[(long)b * H + unit];
+            if (CELL == 0) creg[i] = p.Call[(long)b * H + unit];
+        }
+    }
+    const int Tt = p.lengths[tile];
+    float nll = 0.f;
+    const int n_tiles = p.n_tiles, B = p.B;
+    const float* Hall = p.Hall; const float* Xall = p.Xall; const float* Hid = p.Hid;
+    __syncthreads();
+
+    for (int t = 0; t < Tt; ++t) {
+        const int na = active_rows(p.batch_sizes[t], tile, n_tiles);
+        const long off_t = p.offsets[t];
+        const long prev_base = t == 0 ? 0 : (long)B + p.offsets[t - 1];
+
+        // ---- P1: gates + cell ----
+        {
+            float acc[RT][4];
+            zero_acc(acc);
+            auto rpx = [=](int r) -> const float* { return Xall + (prev_base + tile + (long)n_tiles * r) * Fp; };
+            auto rph = [=](int r) -> const float* { return Hall + (prev_base + tile + (long)n_tiles * r) * ABCD_H; };
+            phase_gemm(acc, st, Fp, rpx, H, rph, na, Wg, U * 4, tm1, 1, tid);
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+                int r = tm1.rg + i * RG;
+                if (r >= na) continue;
+                long frame = off_t + tile + (long)n_tiles * r;
+                float h;
+                if (CELL == 0) {
+                    float ig = sigmoid_acc(acc[i][0] + bias1[0]);
+                    float fg = sigmoid_acc(acc[i][1] + bias1[1]);
+                    float gg = tanhf(acc[i][2] + bias1[2]);
+                    float og = sigmoid_acc(acc[i][3] + bias1[3]);
+                    float c = fg * creg[i] + ig * gg;
+                    h = og * tanhf(c);
+                    creg[i] = c;
+                    *reinterpret_cast<float4*>(p.Gs + frame * (4 * H) + unit * 4) = make_float4(ig, fg, gg, og);
+                    p.Call[((long)B + frame) * H + unit] = c;
+                } else {
+                    float rg_ = sigmoid_acc(acc[i][0] + bias1[0]);
+                    float zg = sigmoid_acc(acc[i][1] + bias1[1]);
+                    float hn = acc[i][3] + bias1[3];
+                    float ng = tanhf(acc[i][2] + bias1[2] + rg_ * hn);
+                    h = (1.f - zg) * ng + zg * hreg[i];
+                    *reinterpret_cast<float4*>(p.Gs + frame * (4 * H) + unit * 4) = make_float4(rg_, zg, ng, hn);
+                }
+                hreg[i] = h;
+                p.Hall[((long)B + frame) * H + unit] = h;
+            }
+        }
+        cluster_sync_all();
+
+        // ---- P2: hidden layers of the two emission MLPs ----
+        {
+            float acc[RT][4];
+            zero_acc(acc);
+            auto rph = [=](int r) -> const float* { return Hall + ((long)B + off_t + tile + (long)n_tiles * r) * ABCD_H; };
+            phase_gemm(acc, st, H, rph, 0, NullRow(), na, W1, 2 * U, tm2, KS2, tid);
+            if (tm2.active && tm2.ks == 0) {
+#pragma unroll
+                for (int i = 0; i < RT; ++i) {
+                    int r = tm2.rg + i * RG;
+                    if (r >= na) continue;
+                    long frame = off_t + tile + (long)n_tiles * r;
+                    int col = tm2.cg * 4;
+                    int which = col / U, uu = col % U;
+                    float4 v = make_float4(tanhf(acc[i][0] + bias2[0]), tanhf(acc[i][1] + bias2[1]),
+                                           tanhf(acc[i][2] + bias2[2]), tanhf(acc[i][3] + bias2[3]));
+                    *reinterpret_cast<float4*>(p.Hid + frame * (2 * M) + which * M + u0 + uu) = v;
+                }
+            }
+        }
+        cluster_sync_all();
+
+        // ---- P3: emission parameters, reparameterised sample, NLL ----
+        {
+            float acc[RT][4];
+            zero_acc(acc);
+            auto rph = [=](int r) -> const float* { return Hid + (off_t + tile + (long)n_tiles * r) * (2 * ABCD_M); };
+            phase_gemm(acc, st, 2 * M, rph, 0, NullRow(), na, W3, NC3, tm3, KS3, tid);
+            if (tm3.active && tm3.ks == 0) {
+#pragma unroll
+                for (int i = 0; i < RT; ++i) {
+                    int r = tm3.rg + i * RG;
+                    if (r >= na) continue;
+                    long frame = off_t + tile + (long)n_tiles * r;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        int c = xc0 + 2 * tm3.cg + j;
+                        if (c >= xc1) continue;
+                        float mean = acc[i][j] + bias3[j];
+                        float lv = acc[i][2 + j] + bias3[2 + j];
+                        float e = p.eps[frame * p.ld_eps + c];
+                        float x = mean + expf(0.5f * lv) * e;
+                        p.Mean[frame * Fp + c] = mean;
+                        p.Lv[frame * Fp + c] = lv;
+                        p.Xall[((long)B + frame) * Fp + c] = x;
+                        if (p.gt) {
+                            float d = p.gt[frame * p.ld_gt + c] - mean;
+                            nll += 0.5f * (LOG_2PI + lv + d * expf(-lv) * d);
+                        }
+                    }
+                }
+            }
+        }
+        cluster_sync_all();
+    }
+    float tot = block_sum(nll, red);
+    if (tid == 0) p.nll_partial[blockIdx.x] = tot;
+}
+
+// -------------------------------------------------------------------------------------------------
+// backward
+// -------------------------------------------------------------------------------------------------
+template <int CELL>
+__global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
+    extern __shared__ __align__(16) float smem[];
+    const int H = ABCD_H, M = ABCD_M;
+    const int F = p.F, Fp = p.Fp;
+    const int XC = xcols_per_cta(F);
+    const int NCX = pad4(XC);
+    const int NCB1 = U + NCX;
+    float* WB3 = smem;                        // [2Fp][2U]
+    float* WB2 = WB3 + 2 * Fp * (2 * U);      // [2M][U]
+    float* WB1 = WB2 + 2 * M * U;             // [4H][NCB1]
+    float* dh_sm = WB1 + 4 * H * NCB1;        // [ROWS][U]
+    float* dc_sm = dh_sm + ROWS * U;          // [ROWS][U]
+    float* stage0 = dc_sm + ROWS * U;
+    float* stage1 = stage0 + ROWS * DEC_LDA;
+    const Stage st{stage0, stage1, DEC_LDA, DEC_KC};
+
+    const int tid = threadIdx.x;
+    const int rank = (int)cluster_ctarank();
+    const int tile = blockIdx.x / CL;
+    const int u0 = rank * U;
+    const int xc0 = rank * XC;
+    const int xc1 = min(F, xc0 + XC);
+
+    for (int idx = tid; idx < 2 * Fp * 2 * U; idx += NTHREADS) {
+        int col = idx % (2 * U), k = idx / (2 * U);
+        int which = col / U, u = col % U;
+        int kk = which == 0 ? k : k - Fp;
+        float v = 0.f;
+        if (kk >= 0 && kk < F) v = p.em_w2[which][(long)kk * M + u0 + u];
+        WB3[idx] = v;
+    }
+    for (int idx = tid; idx < 2 * M * U; idx += NTHREADS) {
+        int j = idx % U, k = idx / U;
+        int which = k / M, kk = k % M;
+        WB2[idx] = p.em_w1[which][(long)kk * H + u0 + j];
+    }
+    for (int idx = tid; idx < 4 * H * NCB1; idx += NTHREADS) {
+        int col = idx % NCB1, kphys = idx / NCB1;
+        int uu = kphys >> 2, s = kphys & 3;
+        float v = 0.f;
+        if (col < U) {
+            int gate = CELL == 0 ? s : (s == 0 ? 0 : s == 1 ? 1 : s == 3 ? 2 : -1);
+            if (gate >= 0) v = p.w_hh[(long)(gate * H + uu) * H + u0 + col];
+        } else {
+            int c = xc0 + (col - U);
+            int gate = CELL == 0 ? s : (s == 3 ? -1 : s);
+            if (gate >= 0 && (col - U) < XC && c < xc1) v = p.w_ih[(long)(gate * H + uu) * F + c];
+        }
+        WB1[idx] = v;
+    }
+    for (int idx = tid; idx < ROWS * U; idx += NTHREADS) { dh_sm[idx] = 0.f; dc_sm[idx] = 0.f; }
+
+    const int KS3 = pick_ks(2 * U / 4);
+    const ThreadMap tm3 = make_map(tid, 2 * U / 4, KS3);
+    const int KS2 = pick_ks(U / 4);
+    const ThreadMap tm2 = make_map(tid, U / 4, KS2);
+    const int ncg1 = NCB1 / 4;
+    const int KS1 = pick_ks(ncg1);
+    const ThreadMap tm1 = make_map(tid, ncg1, KS1);
+    const int pu = tid % U, prg = tid / U;
+    const int unit = u0 + pu;
+
+    const int Tt = p.lengths[tile];
+    const int n_tiles = p.n_tiles, B = p.B;
+    const float* dML = p.dML; const float* dHidPre = p.dHidPre; const float* dG = p.dG;
+    __syncthreads();
+
+    for (int t = Tt - 1; t >= 0; --t) {
+        const int na = active_rows(p.batch_sizes[t], tile, n_tiles);
+        const long off_t = p.offsets[t];
+        const long prev_base = t == 0 ? 0 : (long)B + p.offsets[t - 1];
+
+        // ---- B3: gradient w.r.t. the MLP hidden pre-activations ----
+        {
+            float acc[RT][4];
+            zero_acc(acc);
+            auto rp = [=](int r) -> const float* { return dML + (off_t + tile + (long)n_tiles * r) * (2 * Fp); };
+            phase_gemm(acc, st, 2 * Fp, rp, 0, NullRow(), na, WB3, 2 * U, tm3, KS3, tid);
+            if (tm3.active && tm3.ks == 0) {
+#pragma unroll
+                for (int i = 0; i < RT; ++i) {
+                    int r = tm3.rg + i * RG;
+                    if (r >= na) continue;
+                    long frame = off_t + tile + (long)n_tiles * r;
+                    int col = tm3.cg * 4;
+                    int which = col / U, uu = col % U;
+                    long o = frame * (2 * M) + which * M + u0 + uu;
+                    float4 hd = *reinterpret_cast<const float4*>(p.Hid + o);
+                    float4 v = make_float4(acc[i][0] * (1.f - hd.x * hd.x), acc[i][1] * (1.f - hd.y * hd.y),
+                                           acc[i][2] * (1.f - hd.z * hd.z), acc[i][3] * (1.f - hd.w * hd.w));
+                    *reinterpret_cast<float4*>(p.dHidPre + o) = v;
+                }
+            }
+        }
+        cluster_sync_all();
+
+        // ---- B2: dh from the emission MLPs, then gate gradients ----
+        {
+            float acc[RT][4];
+            zero_acc(acc);
+            auto rp = [=](int r) -> const float* { return dHidPre + (off_t + tile + (long)n_tiles * r) * (2 * ABCD_M); };
+            phase_gemm(acc, st, 2 * M, rp, 0, NullRow(), na, WB2, U, tm2, KS2, tid);
+            if (tm2.active && tm2.ks == 0) {
+#pragma unroll
+                for (int i = 0; i < RT; ++i) {
+                    int r = tm2.rg + i * RG;
+                    if (r >= na) continue;
+                    float4* d = reinterpret_cast<float4*>(dh_sm + r * U + tm2.cg * 4);
+                    float4 v = *d;
+                    v.x += acc[i][0]; v.y += acc[i][1]; v.z += acc[i][2]; v.w += acc[i][3];
+                    *d = v;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+                int r = prg + i * RG;
+                if (r >= na) continue;
+                long b = tile + (long)n_tiles * r;
+                long frame = off_t + b;
+                long prow = prev_base + b;
+                float dh = dh_sm[r * U + pu] + p.dHoff[frame * H + unit];
+                float carry = dc_sm[r * U + pu];
+                const float4 g4 = *reinterpret_cast<const float4*>(p.Gs + frame * (4 * H) + unit * 4);
+                float4 dgv;
+                if (CELL == 0) {
+                    float c = p.Call[((long)B + frame) * H + unit];
+                    float c_prev = p.Call[prow * H + unit];
+                    float tc = tanhf(c);
+                    float ig = g4.x, fg = g4.y, gg = g4.z, og = g4.w;
+                    float dc = carry + dh * og * (1.f - tc * tc);
+                    dgv.x = dc * gg * ig * (1.f - ig);
+                    dgv.y = dc * c_prev * fg * (1.f - fg);
+                    dgv.z = dc * ig * (1.f - gg * gg);
+                    dgv.w = dh * tc * og * (1.f - og);
+                    dc_sm[r * U + pu] = dc * fg;
+                } else {
+                    dh += carry;
+                    float h_prev = p.Hall[prow * H + unit];
+                    float rg_ = g4.x, zg = g4.y, ng = g4.z, hn = g4.w;
+                    float dn_pre = dh * (1.f - zg) * (1.f - ng * ng);
+                    dgv.x = dn_pre * hn * rg_ * (1.f - rg_);
+                    dgv.y = dh * (h_prev - ng) * zg * (1.f - zg);
+                    dgv.z = dn_pre;
+                    dgv.w = dn_pre * rg_;
+                    dc_sm[r * U + pu] = dh * zg;
+                }
+                *reinterpret_cast<float4*>(p.dG + frame * (4 * H) + unit * 4) = dgv;
+            }
+        }
+        cluster_sync_all();
+
+        // ---- B1: [dh_{t-1} | dx_t] = dG * [W_hh | W_ih] ----
+        {
+            float acc[RT][4];
+            zero_acc(acc);
+            auto rp = [=](int r) -> const float* { return dG + (off_t + tile + (long)n_tiles * r) * (4 * ABCD_H); };
+            phase_gemm(acc, st, 4 * H, rp, 0, NullRow(), na, WB1, NCB1, tm1, KS1, tid);
+            if (tm1.active && tm1.ks == 0) {
+#pragma unroll
+                for (int i = 0; i < RT; ++i) {
+                    int r = tm1.rg + i * RG;
+                    if (r >= na) continue;
+                    if (tm1.cg < U / 4) {
+                        *reinterpret_cast<float4*>(dh_sm + r * U + tm1.cg * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                    } else if (t > 0) {
+                        long pf = p.offsets[t - 1] + tile + (long)n_tiles * r;   // frame that produced x_t
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            int q = (tm1.cg - U / 4) * 4 + j;
+                            int c = xc0 + q;
+                            if (q < XC && c < xc1) {
+                                float dx = acc[i][j];
+                                float lv = p.Lv[pf * Fp + c];
+                                float e = p.eps[pf * p.ld_eps + c];
+                                p.dML[pf * (2 * Fp) + c] += dx;
+                                p.dML[pf * (2 * Fp) + Fp + c] += dx * 0.5f * expf(0.5f * lv) * e;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        cluster_sync_all();
+    }
+    // gradient w.r.t. the initial state produced by feature2hidden (h0 = even, c0 = odd columns; model.py:100)
+    for (int i = 0; i < RT; ++i) {
+        int r = prg + i * RG;
+        long b = tile + (long)n_tiles * r;
+        if (b >= B) continue;
+        if (CELL == 0) {
+            p.dHC0[b * (2 * H) + 2 * unit] = dh_sm[r * U + pu];
+            p.dHC0[b * (2 * H) + 2 * unit + 1] = dc_sm[r * U + pu];
+        } else {
+            p.dHC0[b * H + unit] = dh_sm[r * U + pu] + dc_sm[r * U + pu];
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// helper kernels outside the time loop
+// -------------------------------------------------------------------------------------------------
+// hc0 [B][2H] interleaved (h even, c odd) -> Hall[0..B), Call[0..B)   (GRU: hc0 [B][H] -> Hall)
+__global__ void split_hc0_kernel(int cell, int B, const float* __restrict__ hc0, float* __restrict__ Hall, float* __restrict__ Call) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * ABCD_H) return;
+    if (cell == 0) {
+        Hall[idx] = hc0[2 * (long)idx];
+        Call[idx] = hc0[2 * (long)idx + 1];
+    } else {
+        Hall[idx] = hc0[idx];
+    }
+}
+
+__global__ void final_sum_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+    __shared__ double red[40];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)partial[i];
+    s = block_sum_d(s, red);
+    if (threadIdx.x == 0) *out = (float)s;
+}
+
+// offset logit = hid . w2 + b2 ; BCE-with-logits (sum) against is_offset  (model.py:122,191-195)
+__global__ void offset_head_kernel(int sumT, const float* __restrict__ hid, const float* __restrict__ w2,
+                                   const float* __restrict__ b2, const float* __restrict__ y,
+                                   float* __restrict__ logit_out, float* __restrict__ partial) {
+    __shared__ float red[40];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float loss = 0.f;
+    for (long n = (long)blockIdx.x * nw + w; n < sumT; n += (long)gridDim.x * nw) {
+        float s = 0.f;
+        for (int j = lane; j < ABCD_M; j += 32) s += hid[n * ABCD_M + j] * w2[j];
+        s = warp_sum(s) + b2[0];
+        if (lane == 0) {
+            logit_out[n] = s;
+            if (y) loss += fmaxf(s, 0.f) - s * y[n] + log1pf(expf(-fabsf(s)));
+        }
+    }
+    float tot = block_sum(loss, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+// d logit = (sigmoid(logit) - y) * g_off ;  dHidOffPre[n][j] = dlogit * w2[j] * (1 - hid^2)
+__global__ void offset_head_bwd_kernel(int sumT, const float* __restrict__ hid, const float* __restrict__ w2,
+                                       const float* __restrict__ logit, const float* __restrict__ y,
+                                       const float* __restrict__ g_losses, float* __restrict__ dlogit,
+                                       float* __restrict__ dpre) {
+    const float g = g_losses[1];
+    long total = (long)sumT * ABCD_M;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        long n = idx / ABCD_M; int j = (int)(idx % ABCD_M);
+        float dl = (sigmoid_acc(logit[n]) - y[n]) * g;
+        float hd = hid[idx];
+        dpre[idx] = dl * w2[j] * (1.f - hd * hd);
+        if (j == 0) dlogit[n] = dl;
+    }
+}
+
+// dML[n] = [ d nll/d mean | d nll/d logvar ] * g_em   (padding columns zero)   (model.py:30-37)
+__global__ void nll_grad_kernel(int sumT, int F, int Fp, const float* __restrict__ mean, const float* __restrict__ lv,
+                                const float* __restrict__ gt, int ld_gt, const float* __restrict__ g_losses,
+                                float* __restrict__ dML) {
+    const float g = g_losses[0];
+    long total = (long)sumT * Fp;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        long n = idx / Fp; int c = (int)(idx % Fp);
+        float dm = 0.f, dl = 0.f;
+        if (c < F) {
+            float d = gt[n * ld_gt + c] - mean[idx];
+            float e = expf(-lv[idx]);
+            dm = -d * e * g;
+            dl = 0.5f * (1.f - d * d * e) * g;
+        }
+        dML[n * (2 * Fp) + c] = dm;
+        dML[n * (2 * Fp) + Fp + c] = dl;
+    }
+}
+
+__global__ void dec_prev_index_kernel(int T_max, int B, const int* __restrict__ batch_sizes, const int* __restrict__ offsets,
+                                      int* __restrict__ prev) {
+    for (int t = blockIdx.x; t < T_max; t += gridDim.x) {
+        int bs = batch_sizes[t], off = offsets[t];
+        for (int b = threadIdx.x; b < bs; b += blockDim.x) prev[off + b] = t > 0 ? B + offsets[t - 1] + b : b;
+    }
+}
+
+__global__ void unpad_copy_kernel(long rows, int F, int ld_src, const float* __restrict__ src, float* __restrict__ dst) {
+    long total = rows * F;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        long n = idx / F; int c = (int)(idx % F);
+        dst[idx] = src[n * ld_src + c];
+    }
+}
+
+size_t dec_fwd_smem(int F) {
+    int Fp = pad4(F), XC = xcols_per_cta(F), NC3 = ((XC + 1) / 2) * 4;
+    return (size_t)((Fp + ABCD_H) * U * 4 + ABCD_H * 2 * U + 2 * ABCD_M * NC3 + 2 * ROWS * DEC_LDA + 64) * sizeof(float);
+}
+size_t dec_bwd_smem(int F) {
+    int Fp = pad4(F), XC = xcols_per_cta(F), NCB1 = U + pad4(XC);
+    return (size_t)(2 * Fp * 2 * U + 2 * ABCD_M * U + 4 * ABCD_H * NCB1 + 2 * ROWS * U + 2 * ROWS * DEC_LDA) * sizeof(float);
+}
+constexpr int DEC_MAX_F = 129;
+
+template <class K>
+int launch_cluster_dec(K kernel, int n_clusters, size_t smem, cudaStream_t stream, const DecK& params) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(n_clusters * CL);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, params));
+    return ABCD_OK;
+}
+
+struct DecWs {
+    float *hc0, *Hall, *Call, *Xall, *Gs, *Hid, *Mean, *Lv, *HidOff, *OffLogit, *nll_partial, *bce_partial;
+    float *dML, *dHidPre, *dG, *dHoff, *dHidOffPre, *dLogit, *dHC0, *partials;
+    int* prev;
+    size_t partial_floats;
+    size_t bytes;
+};
+constexpr int BCE_BLOCKS = 296;
+
+DecWs dec_carve(void* base, size_t cap, int cell, int F, int fin, int B, int sumT) {
+    Arena a(base, cap);
+    DecWs w;
+    memset(&w, 0, sizeof(w));
+    const int H = ABCD_H, M = ABCD_M, Fp = pad4(F);
+    const int hc = cell == 0 ? 2 * H : H;
+    const int n_tiles = (B + ROWS - 1) / ROWS;
+    w.hc0 = a.take<float>((size_t)B * hc);
+    w.Hall = a.take<float>((size_t)(B + sumT) * H);
+    w.Call = a.take<float>((size_t)(B + sumT) * H);
+    w.Xall = a.take<float>((size_t)(B + sumT) * Fp);
+    w.Gs = a.take<float>((size_t)sumT * 4 * H);
+    w.Hid = a.take<float>((size_t)sumT * 2 * M);
+    w.Mean = a.take<float>((size_t)sumT * Fp);
+    w.Lv = a.take<float>((size_t)sumT * Fp);
+    w.HidOff = a.take<float>((size_t)sumT * M);
+    w.OffLogit = a.take<float>((size_t)sumT);
+    w.nll_partial = a.take<float>((size_t)n_tiles * CL);
+    w.bce_partial = a.take<float>(BCE_BLOCKS);
+    w.dML = a.take<float>((size_t)sumT * 2 * Fp);
+    w.dHidPre = a.take<float>((size_t)sumT * 2 * M);
+    w.dG = a.take<float>((size_t)sumT * 4 * H);
+    w.dHoff = a.take<float>((size_t)sumT * H);
+    w.dHidOffPre = a.take<float>((size_t)sumT * M);
+    w.dLogit = a.take<float>((size_t)sumT);
+    w.dHC0 = a.take<float>((size_t)B * hc);
+    w.prev = a.take<int>((size_t)sumT);
+    // largest split-K partial: dW_hh / dW_ih ([4H] x [H|F]) or MLP weights ([M] x [H])
+    size_t mx = 0;
+    {
+        int dims[][3] = {{4 * H, H, sumT}, {4 * H, F, sumT}, {M, H, sumT}, {F, M, sumT}, {1, M, sumT}, {hc, fin, B}};
+        for (auto& d : dims) {
+            size_t v = (size_t)sgemm_pick_splits(d[0], d[1], d[2]) * d[0] * d[1];
+            if (v > mx) mx = v;
+        }
+    }
+    w.partial_floats = mx;
+    w.partials = a.take<float>(mx);
+    w.bytes = a.off;
+    return w;
+}
+
+DecK make_k(const DecParams& P, const PackedMeta& pk, const DecWs& w) {
+    DecK k;
+    memset(&k, 0, sizeof(k));
+    k.cell = P.cell; k.F = P.F; k.Fp = pad4(P.F);
+    k.n_tiles = (pk.B + ROWS - 1) / ROWS; k.B = pk.B; k.T_max = pk.T_max;
+    k.batch_sizes = pk.batch_sizes; k.offsets = pk.offsets; k.lengths = pk.lengths;
+    k.w_ih = P.w_ih; k.w_hh = P.w_hh; k.b_ih = P.b_ih; k.b_hh = P.b_hh;
+    for (int i = 0; i < 2; ++i) { k.em_w1[i] = P.em_w1[i]; k.em_b1[i] = P.em_b1[i]; k.em_w2[i] = P.em_w2[i]; k.em_b2[i] = P.em_b2[i]; }
+    k.Hall = w.Hall; k.Call = w.Call; k.Xall = w.Xall; k.Gs = w.Gs; k.Hid = w.Hid; k.Mean = w.Mean; k.Lv = w.Lv;
+    k.nll_partial = w.nll_partial;
+    k.dML = w.dML; k.dHidPre = w.dHidPre; k.dG = w.dG; k.dHoff = w.dHoff; k.dHC0 = w.dHC0;
+    return k;
+}
+
+int check_dec(const DecParams& P) {
+    ARG_CHECK(P.H == ABCD_H, "decoder: rnn_hidden_size %d unsupported (kernels are specialised for %d)", P.H, ABCD_H);
+    ARG_CHECK(P.M == ABCD_M, "decoder: mlp_hidden_size %d unsupported (kernels are specialised for %d)", P.M, ABCD_M);
+    ARG_CHECK(P.F >= 1 && P.F <= DEC_MAX_F, "decoder: output_size %d unsupported (1..%d)", P.F, DEC_MAX_F);
+    ARG_CHECK(P.cell == 0 || P.cell == 1, "decoder: rnn_type must be LSTM or GRU");
+    return ABCD_OK;
+}
+
+}  // namespace
+
+int dec_init() {
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0>, dec_fwd_smem(DEC_MAX_F)));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1>, dec_fwd_smem(DEC_MAX_F)));
+    TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<0>, dec_bwd_smem(DEC_MAX_F)));
+    TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<1>, dec_bwd_smem(DEC_MAX_F)));
+    return ABCD_OK;
+}
+
+size_t dec_workspace_bytes(int cell, int F, int fin, int B, int sumT) {
+    return dec_carve(nullptr, 0, cell, F, fin, B, sumT).bytes;
+}
+
+int dec_forward(const DecParams& P, const PackedMeta& pk, const float* feat_in, const float* eps, int ld_eps,
+                const float* gt, int ld_gt, const float* is_offset, float* losses, float* out_x, float* out_mean,
+                float* out_logvar, float* out_offset_logit, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    TRY(check_dec(P));
+    ARG_CHECK(pk.B > 0 && pk.T_max > 0 && pk.sumT > 0, "decoder: empty packed batch");
+    ARG_CHECK(eps != nullptr, "decoder: emission noise buffer is required");
+    const int H = ABCD_H, M = ABCD_M, Fp = pad4(P.F);
+    const int hc = P.cell == 0 ? 2 * H : H;
+    DecWs w = dec_carve(ws, ws_bytes, P.cell, P.F, P.fin, pk.B, pk.sumT);
+    if (w.bytes > ws_bytes) { abcd_set_error("decoder: workspace too small (%zu < %zu)", ws_bytes, w.bytes); return ABCD_ERR_WORKSPACE; }
+    const int n_tiles = (pk.B + ROWS - 1) / ROWS;
+
+    // feature2hidden (model.py:169-170): hc0 = feat_in W^T + b
+    GemmArgs g = gemm_args_zero();
+    g.M = pk.B; g.N = hc; g.K = P.fin;
+    g.A = feat_in; g.lda = P.fin; g.a_kmajor = 1;
+    g.B = P.w_f2h; g.ldb = P.fin; g.b_kmajor = 1;
+    g.C = w.hc0; g.ldc = hc; g.bias = P.b_f2h;
+    TRY(sgemm_launch(g, stream));
+    split_hc0_kernel<<<(pk.B * H + 255) / 256, 256, 0, stream>>>(P.cell, pk.B, w.hc0, w.Hall, w.Call);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemsetAsync(w.Xall, 0, (size_t)(pk.B + pk.sumT) * Fp * sizeof(float), stream));
+
+    DecK k = make_k(P, pk, w);
+    k.eps = eps; k.ld_eps = ld_eps; k.gt = gt; k.ld_gt = ld_gt;
+    if (P.cell == 0) TRY(launch_cluster_dec(dec_fwd_kernel<0>, n_tiles, dec_fwd_smem(P.F), stream, k));
+    else TRY(launch_cluster_dec(dec_fwd_kernel<1>, n_tiles, dec_fwd_smem(P.F), stream, k));
+    if (gt && losses) {
+        final_sum_kernel<<<1, 256, 0, stream>>>(w.nll_partial, n_tiles * CL, losses + 0);
+        CUDA_TRY(cudaGetLastError());
+    }
+    // offset predictor over all frames (model.py:191)
+    g = gemm_args_zero();
+    g.M = pk.sumT; g.N = M; g.K = H;
+    g.A = w.Hall + (size_t)pk.B * H; g.lda = H; g.a_kmajor = 1;
+    g.B = P.off_w1; g.ldb = H; g.b_kmajor = 1;
+    g.C = w.HidOff; g.ldc = M; g.bias = P.off_b1; g.act = 1;
+    TRY(sgemm_launch(g, stream));
+    offset_head_kernel<<<BCE_BLOCKS, 256, 0, stream>>>(pk.sumT, w.HidOff, P.off_w2, P.off_b2, is_offset, w.OffLogit, w.bce_partial);
+    CUDA_TRY(cudaGetLastError());
+    if (is_offset && losses) {
+        final_sum_kernel<<<1, 256, 0, stream>>>(w.bce_partial, BCE_BLOCKS, losses + 1);
+        CUDA_TRY(cudaGetLastError());
+    }
+    const int cp_blocks = 592;
+    if (out_x) unpad_copy_kernel<<<cp_blocks, 256, 0, stream>>>(pk.sumT, P.F, Fp, w.Xall + (size_t)pk.B * Fp, out_x);
+    if (out_mean) unpad_copy_kernel<<<cp_blocks, 256, 0, stream>>>(pk.sumT, P.F, Fp, w.Mean, out_mean);
+    if (out_logvar) unpad_copy_kernel<<<cp_blocks, 256, 0, stream>>>(pk.sumT, P.F, Fp, w.Lv, out_logvar);
+    if (out_offset_logit) CUDA_TRY(cudaMemcpyAsync(out_offset_logit, w.OffLogit, (size_t)pk.sumT * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(cudaGetLastError());
+    return ABCD_OK;
+}
+
+int dec_backward(const DecParams& P, const DecGrads& G, const PackedMeta& pk, const float* feat_in, const float* eps,
+                 int ld_eps, const float* gt, int ld_gt, const float* is_offset, const float* g_losses,
+                 float* d_feat_in, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    TRY(check_dec(P));
+    ARG_CHECK(gt && is_offset && g_losses && eps, "decoder bwd: ground truth, offsets, noise and loss gradients are required");
+    const int H = ABCD_H, M = ABCD_M, F = P.F, Fp = pad4(P.F);
+    const int hc = P.cell == 0 ? 2 * H : H;
+    DecWs w = dec_carve(ws, ws_bytes, P.cell, P.F, P.fin, pk.B, pk.sumT);
+    if (w.bytes > ws_bytes) { abcd_set_error("decoder bwd: workspace too small"); return ABCD_ERR_WORKSPACE; }
+    const int n_tiles = (pk.B + ROWS - 1) / ROWS;
+    const int sumT = pk.sumT;
+    const float* Hfr = w.Hall + (size_t)pk.B * H;   // h of frame n
+
+    // ---- loss-head gradients over all frames ----
+    nll_grad_kernel<<<592, 256, 0, stream>>>(sumT, F, Fp, w.Mean, w.Lv, gt, ld_gt, g_losses, w.dML);
+    CUDA_TRY(cudaGetLastError());
+    offset_head_bwd_kernel<<<592, 256, 0, stream>>>(sumT, w.HidOff, P.off_w2, w.OffLogit, is_offset, g_losses, w.dLogit, w.dHidOffPre);
+    CUDA_TRY(cudaGetLastError());
+    GemmArgs g = gemm_args_zero();   // dHoff = dHidOffPre * off_w1
+    g.M = sumT; g.N = H; g.K = M;
+    g.A = w.dHidOffPre; g.lda = M; g.a_kmajor = 1;
+    g.B = P.off_w1; g.ldb = H; g.b_kmajor = 0;
+    g.C = w.dHoff; g.ldc = H;
+    TRY(sgemm_launch(g, stream));
+
+    // ---- BPTT ----
+    DecK k = make_k(P, pk, w);
+    k.eps = eps; k.ld_eps = ld_eps; k.gt = gt; k.ld_gt = ld_gt;
+    if (P.cell == 0) TRY(launch_cluster_dec(dec_bwd_kernel<0>, n_tiles, dec_bwd_smem(P.F), stream, k));
+    else TRY(launch_cluster_dec(dec_bwd_kernel<1>, n_tiles, dec_bwd_smem(P.F), stream, k));
+
+    // ---- weight gradients: reductions over all packed frames ----
+    dec_prev_index_kernel<<<min(pk.T_max, 592), 128, 0, stream>>>(pk.T_max, pk.B, pk.batch_sizes, pk.offsets, w.prev);
+    CUDA_TRY(cudaGetLastError());
+    auto tn = [&](int Mo, int No, const float* A, long lda, const float* Bm, long ldb, const int* gather, GateMap md,
+                  float* C, long ldc, int Kred) -> int {
+        GemmArgs q = gemm_args_zero();
+        q.M = Mo; q.N = No; q.K = Kred;
+        q.A = A; q.lda = lda; q.a_kmajor = 0;
+        q.B = Bm; q.ldb = ldb; q.b_kmajor = 0; q.b_kgather = gather;
+        q.m_dst = md; q.C = C; q.ldc = ldc; q.accumulate = 1;
+        q.splits = sgemm_pick_splits(Mo, No, Kred); q.partials = w.partials;
+        if ((size_t)q.splits * Mo * No > w.partial_floats) q.splits = 1;
+        return sgemm_launch(q, stream);
+    };
+    const GateMap map_ih = P.cell == 0 ? gate_map(H, 0, 1, 2, 3) : gate_map(H, 0, 1, 2, -1);
+    const GateMap map_hh = P.cell == 0 ? gate_map(H, 0, 1, 2, 3) : gate_map(H, 0, 1, -1, 2);
+    TRY(tn(4 * H, F, w.dG, 4 * H, w.Xall, Fp, w.prev, map_ih, G.w_ih, F, sumT));
+    TRY(tn(4 * H, H, w.dG, 4 * H, w.Hall, H, w.prev, map_hh, G.w_hh, H, sumT));
+    TRY(colsum_launch(w.dG, 4 * H, sumT, 4 * H, 1.f, G.b_ih, 1, map_ih, stream));
+    TRY(colsum_launch(w.dG, 4 * H, sumT, 4 * H, 1.f, G.b_hh, 1, map_hh, stream));
+    for (int i = 0; i < 2; ++i) {
+        TRY(tn(M, H, w.dHidPre + i * M, 2 * M, Hfr, H, nullptr, gate_map_none(), G.em_w1[i], H, sumT));
+        TRY(colsum_launch(w.dHidPre + i * M, 2 * M, sumT, M, 1.f, G.em_b1[i], 1, gate_map_none(), stream));
+        TRY(tn(F, M, w.dML + i * Fp, 2 * Fp, w.Hid + i * M, 2 * M, nullptr, gate_map_none(), G.em_w2[i], M, sumT));
+        TRY(colsum_launch(w.dML + i * Fp, 2 * Fp, sumT, F, 1.f, G.em_b2[i], 1, gate_map_none(), stream));
+    }
+    TRY(tn(M, H, w.dHidOffPre, M, Hfr, H, nullptr, gate_map_none(), G.off_w1, H, sumT));
+    TRY(colsum_launch(w.dHidOffPre, M, sumT, M, 1.f, G.off_b1, 1, gate_map_none(), stream));
+    TRY(tn(1, M, w.dLogit, 1, w.HidOff, M, nullptr, gate_map_none(), G.off_w2, M, sumT));
+    TRY(colsum_launch(w.dLogit, 1, sumT, 1, 1.f, G.off_b2, 1, gate_map_none(), stream));
+    // feature2hidden
+    TRY(tn(hc, P.fin, w.dHC0, hc, feat_in, P.fin, nullptr, gate_map_none(), G.w_f2h, P.fin, pk.B));
+    TRY(colsum_launch(w.dHC0, hc, pk.B, hc, 1.f, G.b_f2h, 1, gate_map_none(), stream));
+    if (d_feat_in) {
+        g = gemm_args_zero();
+        g.M = pk.B; g.N = P.fin; g.K = hc;
+        g.A = w.dHC0; g.lda = hc; g.a_kmajor = 1;
+        g.B = P.w_f2h; g.ldb = P.fin; g.b_kmajor = 0;
+        g.C = d_feat_in; g.ldc = P.fin;
+        TRY(sgemm_launch(g, stream));
+    }
+    return ABCD_OK;
+}

@@ -1,0 +1,475 @@
+// Encoder recurrence: bidirectional single-layer LSTM/GRU over packed variable-length segments, returning
+// only the final states, i.e. RNN_Variational_Encoder.forward (ABCD-VAE/modules/model.py:60-66) and its
+// backward.  Gate order follows torch.nn.LSTM (i,f,g,o) / torch.nn.GRU (r,z,n) (model.py:53).
+//
+// Forward = hoisted input projection (sgemm NT over all packed frames, gates stored unit-major interleaved)
+//         + one persistent cluster kernel per launch that runs both directions concurrently.
+// Backward = persistent BPTT kernel producing pre-activation gate gradients for every frame
+//         + weight/bias gradients as large TN GEMMs over all frames.
+#include "rnn_common.cuh"
+#include "sgemm.cuh"
+#include "enc.cuh"
+
+using namespace rnn;
+
+namespace {
+
+constexpr int ENC_KC = 128;
+constexpr int ENC_LDA = ENC_KC + 4;
+
+// -------------------------------------------------------------------------------------------------
+// small helper kernels
+// -------------------------------------------------------------------------------------------------
+// Combined projection bias: LSTM b_ih+b_hh (4H); GRU [b_ir+b_hr, b_iz+b_hz, b_in] (3H) -- b_hn stays inside
+// the r*(W_hn h + b_hn) term.
+__global__ void combine_bias_kernel(int cell, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                    float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = (cell == 0 ? 4 : 3) * ABCD_H;
+    if (i >= n) return;
+    float v = b_ih[i];
+    if (cell == 0 || i < 2 * ABCD_H) v += b_hh[i];
+    out[i] = v;
+}
+
+// prev_fwd[n]: packed index of the same sequence at t-1 (or -1); prev_bwd[n]: at t+1 (or -1)
+__global__ void prev_index_kernel(int T_max, const int* __restrict__ batch_sizes, const int* __restrict__ offsets,
+                                  int* __restrict__ prev_fwd, int* __restrict__ prev_bwd) {
+    for (int t = blockIdx.x; t < T_max; t += gridDim.x) {
+        int bs = batch_sizes[t], off = offsets[t];
+        int bs_next = (t + 1 < T_max) ? batch_sizes[t + 1] : 0;
+        for (int b = threadIdx.x; b < bs; b += blockDim.x) {
+            prev_fwd[off + b] = t > 0 ? offsets[t - 1] + b : -1;
+            prev_bwd[off + b] = b < bs_next ? offsets[t + 1] + b : -1;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// forward
+// -------------------------------------------------------------------------------------------------
+struct EncFwdK {
+    int n_tiles, B, ndirs, save, out_ld;
+    const int* batch_sizes; const int* offsets; const int* lengths;
+    const float* w_hh[2];
+    const float* b_hh[2];
+    const float* xproj[2];   // [sumT][4H] interleaved
+    float* hs[2];            // save: [sumT][H]; else ping-pong [2][B][H]
+    float* gs[2];            // save: [sumT][4H] interleaved activations
+    float* cs[2];            // save (LSTM): [sumT][H]
+    float* out;              // [B][out_ld]
+};
+
+template <int CELL>
+__global__ void __launch_bounds__(NTHREADS, 1) enc_fwd_kernel(EncFwdK p) {
+    extern __shared__ __align__(16) float smem[];
+    float* Wsm = smem;                          // [H][U*4]
+    float* stage0 = Wsm + ABCD_H * (U * 4);
+    float* stage1 = stage0 + ROWS * ENC_LDA;
+    const Stage st{stage0, stage1, ENC_LDA, ENC_KC};
+
+    const int tid = threadIdx.x;
+    const int rank = (int)cluster_ctarank();
+    const int cid = blockIdx.x / CL;
+    const int tile = cid % p.n_tiles, dir = cid / p.n_tiles;
+    const int u0 = rank * U;
+    const int H = ABCD_H;
+
+    // resident recurrent weights: Wsm[k][u*4+slot] = W_hh[gate(slot)*H + u0+u][k]
+    {
+        const float* W = p.w_hh[dir];
+        for (int idx = tid; idx < U * 4 * (H / 4); idx += NTHREADS) {
+            int kq = idx % (H / 4), col = idx / (H / 4);
+            int u = col >> 2, s = col & 3;
+            int gate = CELL == 0 ? s : (s == 0 ? 0 : s == 1 ? 1 : s == 3 ? 2 : -1);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gate >= 0) v = *reinterpret_cast<const float4*>(W + (long)(gate * H + u0 + u) * H + kq * 4);
+            Wsm[(kq * 4 + 0) * (U * 4) + col] = v.x;
+            Wsm[(kq * 4 + 1) * (U * 4) + col] = v.y;
+            Wsm[(kq * 4 + 2) * (U * 4) + col] = v.z;
+            Wsm[(kq * 4 + 3) * (U * 4) + col] = v.w;
+        }
+    }
+    const ThreadMap tm = make_map(tid, U, 1);   // cg == unit, ks == 0 for all 256 threads
+    const int unit = u0 + tm.cg;
+    const float bhn = CELL == 1 ? p.b_hh[dir][2 * H + unit] : 0.f;
+
+    int len[RT];
+    float creg[RT], hreg[RT];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+        int b = tile + p.n_tiles * (tm.rg + i * RG);
+        len[i] = b < p.B ? p.lengths[b] : 0;
+        creg[i] = 0.f; hreg[i] = 0.f;
+    }
+    const int Tt = p.lengths[tile];
+    const float* xp_base = p.xproj[dir];
+    float* hs = p.hs[dir];
+    __syncthreads();
+
+    for (int s = 0; s < Tt; ++s) {
+        const int t = dir == 0 ? s : Tt - 1 - s;
+        const int na = active_rows(p.batch_sizes[t], tile, p.n_tiles);
+        const int off_t = p.offsets[t];
+        // rows that already carry state from the previous step of this direction
+        int na_prev, off_prev;
+        if (dir == 0) { na_prev = s > 0 ? na : 0; off_prev = s > 0 ? p.offsets[t - 1] : 0; }
+        else { na_prev = s > 0 ? active_rows(p.batch_sizes[t + 1], tile, p.n_tiles) : 0; off_prev = s > 0 ? p.offsets[t + 1] : 0; }
+
+        // projected inputs for this thread's rows (issued early; consumed after the GEMM)
+        float4 xp[RT];
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            int r = tm.rg + i * RG;
+            xp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < na) {
+                long frame = off_t + tile + p.n_tiles * r;
+                xp[i] = __ldg(reinterpret_cast<const float4*>(xp_base + frame * (4 * H) + unit * 4));
+            }
+        }
+        float acc[RT][4];
+        zero_acc(acc);
+        if (na_prev > 0) {
+            const int n_tiles = p.n_tiles, B = p.B, save = p.save;
+            auto rp = [=](int r) -> const float* {
+                if (r >= na_prev) return nullptr;
+                long b = tile + n_tiles * r;
+                long row = save ? (long)off_prev + b : (long)((s - 1) & 1) * B + b;
+                return hs + row * ABCD_H;
+            };
+            phase_gemm(acc, st, H, rp, 0, NullRow(), na, Wsm, U * 4, tm, 1, tid);
+        }
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            int r = tm.rg + i * RG;
+            if (r >= na) continue;
+            long b = tile + p.n_tiles * r;
+            long frame = off_t + b;
+            float h;
+            if (CELL == 0) {
+                float ig = sigmoid_acc(acc[i][0] + xp[i].x);
+                float fg = sigmoid_acc(acc[i][1] + xp[i].y);
+                float gg = tanhf(acc[i][2] + xp[i].z);
+                float og = sigmoid_acc(acc[i][3] + xp[i].w);
+                float c = fg * creg[i] + ig * gg;
+                h = og * tanhf(c);
+                creg[i] = c;
+                if (p.save) {
+                    *reinterpret_cast<float4*>(p.gs[dir] + frame * (4 * H) + unit * 4) = make_float4(ig, fg, gg, og);
+                    p.cs[dir][frame * H + unit] = c;
+                }
+            } else {
+                float rg_ = sigmoid_acc(acc[i][0] + xp[i].x);
+                float zg = sigmoid_acc(acc[i][1] + xp[i].y);
+                float hn = acc[i][3] + bhn;
+                float ng = tanhf(xp[i].z + rg_ * hn);
+                h = (1.f - zg) * ng + zg * hreg[i];
+                if (p.save)
+                    *reinterpret_cast<float4*>(p.gs[dir] + frame * (4 * H) + unit * 4) = make_float4(rg_, zg, ng, hn);
+            }
+            hreg[i] = h;
+            long row = p.save ? frame : (long)(s & 1) * p.B + b;
+            hs[row * H + unit] = h;
+            const bool last = dir == 0 ? (t == len[i] - 1) : (t == 0);
+            if (last) {
+                float* o = p.out + b * p.out_ld;
+                if (CELL == 0) { o[dir * 2 * H + unit] = h; o[dir * 2 * H + H + unit] = creg[i]; }
+                else o[dir * H + unit] = h;
+            }
+        }
+        cluster_sync_all();
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// backward (BPTT): produces dG[dir][frame][u*4+slot] (pre-activation gate gradients)
+// -------------------------------------------------------------------------------------------------
+struct EncBwdK {
+    int n_tiles, B, ndirs, out_ld;
+    const int* batch_sizes; const int* offsets; const int* lengths;
+    const float* w_hh[2];
+    const float* hs[2]; const float* gs[2]; const float* cs[2];
+    const float* d_out;   // [B][out_ld]
+    float* dg[2];         // [sumT][4H]
+};
+
+template <int CELL>
+__global__ void __launch_bounds__(NTHREADS, 1) enc_bwd_kernel(EncBwdK p) {
+    extern __shared__ __align__(16) float smem[];
+    const int H = ABCD_H;
+    float* Wsm = smem;                       // [4H][U]: Wsm[uu*4+slot][j] = W_hh[gate(slot)*H+uu][u0+j]
+    float* dh_sm = Wsm + 4 * H * U;          // [ROWS][U] recurrent dh carried to the next (earlier) step
+    float* dc_sm = dh_sm + ROWS * U;         // [ROWS][U] LSTM: dc carry; GRU: direct dh*z carry
+    float* stage0 = dc_sm + ROWS * U;
+    float* stage1 = stage0 + ROWS * ENC_LDA;
+    const Stage st{stage0, stage1, ENC_LDA, ENC_KC};
+
+    const int tid = threadIdx.x;
+    const int rank = (int)cluster_ctarank();
+    const int cid = blockIdx.x / CL;
+    const int tile = cid % p.n_tiles, dir = cid / p.n_tiles;
+    const int u0 = rank * U;
+    {
+        const float* W = p.w_hh[dir];
+        for (int idx = tid; idx < 4 * H * (U / 4); idx += NTHREADS) {
+            int jq = idx % (U / 4), kphys = idx / (U / 4);
+            int uu = kphys >> 2, s = kphys & 3;
+            int gate = CELL == 0 ? s : (s == 0 ? 0 : s == 1 ? 1 : s == 3 ? 2 : -1);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gate >= 0) v = *reinterpret_cast<const float4*>(W + (long)(gate * H + uu) * H + u0 + jq * 4);
+            *reinterpret_cast<float4*>(Wsm + kphys * U + jq * 4) = v;
+        }
+        for (int idx = tid; idx < ROWS * U; idx += NTHREADS) { dh_sm[idx] = 0.f; dc_sm[idx] = 0.f; }
+    }
+    // pointwise mapping: thread -> (unit pu, rows prg + i*RG)
+    const int pu = tid % U, prg = tid / U;
+    const int unit = u0 + pu;
+    int len[RT];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+        int b = tile + p.n_tiles * (prg + i * RG);
+        len[i] = b < p.B ? p.lengths[b] : 0;
+    }
+    const ThreadMap tm = make_map(tid, U / 4, pick_ks(U / 4));
+    const int KS = pick_ks(U / 4);
+    const int Tt = p.lengths[tile];
+    const float* gs = p.gs[dir];
+    const float* cs = p.cs[dir];
+    const float* hs = p.hs[dir];
+    float* dg = p.dg[dir];
+    __syncthreads();
+
+    for (int s = 0; s < Tt; ++s) {
+        // walk the forward recurrence of this direction backwards
+        const int t = dir == 0 ? Tt - 1 - s : s;
+        const int na = active_rows(p.batch_sizes[t], tile, p.n_tiles);
+        const int off_t = p.offsets[t];
+        // "previous" frame in the forward recurrence of this direction (source of h_prev / c_prev)
+        int na_src, off_src;
+        if (dir == 0) { na_src = t > 0 ? na : 0; off_src = t > 0 ? p.offsets[t - 1] : 0; }
+        else { na_src = (t + 1 < Tt) ? active_rows(p.batch_sizes[t + 1], tile, p.n_tiles) : 0; off_src = (t + 1 < Tt) ? p.offsets[t + 1] : 0; }
+
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            int r = prg + i * RG;
+            if (r >= na) continue;
+            long b = tile + p.n_tiles * r;
+            long frame = off_t + b;
+            const bool is_final = dir == 0 ? (t == len[i] - 1) : (t == 0);
+            float dh = dh_sm[r * U + pu];
+            float carry = dc_sm[r * U + pu];
+            const float* dout = p.d_out + b * p.out_ld;
+            const float4 g4 = *reinterpret_cast<const float4*>(gs + frame * (4 * H) + unit * 4);
+            float4 dgv;
+            if (CELL == 0) {
+                float dc = carry;
+                if (is_final) { dh += dout[dir * 2 * H + unit]; dc += dout[dir * 2 * H + H + unit]; }
+                float c = cs[frame * H + unit];
+                float c_prev = r < na_src ? cs[((long)off_src + b) * H + unit] : 0.f;
+                float tc = tanhf(c);
+                float ig = g4.x, fg = g4.y, gg = g4.z, og = g4.w;
+                dc += dh * og * (1.f - tc * tc);
+                dgv.x = dc * gg * ig * (1.f - ig);
+                dgv.y = dc * c_prev * fg * (1.f - fg);
+                dgv.z = dc * ig * (1.f - gg * gg);
+                dgv.w = dh * tc * og * (1.f - og);
+                dc_sm[r * U + pu] = dc * fg;
+            } else {
+                dh += carry;
+                if (is_final) dh += dout[dir * H + unit];
+                float h_prev = r < na_src ? hs[((long)off_src + b) * H + unit] : 0.f;
+                float rg_ = g4.x, zg = g4.y, ng = g4.z, hn = g4.w;
+                float dn_pre = dh * (1.f - zg) * (1.f - ng * ng);
+                dgv.x = dn_pre * hn * rg_ * (1.f - rg_);
+                dgv.y = dh * (h_prev - ng) * zg * (1.f - zg);
+                dgv.z = dn_pre;
+                dgv.w = dn_pre * rg_;
+                dc_sm[r * U + pu] = dh * zg;
+            }
+            *reinterpret_cast<float4*>(dg + frame * (4 * H) + unit * 4) = dgv;
+        }
+        cluster_sync_all();
+        // dh_prev[rows, my units] = dG[rows, 4H] * W_hh[4H, my units]; only rows that have a previous frame
+        if (na_src > 0) {
+            float acc[RT][4];
+            zero_acc(acc);
+            const int n_tiles = p.n_tiles;
+            auto rp = [=](int r) -> const float* { return dg + ((long)off_t + tile + (long)n_tiles * r) * (4 * ABCD_H); };
+            phase_gemm(acc, st, 4 * H, rp, 0, NullRow(), na_src, Wsm, U, tm, KS, tid);
+            if (tm.active && tm.ks == 0) {
+#pragma unroll
+                for (int i = 0; i < RT; ++i) {
+                    int r = tm.rg + i * RG;
+                    if (r < na_src)
+                        *reinterpret_cast<float4*>(dh_sm + r * U + tm.cg * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+size_t enc_fwd_smem() { return (size_t)(ABCD_H * U * 4 + 2 * ROWS * ENC_LDA) * sizeof(float); }
+size_t enc_bwd_smem() { return (size_t)(4 * ABCD_H * U + 2 * ROWS * U + 2 * ROWS * ENC_LDA) * sizeof(float); }
+
+template <class K, class P>
+int launch_cluster(K kernel, int n_clusters, size_t smem, cudaStream_t stream, const P& params) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(n_clusters * CL);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, params));
+    return ABCD_OK;
+}
+
+}  // namespace
+
+int rnn_prepare_kernel(const void* fn, size_t smem) {
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    return ABCD_OK;
+}
+
+int enc_init() {
+    TRY(rnn_prepare_kernel((const void*)enc_fwd_kernel<0>, enc_fwd_smem()));
+    TRY(rnn_prepare_kernel((const void*)enc_fwd_kernel<1>, enc_fwd_smem()));
+    TRY(rnn_prepare_kernel((const void*)enc_bwd_kernel<0>, enc_bwd_smem()));
+    TRY(rnn_prepare_kernel((const void*)enc_bwd_kernel<1>, enc_bwd_smem()));
+    return ABCD_OK;
+}
+
+// ---- workspace layout --------------------------------------------------------------------------
+struct EncWs {
+    float* bias_comb[2];
+    float* xproj[2];
+    float* hs[2];
+    float* gs[2];
+    float* cs[2];
+    float* dg[2];
+    int* prev_fwd;
+    int* prev_bwd;
+    float* partials;
+    size_t partial_floats;
+    size_t bytes;
+};
+
+static EncWs enc_carve(void* base, size_t cap, int cell, int F, int B, int sumT, int ndirs, int save) {
+    Arena a(base, cap);
+    EncWs w;
+    memset(&w, 0, sizeof(w));
+    const int H = ABCD_H;
+    for (int d = 0; d < ndirs; ++d) {
+        w.bias_comb[d] = a.take<float>(4 * H);
+        w.xproj[d] = a.take<float>((size_t)sumT * 4 * H);
+        w.hs[d] = a.take<float>(save ? (size_t)sumT * H : (size_t)2 * B * H);
+        if (save) {
+            w.gs[d] = a.take<float>((size_t)sumT * 4 * H);
+            if (cell == 0) w.cs[d] = a.take<float>((size_t)sumT * H);
+        }
+    }
+    if (save) {
+        // dG aliases xproj (dead after the forward recurrence) -- both [sumT][4H] per direction
+        for (int d = 0; d < ndirs; ++d) w.dg[d] = w.xproj[d];
+        w.prev_fwd = a.take<int>(sumT);
+        w.prev_bwd = a.take<int>(sumT);
+        int s1 = sgemm_pick_splits(4 * H, H, sumT), s2 = sgemm_pick_splits(4 * H, F, sumT);
+        w.partial_floats = (size_t)4 * H * ((size_t)s1 * H > (size_t)s2 * F ? (size_t)s1 * H : (size_t)s2 * F);
+        w.partials = a.take<float>(w.partial_floats);
+    }
+    w.bytes = a.off;
+    return w;
+}
+
+size_t enc_workspace_bytes(int cell, int F, int B, int sumT, int bidir, int save) {
+    return enc_carve(nullptr, 0, cell, F, B, sumT, bidir ? 2 : 1, save).bytes;
+}
+
+int enc_forward(const EncParams& P, const PackedMeta& pk, const float* x, int ldx, float* last_hidden,
+                int save, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    ARG_CHECK(P.H == ABCD_H, "encoder: rnn_hidden_size %d unsupported (kernels are specialised for %d)", P.H, ABCD_H);
+    ARG_CHECK(P.cell == 0 || P.cell == 1, "encoder: rnn_type must be LSTM or GRU");
+    ARG_CHECK(pk.B > 0 && pk.T_max > 0 && pk.sumT > 0, "encoder: empty packed batch");
+    const int ndirs = P.bidir ? 2 : 1;
+    const int H = ABCD_H;
+    EncWs w = enc_carve(ws, ws_bytes, P.cell, P.F, pk.B, pk.sumT, ndirs, save);
+    if (w.bytes > ws_bytes) { abcd_set_error("encoder: workspace too small (%zu < %zu)", ws_bytes, w.bytes); return ABCD_ERR_WORKSPACE; }
+    const int n_tiles = (pk.B + ROWS - 1) / ROWS;
+    const int ngates = P.cell == 0 ? 4 : 3;
+
+    EncFwdK k;
+    memset(&k, 0, sizeof(k));
+    k.n_tiles = n_tiles; k.B = pk.B; k.ndirs = ndirs; k.save = save;
+    k.out_ld = ndirs * H * (P.cell == 0 ? 2 : 1);
+    k.batch_sizes = pk.batch_sizes; k.offsets = pk.offsets; k.lengths = pk.lengths;
+    k.out = last_hidden;
+    for (int d = 0; d < ndirs; ++d) {
+        combine_bias_kernel<<<(4 * H + 255) / 256, 256, 0, stream>>>(P.cell, P.b_ih[d], P.b_hh[d], w.bias_comb[d]);
+        CUDA_TRY(cudaGetLastError());
+        GemmArgs g = gemm_args_zero();
+        g.M = pk.sumT; g.N = 4 * H; g.K = P.F;
+        g.A = x; g.lda = ldx; g.a_kmajor = 1;
+        g.B = P.w_ih[d]; g.ldb = P.F; g.b_kmajor = 1;
+        g.b_nsrc = P.cell == 0 ? gate_map(H, 0, 1, 2, 3) : gate_map(H, 0, 1, 2, -1);
+        g.C = w.xproj[d]; g.ldc = 4 * H;
+        g.bias = w.bias_comb[d];
+        TRY(sgemm_launch(g, stream));
+        k.w_hh[d] = P.w_hh[d]; k.b_hh[d] = P.b_hh[d];
+        k.xproj[d] = w.xproj[d]; k.hs[d] = w.hs[d]; k.gs[d] = w.gs[d]; k.cs[d] = w.cs[d];
+    }
+    (void)ngates;
+    if (P.cell == 0) TRY(launch_cluster(enc_fwd_kernel<0>, n_tiles * ndirs, enc_fwd_smem(), stream, k));
+    else TRY(launch_cluster(enc_fwd_kernel<1>, n_tiles * ndirs, enc_fwd_smem(), stream, k));
+    return ABCD_OK;
+}
+
+int enc_backward(const EncParams& P, const EncGrads& G, const PackedMeta& pk, const float* x, int ldx,
+                 const float* d_last_hidden, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    ARG_CHECK(P.H == ABCD_H, "encoder: rnn_hidden_size %d unsupported", P.H);
+    const int ndirs = P.bidir ? 2 : 1;
+    const int H = ABCD_H;
+    EncWs w = enc_carve(ws, ws_bytes, P.cell, P.F, pk.B, pk.sumT, ndirs, 1);
+    if (w.bytes > ws_bytes) { abcd_set_error("encoder bwd: workspace too small"); return ABCD_ERR_WORKSPACE; }
+    const int n_tiles = (pk.B + ROWS - 1) / ROWS;
+
+    EncBwdK k;
+    memset(&k, 0, sizeof(k));
+    k.n_tiles = n_tiles; k.B = pk.B; k.ndirs = ndirs;
+    k.out_ld = ndirs * H * (P.cell == 0 ? 2 : 1);
+    k.batch_sizes = pk.batch_sizes; k.offsets = pk.offsets; k.lengths = pk.lengths;
+    k.d_out = d_last_hidden;
+    for (int d = 0; d < ndirs; ++d) {
+        k.w_hh[d] = P.w_hh[d]; k.hs[d] = w.hs[d]; k.gs[d] = w.gs[d]; k.cs[d] = w.cs[d]; k.dg[d] = w.dg[d];
+    }
+    if (P.cell == 0) TRY(launch_cluster(enc_bwd_kernel<0>, n_tiles * ndirs, enc_bwd_smem(), stream, k));
+    else TRY(launch_cluster(enc_bwd_kernel<1>, n_tiles * ndirs, enc_bwd_smem(), stream, k));
+
+    prev_index_kernel<<<min(pk.T_max, 592), 128, 0, stream>>>(pk.T_max, pk.batch_sizes, pk.offsets, w.prev_fwd, w.prev_bwd);
+    CUDA_TRY(cudaGetLastError());
+    for (int d = 0; d < ndirs; ++d) {
+        const GateMap map_ih = P.cell == 0 ? gate_map(H, 0, 1, 2, 3) : gate_map(H, 0, 1, 2, -1);
+        const GateMap map_hh = P.cell == 0 ? gate_map(H, 0, 1, 2, 3) : gate_map(H, 0, 1, -1, 2);
+        // dW_hh[gate rows][H] += dG^T * H_prev
+        GemmArgs g = gemm_args_zero();
+        g.M = 4 * H; g.N = H; g.K = pk.sumT;
+        g.A = w.dg[d]; g.lda = 4 * H; g.a_kmajor = 0;
+        g.B = w.hs[d]; g.ldb = H; g.b_kmajor = 0; g.b_kgather = d == 0 ? w.prev_fwd : w.prev_bwd;
+        g.m_dst = map_hh;
+        g.C = G.w_hh[d]; g.ldc = H; g.accumulate = 1;
+        g.splits = sgemm_pick_splits(g.M, g.N, g.K); g.partials = w.partials;
+        TRY(sgemm_launch(g, stream));
+        // dW_ih += dG^T * X
+        g.N = P.F; g.B = x; g.ldb = ldx; g.b_kgather = nullptr;
+        g.m_dst = map_ih; g.C = G.w_ih[d]; g.ldc = P.F;
+        g.splits = sgemm_pick_splits(g.M, g.N, g.K);
+        TRY(sgemm_launch(g, stream));
+        TRY(colsum_launch(w.dg[d], 4 * H, pk.sumT, 4 * H, 1.f, G.b_ih[d], 1, map_ih, stream));
+        TRY(colsum_launch(w.dg[d], 4 * H, pk.sumT, 4 * H, 1.f, G.b_hh[d], 1, map_hh, stream));
+    }
+    return ABCD_OK;
+}

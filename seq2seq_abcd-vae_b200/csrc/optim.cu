@@ -1,0 +1,145 @@
+// Fused global-norm gradient clipping + SGD step over one flat parameter/gradient arena, and Philox noise.
+//   torch.nn.utils.clip_grad_norm_(params, max_norm)  (ABCD-VAE/learning.py:161)
+//        total = ||g||_2 over ALL parameters; g *= min(1, max_norm / (total + 1e-6))
+//   torch.optim.SGD(lr, momentum).step()               (ABCD-VAE/learning.py:163,256)
+//        buf = momentum*buf + g ; p -= lr*buf   (buf starts at zero, dampening 0, no nesterov/weight decay)
+// Two launches: (1) per-CTA partial sums of squares, (2) every CTA re-reduces the few hundred partials in a
+// fixed order (deterministic, no atomics), derives the clip coefficient and applies the step.  Algorithmic
+// traffic 16 B/parameter (4 read for the norm, 8 read + 4 written for the step), +8 with momentum.
+#include "common.cuh"
+#include "stft.cuh"
+
+namespace {
+
+constexpr int OPT_BLOCKS = 592;   // 4 CTAs per SM
+constexpr int OPT_THREADS = 256;
+
+__global__ void __launch_bounds__(OPT_THREADS) sumsq_kernel(const float* __restrict__ g, long n, float* __restrict__ partial) {
+    __shared__ double red[40];
+    double s = 0.0;
+    const long n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float a = 0.f;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 v = g4[i];
+        a += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    s = (double)a;
+    if (blockIdx.x == 0)
+        for (long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) s += (double)g[i] * (double)g[i];
+    s = block_sum_d(s, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = (float)s;
+}
+
+__global__ void __launch_bounds__(OPT_THREADS) clip_sgd_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                               float* __restrict__ mbuf, long n, float lr, float momentum,
+                                                               float max_norm, int zero_grads,
+                                                               const float* __restrict__ partial, int n_partial,
+                                                               float* __restrict__ norm_out) {
+    __shared__ double red[40];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n_partial; i += blockDim.x) s += (double)partial[i];
+    s = block_sum_d(s, red);
+    const float total = (float)sqrt(s);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && norm_out) *norm_out = total;
+    float coef = max_norm / (total + 1e-6f);
+    coef = coef < 1.f ? coef : 1.f;
+    if (max_norm <= 0.f) coef = 1.f;
+    const long n4 = n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    float4* g4 = reinterpret_cast<float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(mbuf);
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 gv = g4[i], pv = p4[i];
+        gv.x *= coef; gv.y *= coef; gv.z *= coef; gv.w *= coef;
+        float4 st = gv;
+        if (mbuf) {
+            float4 mv = m4[i];
+            mv.x = momentum * mv.x + gv.x; mv.y = momentum * mv.y + gv.y;
+            mv.z = momentum * mv.z + gv.z; mv.w = momentum * mv.w + gv.w;
+            m4[i] = mv; st = mv;
+        }
+        pv.x -= lr * st.x; pv.y -= lr * st.y; pv.z -= lr * st.z; pv.w -= lr * st.w;
+        p4[i] = pv;
+        g4[i] = zero_grads ? make_float4(0.f, 0.f, 0.f, 0.f) : gv;
+    }
+    if (blockIdx.x == 0)
+        for (long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+            float gv = g[i] * coef, st = gv;
+            if (mbuf) { float mv = momentum * mbuf[i] + gv; mbuf[i] = mv; st = mv; }
+            p[i] -= lr * st;
+            g[i] = zero_grads ? 0.f : gv;
+        }
+}
+
+// ---- Philox4x32-10 counter-based generator -------------------------------------------------------
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+}
+__device__ __forceinline__ void philox4(uint64_t seed, uint64_t ctr, uint32_t (&out)[4]) {
+    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+    uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(c, k);
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0,1)
+
+// kind 0: standard normal (Box-Muller); kind 1: standard Gumbel  -log(-log U)  (= -log of an Exp(1) draw,
+// torch.nn.functional.gumbel_softmax's noise, model.py:604)
+__global__ void philox_kernel(float* __restrict__ out, long n, uint64_t seed, uint64_t offset, int kind) {
+    const long n4 = (n + 3) >> 2;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        uint32_t r[4];
+        philox4(seed, offset + (uint64_t)i, r);
+        float v[4];
+        if (kind == 0) {
+            float u0 = u01(r[0]), u1 = u01(r[1]), u2 = u01(r[2]), u3 = u01(r[3]);
+            float m0 = sqrtf(-2.f * logf(u0)), m1 = sqrtf(-2.f * logf(u2));
+            float s0, c0, s1, c1;
+            sincospif(2.f * u1, &s0, &c0);
+            sincospif(2.f * u3, &s1, &c1);
+            v[0] = m0 * c0; v[1] = m0 * s0; v[2] = m1 * c1; v[3] = m1 * s1;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = -logf(-logf(u01(r[j])));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i * 4 + j < n) out[i * 4 + j] = v[j];
+    }
+}
+
+}  // namespace
+
+int optim_partial_count() { return OPT_BLOCKS; }
+
+int gradnorm_clip_sgd(float* params, float* grads, float* momentum_buf, long n, float lr, float momentum,
+                      float max_norm, int zero_grads, float* norm_out, float* partial, int n_partial,
+                      cudaStream_t stream) {
+    ARG_CHECK(params && grads && partial && n_partial >= OPT_BLOCKS, "gradnorm_clip_sgd: bad arguments");
+    ARG_CHECK(((uintptr_t)params % 16 == 0) && ((uintptr_t)grads % 16 == 0) && (!momentum_buf || (uintptr_t)momentum_buf % 16 == 0),
+              "gradnorm_clip_sgd: arenas must be 16-byte aligned");
+    if (n <= 0) return ABCD_OK;
+    sumsq_kernel<<<OPT_BLOCKS, OPT_THREADS, 0, stream>>>(grads, n, partial);
+    CUDA_TRY(cudaGetLastError());
+    clip_sgd_kernel<<<OPT_BLOCKS, OPT_THREADS, 0, stream>>>(params, grads, momentum_buf, n, lr, momentum, max_norm,
+                                                          zero_grads, partial, OPT_BLOCKS, norm_out);
+    CUDA_TRY(cudaGetLastError());
+    return ABCD_OK;
+}
+
+int philox_fill(float* out, long n, unsigned long long seed, unsigned long long offset, int kind, cudaStream_t stream) {
+    if (n <= 0) return ABCD_OK;
+    long n4 = (n + 3) >> 2;
+    int blocks = (int)((n4 + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    philox_kernel<<<blocks, 256, 0, stream>>>(out, n, (uint64_t)seed, (uint64_t)offset, kind);
+    CUDA_TRY(cudaGetLastError());
+    return ABCD_OK;
+}

@@ -1,0 +1,324 @@
+// fp32 FFMA GEMM for sm_100a: C[M,N] = alpha * A[M,K] * B[K,N] (+bias)(tanh), register-tiled with
+// double-buffered shared-memory staging.  Three operand layouts cover the whole path:
+//   NT  (A k-major, B k-major)  y = x W^T           hoisted input projection, MLP forward
+//   NN  (A k-major, B n-major)  dx = dy W           data gradients outside the time loop
+//   TN  (A m-major, B n-major)  dW = dy^T x         weight gradients, reduction over packed frames
+// The TN form takes an optional row-gather on the reduction index (frame -> previous frame of the same
+// sequence) and split-K with a deterministic second-pass reduce.  Gate maps let the recurrent kernels keep
+// their unit-major interleaved gate order while parameters/gradients stay in PyTorch's gate-major order
+// (reference layouts: torch.nn.LSTM/GRU weight_ih_l0 [4H|3H, F], ABCD-VAE/modules/model.py:53).
+#include "sgemm.cuh"
+
+namespace {
+
+constexpr int BK = 16;
+
+__device__ __forceinline__ int gate_src_row(const GateMap& gm, int phys) {
+    // physical interleaved index u*4+slot -> standard row gate*H+u (or -1)
+    if (!gm.enabled) return phys;
+    int u = phys >> 2, s = phys & 3;
+    int g = gm.gate_of_slot[s];
+    return g < 0 ? -1 : g * gm.H + u;
+}
+
+template <int BM, int BN, int TM, int TN, bool A_KM, bool B_KM>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+sgemm_kernel(GemmArgs g, int a_vec, int b_vec) {
+    constexpr int NT = (BM / TM) * (BN / TN);
+    constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
+    __shared__ __align__(16) float As[2][BK][LDA_S];
+    __shared__ __align__(16) float Bs[2][BK][LDB_S];
+
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    // split-K range (multiples of BK)
+    const int ksplit = gridDim.z;
+    const int ktiles_total = (g.K + BK - 1) / BK;
+    const int ktiles_per = (ktiles_total + ksplit - 1) / ksplit;
+    const int kt_begin = blockIdx.z * ktiles_per;
+    const int kt_end = min(ktiles_total, kt_begin + ktiles_per);
+
+    constexpr int A_LD = BM * BK / 4 / NT;   // float4 loads per thread per tile
+    constexpr int B_LD = BN * BK / 4 / NT;
+    static_assert(A_LD >= 1 && B_LD >= 1, "tile too small for thread count");
+    float4 ra[A_LD], rb[B_LD];
+
+    auto load_a = [&](int kt) {
+        const int k0 = kt * BK;
+#pragma unroll
+        for (int i = 0; i < A_LD; ++i) {
+            int idx = tid + i * NT;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (A_KM) {
+                int kq = idx % (BK / 4), m = idx / (BK / 4);
+                int gm = m0 + m, gk = k0 + kq * 4;
+                if (gm < g.M) {
+                    const float* src = g.A + (long)gm * g.lda + gk;
+                    if (a_vec && gk + 3 < g.K) v = *reinterpret_cast<const float4*>(src);
+                    else {
+                        if (gk + 0 < g.K) v.x = src[0];
+                        if (gk + 1 < g.K) v.y = src[1];
+                        if (gk + 2 < g.K) v.z = src[2];
+                        if (gk + 3 < g.K) v.w = src[3];
+                    }
+                }
+            } else {
+                int mq = idx % (BM / 4), k = idx / (BM / 4);
+                int gm = m0 + mq * 4, gk = k0 + k;
+                if (gk < g.K) {
+                    const float* src = g.A + (long)gk * g.lda + gm;
+                    if (a_vec && gm + 3 < g.M) v = *reinterpret_cast<const float4*>(src);
+                    else {
+                        if (gm + 0 < g.M) v.x = src[0];
+                        if (gm + 1 < g.M) v.y = src[1];
+                        if (gm + 2 < g.M) v.z = src[2];
+                        if (gm + 3 < g.M) v.w = src[3];
+                    }
+                }
+            }
+            ra[i] = v;
+        }
+    };
+    auto load_b = [&](int kt) {
+        const int k0 = kt * BK;
+#pragma unroll
+        for (int i = 0; i < B_LD; ++i) {
+            int idx = tid + i * NT;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (B_KM) {
+                int kq = idx % (BK / 4), n = idx / (BK / 4);
+                int gn = n0 + n, gk = k0 + kq * 4;
+                if (gn < g.N) {
+                    int row = gate_src_row(g.b_nsrc, gn);
+                    if (row >= 0) {
+                        const float* src = g.B + (long)row * g.ldb + gk;
+                        if (b_vec && gk + 3 < g.K) v = *reinterpret_cast<const float4*>(src);
+                        else {
+                            if (gk + 0 < g.K) v.x = src[0];
+                            if (gk + 1 < g.K) v.y = src[1];
+                            if (gk + 2 < g.K) v.z = src[2];
+                            if (gk + 3 < g.K) v.w = src[3];
+                        }
+                    }
+                }
+            } else {
+                int nq = idx % (BN / 4), k = idx / (BN / 4);
+                int gn = n0 + nq * 4, gk = k0 + k;
+                if (gk < g.K) {
+                    long row = g.b_kgather ? (long)g.b_kgather[gk] : (long)gk;
+                    if (row >= 0) {
+                        const float* src = g.B + row * g.ldb + gn;
+                        if (b_vec && gn + 3 < g.N) v = *reinterpret_cast<const float4*>(src);
+                        else {
+                            if (gn + 0 < g.N) v.x = src[0];
+                            if (gn + 1 < g.N) v.y = src[1];
+                            if (gn + 2 < g.N) v.z = src[2];
+                            if (gn + 3 < g.N) v.w = src[3];
+                        }
+                    }
+                }
+            }
+            rb[i] = v;
+        }
+    };
+    auto store_ab = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < A_LD; ++i) {
+            int idx = tid + i * NT;
+            if (A_KM) {
+                int kq = idx % (BK / 4), m = idx / (BK / 4);
+                As[buf][kq * 4 + 0][m] = ra[i].x;
+                As[buf][kq * 4 + 1][m] = ra[i].y;
+                As[buf][kq * 4 + 2][m] = ra[i].z;
+                As[buf][kq * 4 + 3][m] = ra[i].w;
+            } else {
+                int mq = idx % (BM / 4), k = idx / (BM / 4);
+                *reinterpret_cast<float4*>(&As[buf][k][mq * 4]) = ra[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < B_LD; ++i) {
+            int idx = tid + i * NT;
+            if (B_KM) {
+                int kq = idx % (BK / 4), n = idx / (BK / 4);
+                Bs[buf][kq * 4 + 0][n] = rb[i].x;
+                Bs[buf][kq * 4 + 1][n] = rb[i].y;
+                Bs[buf][kq * 4 + 2][n] = rb[i].z;
+                Bs[buf][kq * 4 + 3][n] = rb[i].w;
+            } else {
+                int nq = idx % (BN / 4), k = idx / (BN / 4);
+                *reinterpret_cast<float4*>(&Bs[buf][k][nq * 4]) = rb[i];
+            }
+        }
+    };
+
+    // thread -> output micro-tile: TM rows as TM/4 float4 groups strided by BM/(TM/4), same for cols
+    constexpr int TXN = BN / TN, TYN = BM / TM;
+    const int tx = tid % TXN, ty = tid / TXN;
+    constexpr int MG = TM / 4, NG = TN / 4;
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    if (kt_begin < kt_end) {
+        load_a(kt_begin);
+        load_b(kt_begin);
+        store_ab(0);
+        __syncthreads();
+        for (int kt = kt_begin; kt < kt_end; ++kt) {
+            const int buf = (kt - kt_begin) & 1;
+            const bool has_next = kt + 1 < kt_end;
+            if (has_next) { load_a(kt + 1); load_b(kt + 1); }
+#pragma unroll
+            for (int k = 0; k < BK; ++k) {
+                float a[TM], b[TN];
+#pragma unroll
+                for (int gq = 0; gq < MG; ++gq) {
+                    float4 v = *reinterpret_cast<const float4*>(&As[buf][k][gq * (TYN * 4) + ty * 4]);
+                    a[gq * 4 + 0] = v.x; a[gq * 4 + 1] = v.y; a[gq * 4 + 2] = v.z; a[gq * 4 + 3] = v.w;
+                }
+#pragma unroll
+                for (int gq = 0; gq < NG; ++gq) {
+                    float4 v = *reinterpret_cast<const float4*>(&Bs[buf][k][gq * (TXN * 4) + tx * 4]);
+                    b[gq * 4 + 0] = v.x; b[gq * 4 + 1] = v.y; b[gq * 4 + 2] = v.z; b[gq * 4 + 3] = v.w;
+                }
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+            if (has_next) {
+                store_ab(buf ^ 1);
+                __syncthreads();
+            }
+        }
+    }
+
+    // epilogue
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + (i / 4) * (TYN * 4) + ty * 4 + (i % 4);
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + (j / 4) * (TXN * 4) + tx * 4 + (j % 4);
+            if (n >= g.N) continue;
+            if (ksplit > 1) {
+                g.partials[((long)blockIdx.z * g.M + m) * g.N + n] = acc[i][j];
+            } else {
+                int mrow = gate_src_row(g.m_dst, m);
+                if (mrow < 0) continue;
+                float v = g.alpha * acc[i][j];
+                if (g.bias) v += g.bias_on_m ? g.bias[mrow] : g.bias[gate_src_row(g.b_nsrc, n) < 0 ? 0 : gate_src_row(g.b_nsrc, n)];
+                if (g.act == 1) v = tanhf(v);
+                float* dst = g.C + (long)mrow * g.ldc + n;
+                if (g.accumulate) v += *dst;
+                *dst = v;
+            }
+        }
+    }
+}
+
+__global__ void splitk_reduce_kernel(GemmArgs g) {
+    long total = (long)g.M * g.N;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        int m = (int)(idx / g.N), n = (int)(idx % g.N);
+        float s = 0.f;
+        for (int z = 0; z < g.splits; ++z) s += g.partials[(long)z * total + idx];
+        int mrow = gate_src_row(g.m_dst, m);
+        if (mrow < 0) continue;
+        float v = g.alpha * s;
+        if (g.bias) {
+            int nb = gate_src_row(g.b_nsrc, n);
+            v += g.bias_on_m ? g.bias[mrow] : g.bias[nb < 0 ? 0 : nb];
+        }
+        if (g.act == 1) v = tanhf(v);
+        float* dst = g.C + (long)mrow * g.ldc + n;
+        if (g.accumulate) v += *dst;
+        *dst = v;
+    }
+}
+
+__global__ void colsum_kernel(const float* __restrict__ A, long lda, int rows, int cols, float alpha,
+                              float* __restrict__ out, int accumulate, GateMap dst) {
+    // one block per 32 columns, 8 warps striding rows; deterministic tree reduce in shared memory
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int w = threadIdx.x >> 5;
+    float s = 0.f;
+    if (c < cols)
+        for (int r = w; r < rows; r += 8) s += A[(long)r * lda + c];
+    red[w][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (w == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
+        int d = gate_src_row(dst, c);
+        if (d >= 0) {
+            t *= alpha;
+            out[d] = accumulate ? out[d] + t : t;
+        }
+    }
+}
+
+template <int BM, int BN, int TM, int TN>
+int launch_cfg(const GemmArgs& g, int a_vec, int b_vec, cudaStream_t stream) {
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.splits);
+    dim3 block((BM / TM) * (BN / TN));
+    if (g.a_kmajor && g.b_kmajor) sgemm_kernel<BM, BN, TM, TN, true, true><<<grid, block, 0, stream>>>(g, a_vec, b_vec);
+    else if (g.a_kmajor && !g.b_kmajor) sgemm_kernel<BM, BN, TM, TN, true, false><<<grid, block, 0, stream>>>(g, a_vec, b_vec);
+    else if (!g.a_kmajor && !g.b_kmajor) sgemm_kernel<BM, BN, TM, TN, false, false><<<grid, block, 0, stream>>>(g, a_vec, b_vec);
+    else {
+        abcd_set_error("sgemm: (A m-major, B k-major) layout is not on the path");
+        return ABCD_ERR_UNSUPPORTED;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return ABCD_OK;
+}
+
+}  // namespace
+
+int sgemm_pick_splits(int M, int N, int K) {
+    long tiles = (long)((M + 127) / 128) * ((N + 127) / 128);
+    if (M <= 64 || N <= 64) tiles = (long)((M + 63) / 64) * ((N + 63) / 64);
+    int ktiles = (K + BK - 1) / BK;
+    int s = 1;
+    // fill ~2 waves of 148 SMs, keep at least 8 k-tiles per split
+    while (tiles * s < 296 && ktiles / (s * 2) >= 8 && s < 64) s *= 2;
+    return s;
+}
+
+int sgemm_launch(const GemmArgs& gin, cudaStream_t stream) {
+    GemmArgs g = gin;
+    if (g.M <= 0 || g.N <= 0) return ABCD_OK;
+    ARG_CHECK(g.K >= 0 && g.A && g.B && g.C, "sgemm: null operand or negative K");
+    if (g.splits < 1) g.splits = 1;
+    ARG_CHECK(g.splits == 1 || g.partials, "sgemm: split-K needs a partials workspace");
+    ARG_CHECK(!(g.b_kgather && g.b_kmajor), "sgemm: k-gather needs n-major B");
+    ARG_CHECK(!(g.b_nsrc.enabled && !g.b_kmajor), "sgemm: n source map needs k-major B");
+    const int a_vec = ((uintptr_t)g.A % 16 == 0) && (g.lda % 4 == 0);
+    const int b_vec = ((uintptr_t)g.B % 16 == 0) && (g.ldb % 4 == 0);
+    int r;
+    if (g.M <= 64 || g.N <= 64) r = launch_cfg<64, 64, 4, 4>(g, a_vec, b_vec, stream);
+    else r = launch_cfg<128, 128, 8, 8>(g, a_vec, b_vec, stream);
+    if (r != ABCD_OK) return r;
+    if (g.splits > 1) {
+        long total = (long)g.M * g.N;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(g);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return ABCD_OK;
+}
+
+int colsum_launch(const float* A, long lda, int rows, int cols, float alpha, float* out, int accumulate,
+                  GateMap dst, cudaStream_t stream) {
+    if (cols <= 0) return ABCD_OK;
+    colsum_kernel<<<(cols + 31) / 32, 256, 0, stream>>>(A, lda, rows, cols, alpha, out, accumulate, dst);
+    CUDA_TRY(cudaGetLastError());
+    return ABCD_OK;
+}

@@ -1,0 +1,243 @@
+# coding: utf-8
+"""GPU suite: the CUDA path (through the C ABI, via the nn.Module surface) against the CPU oracle on the same
+seeded inputs, and against the committed golden vectors of the reference.
+
+Tolerances (fp32 mode): losses 2e-5 relative; activations / gradients 1e-4 of the tensor's max magnitude
+(BASELINE.json north_star: "1e-4 relative in fp32 mode"); packing / arg-max bit-exact.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import abcd_oracle as O
+from oracle import cases as CS
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def rel_to_max(a, b):
+	a = a.detach().double().cpu(); b = b.detach().double().cpu()
+	return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def _to_cuda_modules(abcd, cfg):
+	mods = CS.build_modules(abcd.model, cfg)
+	enc_sd, smp_sd, dec_sd, seqs, eps, gumbel, speaker = CS.build_case(cfg, mods)
+	enc, smp, dec = mods
+	enc.load_state_dict(enc_sd); smp.load_state_dict(smp_sd); dec.load_state_dict(dec_sd)
+	for m in mods:
+		m.cuda()
+	smp.temperature = cfg['tau']
+	return mods, (enc_sd, smp_sd, dec_sd), seqs, eps, gumbel, speaker
+
+
+def _cuda_step(abcd, cfg):
+	(enc, smp, dec), sds, seqs, eps, gumbel, speaker = _to_cuda_modules(abcd, cfg)
+	packed = torch.nn.utils.rnn.pack_sequence(seqs)
+	is_off = O.is_offset_packed(packed.batch_sizes.tolist())
+	data = packed.data.cuda()
+	packed_cuda = torch.nn.utils.rnn.PackedSequence(data, packed.batch_sizes)
+	last_hidden = enc(packed_cuda)
+	logits = smp(last_hidden)
+	smp.injected_gumbel_noise = gumbel.cuda()
+	feats = smp.sample(logits, no_sample=cfg['pretrain'])
+	kl = smp.kl_divergence(logits, cfg['N_data'])
+	dec.injected_emission_noise = eps.cuda()
+	em, off, x_all, (mean, lv), off_logit = dec(feats, batch_sizes=packed.batch_sizes, speaker=speaker.cuda() if speaker is not None else None,
+												ground_truth_out=data, ground_truth_offset=is_off.cuda())
+	loss = (em + off + kl) / packed.batch_sizes[0]
+	loss.backward()
+	torch.cuda.synchronize()
+	grads = {'encoder': {k: p.grad for k, p in enc.named_parameters()},
+			'feature_sampler': {k: p.grad for k, p in smp.named_parameters()},
+			'decoder': {k: p.grad for k, p in dec.named_parameters()}}
+	out = dict(emission=em, offset=off, kl=kl, loss=loss, logits=logits, last_hidden=last_hidden, features=feats,
+				flatten_out=x_all, mean=mean, logvar=lv, offset_logit=off_logit, grads=grads)
+	return out, sds, seqs, eps, gumbel, speaker
+
+
+@pytest.mark.parametrize('name', sorted(CS.TRAIN_CASES))
+def test_train_step_matches_oracle_and_golden(abcd, golden_dir, name):
+	cfg = CS.TRAIN_CASES[name]
+	out, (enc_sd, smp_sd, dec_sd), seqs, eps, gumbel, speaker = _cuda_step(abcd, cfg)
+	dt = torch.float64
+	cast = lambda d: {k: (v.to(dt) if v.dtype.is_floating_point else v) for k, v in d.items()}
+	o = O.train_step(cast(enc_sd), cast(smp_sd), cast(dec_sd), [s.to(dt) for s in seqs], eps.to(dt), gumbel.to(dt),
+					cfg['N_data'], cfg['pretrain'], cfg['tau'], cfg['rnn'], 1.0, speaker)
+	report = {}
+	for k in ('emission', 'offset', 'kl', 'loss'):
+		report[k] = abs(out[k].item() - o[k].item()) / (abs(o[k].item()) + 1e-30)
+	for k in ('last_hidden', 'logits', 'features', 'flatten_out', 'mean', 'logvar', 'offset_logit'):
+		report[k] = rel_to_max(out[k], o[k])
+	worst = ('', 0.0)
+	for m in o['grads']:
+		for k, g in o['grads'][m].items():
+			got = out['grads'][m][k]
+			assert got is not None, 'missing gradient {}/{}'.format(m, k)
+			r = rel_to_max(got, g)
+			report['grad/{}/{}'.format(m, k)] = r
+			if r > worst[1]:
+				worst = ('{}/{}'.format(m, k), r)
+	print(name, {k: '%.1e' % v for k, v in report.items() if not k.startswith('grad/')}, 'worst grad', worst)
+	for k in ('emission', 'offset', 'loss'):
+		assert report[k] < 2e-5, (k, report[k])
+	assert report['kl'] < 2e-5 or abs(out['kl'].item() - o['kl'].item()) < 1e-3
+	for k, v in report.items():
+		if k not in ('emission', 'offset', 'loss', 'kl'):
+			assert v < TOL, (k, v)
+	# arg-max category assignment is bit-exact (oracle fp64 margin is far above fp32 noise in these cases)
+	assert torch.equal(out['logits'].argmax(-1).cpu(), o['logits'].argmax(-1))
+	# golden vectors from the reference itself
+	g = np.load(os.path.join(golden_dir, name + '.npz'))
+	for k in ('emission', 'offset', 'loss'):
+		assert abs(out[k].item() - float(g[k])) <= 3e-5 * abs(float(g[k])), k
+	np.testing.assert_allclose(out['logits'].detach().cpu().numpy(), g['logits'], rtol=0, atol=TOL * np.abs(g['logits']).max())
+	for m in out['grads']:
+		for k, gr in out['grads'][m].items():
+			ref_norm = float(g['gradnorm/{}/{}'.format(m, k)])
+			assert abs(gr.norm().item() - ref_norm) <= TOL * ref_norm + 1e-9, (m, k)
+			np.testing.assert_allclose(CS.sample_vec(gr), g['gradsample/{}/{}'.format(m, k)], rtol=0, atol=TOL * ref_norm + 1e-12)
+
+
+def test_encoder_large_ragged_batch_matches_oracle(abcd):
+	"""More than one row tile (B > 64), ties, length-1 segments; inference (no-save) path; LSTM and GRU."""
+	for rnn, seed in (('LSTM', 11), ('GRU', 12)):
+		lengths = sorted([1, 1, 2, 3, 3, 5, 8, 8, 8, 13, 21, 21, 34] * 6 + [40, 37], reverse=True)   # B = 80
+		F = 65
+		enc = abcd.model.RNN_Variational_Encoder(F, 256, rnn_type=rnn)
+		sd = CS.det_state(enc, seed)
+		enc.load_state_dict(sd)
+		enc.cuda()
+		seqs = CS.make_inputs(lengths, F, seed)
+		packed = torch.nn.utils.rnn.pack_sequence(seqs)
+		with torch.no_grad():
+			got = enc(torch.nn.utils.rnn.PackedSequence(packed.data.cuda(), packed.batch_sizes))
+		P = {k[len('rnn.'):]: v.double() for k, v in sd.items()}
+		want = O.encoder_forward([s.double() for s in seqs], P, rnn)
+		assert rel_to_max(got, want) < TOL
+
+
+def test_encode_argmax_bit_exact(abcd):
+	"""Encoder.encode (encode.py:28-32): probabilities within tolerance, category arg-max identical."""
+	cfg = dict(rnn='LSTM', F=65, K=128, f=256)
+	lengths = CS.encode_lengths(24, 5)
+	lengths = np.minimum(lengths, 60)
+	lengths = np.sort(lengths)[::-1]
+	mods = CS.build_modules(abcd.model, cfg)
+	enc, smp, _ = mods
+	enc_sd, smp_sd = CS.det_state(enc, 31), CS.det_state(smp, 32)
+	enc.load_state_dict(enc_sd); smp.load_state_dict(smp_sd)
+	enc.cuda(); smp.cuda()
+	seqs = CS.make_inputs([int(l) for l in lengths], 65, 33)
+	packed = torch.nn.utils.rnn.pack_sequence(seqs)
+	with torch.no_grad():
+		logits = smp(enc(torch.nn.utils.rnn.PackedSequence(packed.data.cuda(), packed.batch_sizes)))
+		B, K = logits.shape
+		probs = torch.empty_like(logits)
+		amax = torch.empty(B, dtype=torch.int32, device='cuda')
+		L = abcd._lib
+		L.call('abcd_softmax_argmax', B, K, L.ptr(logits), L.ptr(probs), L.ptr(amax), L.stream_ptr())
+	P = {k[len('rnn.'):]: v.double() for k, v in enc_sd.items()}
+	lh = O.encoder_forward([s.double() for s in seqs], P, 'LSTM')
+	ologits = O.sampler_logits(lh, {k: v.double() for k, v in smp_sd.items()})
+	oprobs = O.softmax_rows(ologits)
+	top2 = ologits.topk(2, -1).values
+	margin = (top2[:, 0] - top2[:, 1]).min().item()
+	assert rel_to_max(probs, oprobs) < TOL
+	assert margin > 1e-4, 'case too close to call in fp32; pick another seed'
+	assert torch.equal(amax.cpu().long(), ologits.argmax(-1))
+
+
+def test_stft_matches_golden_and_oracle(abcd, golden_dir):
+	g = np.load(os.path.join(golden_dir, 'stft_toy.npz'))
+	frame, hop = int(g['frame']), int(g['hop'])
+	stft = abcd.data_utils.STFT(frame, hop, device='cuda')
+	for i in range(2):
+		wav = torch.from_numpy(g['wav_%d' % i].astype(np.float32))
+		amp = stft(wav).cpu().numpy()
+		ref = g['amp_%d' % i]
+		assert amp.shape == ref.shape
+		np.testing.assert_allclose(amp, ref, rtol=0, atol=2e-6 * ref.max())
+		np.testing.assert_allclose(amp, O.stft_amplitude(g['wav_%d' % i], frame, hop), rtol=0, atol=2e-6 * ref.max())
+		logn = abcd.data_utils.LogSTFT(stft, 2.0 ** -15, 11.0)(torch.from_numpy(g['wav_%d' % i]))   # int16 path
+		np.testing.assert_allclose(logn.cpu().numpy(), g['logn_%d' % i], rtol=0, atol=2e-3)
+
+
+def test_sgemm_layouts(abcd):
+	L = abcd._lib
+	L.ensure_device(torch.device('cuda'))
+	torch.manual_seed(0)
+	for (M, N, K) in ((70, 33, 65), (257, 130, 1000), (1024, 65, 3000), (5, 256, 1)):
+		A = torch.randn(M, K, device='cuda'); Bm = torch.randn(K, N, device='cuda')
+		want = (A.double() @ Bm.double()).float()
+		for a_km, b_km in ((1, 1), (1, 0), (0, 0)):
+			Ain = A.contiguous() if a_km else A.t().contiguous()
+			Bin = Bm.t().contiguous() if b_km else Bm.contiguous()
+			for splits in (1, 4):
+				Cout = torch.zeros(M, N, device='cuda')
+				part = torch.empty(splits * M * N, device='cuda')
+				L.call('abcd_sgemm', M, N, K, L.ptr(Ain), Ain.shape[1], a_km, L.ptr(Bin), Bin.shape[1], b_km, L.ptr(Cout), N,
+					1.0, None, 0, 0, splits, L.ptr(part), L.stream_ptr())
+				torch.cuda.synchronize()
+				assert rel_to_max(Cout, want) < 2e-6 * max(1, K ** 0.5), (M, N, K, a_km, b_km, splits)
+
+
+def test_clip_sgd_matches_golden(abcd, golden_dir):
+	L = abcd._lib
+	L.ensure_device(torch.device('cuda'))
+	g = np.load(os.path.join(golden_dir, 'optim.npz'))
+	shapes = [(300, 7), (1024,), (33, 65), (5,)]
+	npart = L.load().abcd_optim_partial_count()
+	for mom, tag in ((0.0, 'plain'), (0.9, 'momentum')):
+		flat = torch.cat([O.det_tensor(s, 900 + i, 'uniform', 0.5).reshape(-1) for i, s in enumerate(shapes)]).cuda()
+		mbuf = torch.zeros_like(flat) if mom else None
+		partial = torch.empty(npart, device='cuda'); norm = torch.empty((), device='cuda')
+		for step in range(2):
+			gr = torch.cat([O.det_tensor(s, 950 + 10 * step + i, 'normal', 0.3).reshape(-1) for i, s in enumerate(shapes)]).cuda()
+			L.call('abcd_gradnorm_clip_sgd', L.ptr(flat), L.ptr(gr), L.ptr(mbuf), flat.numel(), 0.7, mom, 1.0, 1, L.ptr(norm), L.ptr(partial), L.stream_ptr())
+			assert abs(norm.item() - float(g['{}_norm_{}'.format(tag, step)])) < 1e-4
+			assert float(gr.abs().max()) == 0.0   # zero_grads
+		np.testing.assert_allclose(flat.cpu().numpy(), g[tag + '_params'], rtol=0, atol=2e-6)
+
+
+def test_plain_gaussian_latent(abcd, golden_dir):
+	g = np.load(os.path.join(golden_dir, 'plain_latent.npz'))
+	f = 16
+	smp = abcd.model.Sampler(1024, 256, f)
+	sd = CS.det_state(smp, 77)
+	smp.load_state_dict(sd)
+	smp.cuda()
+	x = O.det_tensor((5, 1024), 771, 'uniform', 1.0).cuda().requires_grad_(True)
+	eps = O.det_tensor((5, f), 772, 'normal', 1.0).cuda()
+	w = O.det_tensor((5, f), 773, 'uniform', 1.0).cuda()
+	mean, lv = smp(x)
+	z, kl = abcd.model._GaussLatentFn.apply(mean, lv, eps)
+	((z * w).sum() + kl).backward()
+	np.testing.assert_allclose(z.detach().cpu().numpy(), g['z'], rtol=0, atol=TOL * np.abs(g['z']).max())
+	assert abs(kl.item() - float(g['kl'])) < 2e-5 * abs(float(g['kl']))
+	np.testing.assert_allclose(x.grad.cpu().numpy(), g['dx'], rtol=0, atol=TOL * np.abs(g['dx']).max())
+
+
+def test_philox_moments(abcd):
+	n = 1 << 20
+	t = torch.empty(n, device='cuda')
+	a = abcd.model.noise_like(t)
+	b = abcd.model.noise_like(t)
+	assert abs(a.mean().item()) < 5e-3 and abs(a.std().item() - 1.0) < 5e-3
+	assert not torch.equal(a, b)
+	gmb = abcd.model.noise_like(t, kind='gumbel')
+	assert abs(gmb.mean().item() - 0.5772) < 5e-3
+
+
+def test_unsupported_sizes_fail_loudly(abcd):
+	enc = abcd.model.RNN_Variational_Encoder(65, 128, rnn_type='LSTM').cuda()
+	x = torch.nn.utils.rnn.pack_sequence([torch.randn(4, 65), torch.randn(2, 65)])
+	with pytest.raises(abcd._lib.AbcdError):
+		enc(torch.nn.utils.rnn.PackedSequence(x.data.cuda(), x.batch_sizes))
+	with pytest.raises(NotImplementedError):
+		abcd.model.RNN_Variational_Encoder(65, 256, rnn_type='ESN')
