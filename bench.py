@@ -1,0 +1,342 @@
+# coding: utf-8
+"""Headline benchmark: ABCD-VAE training segments/s (forward + backward + clip + SGD step) on the publication
+configuration (BASELINE.json configs[2]: batch 512, K=128, f=256, LSTM 256/256, F=65 log-STFT bins), synthetic
+Bengalese-finch-like segment lengths.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                 # this implementation
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1  # CPU restatement of the reference path (host cores)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One JSON line on stdout (rank 0).  `value` = segments/s with the batch resident in HBM; `e2e` = the same step
+driven from pinned HOST buffers (H2D of the packed batch + D2H of the loss inside the timed region).
+Weak scaling: every rank trains on its own 512-segment batch (global batch 512*N, gradients all-reduced with NCCL
+and divided by the global batch size, see Learner.train_step).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+	sys.path.insert(0, ROOT)
+
+METRIC = 'train segments/sec (fwd+bwd+step)'
+CFG = dict(rnn='LSTM', F=65, K=128, f=256, H=256, M=256, B=512, N_data=100000)
+
+
+def parse():
+	p = argparse.ArgumentParser()
+	p.add_argument('--gpus', type=int, default=1)
+	p.add_argument('--steps', type=int, default=20)
+	p.add_argument('--warmup', type=int, default=5)
+	p.add_argument('--impl', type=str, default='b200', choices=['b200', 'reference'])
+	p.add_argument('--batch', type=int, default=CFG['B'], help='segments per GPU')
+	p.add_argument('--bins', type=int, default=CFG['F'])
+	p.add_argument('--rnn', type=str, default=CFG['rnn'])
+	p.add_argument('--pretrain', action='store_true', help='softmax (pretraining) mode instead of Gumbel-softmax')
+	p.add_argument('--no-cpu-baseline', action='store_true')
+	p.add_argument('--cpu-steps', type=int, default=3)
+	return p.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# synthetic workload (deterministic; identical for both arms)
+# ---------------------------------------------------------------------------------------------------------
+def make_batch(B, F, seed):
+	from oracle import cases as CS
+	from oracle import abcd_oracle as O
+	lengths = CS.synthetic_lengths(B, 1000 + seed)
+	rng = np.random.RandomState(seed)
+	sumT = int(lengths.sum())
+	x = np.clip(rng.normal(0.45, 0.25, size=(sumT, F)), -0.945, 1.05).astype(np.float32)
+	bs = O.batch_sizes_from_lengths(lengths.tolist())
+	offsets = np.concatenate([[0], np.cumsum(bs)])
+	is_off = np.zeros(sumT, dtype=np.float32)
+	for b, l in enumerate(lengths):
+		is_off[offsets[l - 1] + b] = 1.0
+	return lengths, torch.tensor(bs, dtype=torch.int64), torch.from_numpy(x), torch.from_numpy(is_off)
+
+
+def flops_per_step(lengths, F, H=256, M=256, K=128, f=256, rnn='LSTM'):
+	"""Algorithmic training FLOPs (3 x forward)."""
+	sumT, B = int(lengths.sum()), len(lengths)
+	g = 4 if rnn == 'LSTM' else 3
+	per_frame = 2 * (2 * g * H * (F + H)) + 2 * (g * H * (F + H)) + 2 * (2 * H * M + 2 * M * F) + 2 * (H * M + M)
+	enc_out = (2 if rnn == 'LSTM' else 1) * 2 * H
+	per_seg = 2 * (enc_out * M + M * f) + 2 * f * K + 2 * K * f + 2 * f * ((2 if rnn == 'LSTM' else 1) * H)
+	return 3 * (sumT * per_frame + B * per_seg)
+
+
+class ClockSampler(object):
+	"""nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+	def __init__(self, gpu_index):
+		self.rows = []
+		self.proc = None
+		self.gpu = gpu_index
+
+	def start(self):
+		q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+		try:
+			self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '200'],
+										stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+			self.thread = threading.Thread(target=self._read, daemon=True)
+			self.thread.start()
+		except OSError:
+			self.proc = None
+
+	def _read(self):
+		for line in self.proc.stdout:
+			self.rows.append([c.strip() for c in line.split(',')])
+
+	def stop(self):
+		if self.proc is None:
+			return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+		self.proc.terminate()
+		try:
+			self.proc.wait(timeout=5)
+		except subprocess.TimeoutExpired:
+			self.proc.kill()
+		sm, mx, reasons = [], [], set()
+		names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+		for r in self.rows:
+			try:
+				sm.append(float(r[0])); mx.append(float(r[1]))
+			except (ValueError, IndexError):
+				continue
+			for n, v in zip(names, r[3:7]):
+				if v.lower().startswith('active'):
+					reasons.add(n)
+		return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+				'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle's batched CPU restatement of the same training step
+# ---------------------------------------------------------------------------------------------------------
+def cpu_step_factory(args, lengths, bs, x, is_off):
+	from oracle import abcd_oracle as O
+	from oracle import cases as CS
+	pkg = importlib.import_module('seq2seq_abcd-vae_b200')
+	cfg = dict(rnn=args.rnn, F=args.bins, K=CFG['K'], f=CFG['f'])
+	mods = CS.build_modules(pkg.model, cfg)
+	sds = [CS.det_state(m, 500 + i) for i, m in enumerate(mods)]
+	seqs = O.unpack(x, bs.tolist())
+	sumT = x.shape[0]
+	eps = torch.from_numpy(np.random.RandomState(7).standard_normal((sumT, args.bins)).astype(np.float32))
+	gum = torch.from_numpy(np.random.RandomState(8).gumbel(size=(len(lengths), CFG['K'])).astype(np.float32))
+	state = {'sds': sds}
+
+	def step():
+		enc_sd, smp_sd, dec_sd = state['sds']
+		r = O.train_step(enc_sd, smp_sd, dec_sd, seqs, eps, gum, CFG['N_data'], args.pretrain, 1.0, args.rnn, 1.0, None, batched=True)
+		names, params, grads = [], [], []
+		for m, sd in zip(('encoder', 'feature_sampler', 'decoder'), (enc_sd, smp_sd, dec_sd)):
+			for k, g in r['grads'][m].items():
+				names.append((m, k)); params.append(sd[k]); grads.append(g)
+		new, _, _ = O.clip_and_sgd(params, grads, 1.0, 1.0)
+		for (m, k), p in zip(names, new):
+			{'encoder': enc_sd, 'feature_sampler': smp_sd, 'decoder': dec_sd}[m][k] = p.detach()
+		return float(r['loss'])
+	return step
+
+
+def run_cpu(args, steps, warmup):
+	lengths, bs, x, is_off = make_batch(args.batch, args.bins, 0)
+	torch.set_num_threads(os.cpu_count() or 1)
+	step = cpu_step_factory(args, lengths, bs, x, is_off)
+	for _ in range(warmup):
+		step()
+	t0 = time.perf_counter()
+	for _ in range(steps):
+		step()
+	dt = (time.perf_counter() - t0) / max(steps, 1)
+	return args.batch / dt, dt, lengths
+
+
+def reference_arm(args):
+	rank = int(os.environ.get('RANK', '0'))
+	if rank != 0:
+		return
+	steps, warmup = max(1, min(args.steps, 5)), max(0, min(args.warmup, 1))
+	val, dt, lengths = run_cpu(args, steps, warmup)
+	cores = torch.get_num_threads()
+	sample = '{} warm-up + {} timed full steps of the B={} batch (sumT={})'.format(warmup, steps, args.batch, int(lengths.sum()))
+	line = {
+		'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'segments/s', 'n_gpus': args.gpus, 'steps': steps,
+		'warmup': warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+		'dtype': 'f32', 'data': 'synthetic',
+		'config': workload_config(args, lengths, 1),
+		'cpu_baseline': {'value': val, 'unit': 'segments/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+		'e2e': {'value': val, 'unit': 'segments/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+		'gpu_launches': 0,
+	}
+	print(json.dumps(line), flush=True)
+
+
+def workload_config(args, lengths, world):
+	return {
+		'workload': 'ABCD-VAE publication config (BASELINE.json configs[2]): {} segments/GPU, K=128, f=256, {} 256/256, mlp 256, F={} bins, '
+					'T in [{}, {}] mean {:.1f} frames, sumT={}/GPU, {} mode, SGD lr 1.0 clip 1.0'.format(
+						args.batch, args.rnn, args.bins, int(lengths.min()), int(lengths.max()), float(lengths.mean()), int(lengths.sum()),
+						'pretrain-softmax' if args.pretrain else 'Gumbel-softmax'),
+		'global_batch': args.batch * world, 'parallelism': 'dp{}'.format(world),
+		'l2_policy': 'per-step working set (saved activations + gate gradients, ~0.6 GB at B=512) exceeds the 126 MB L2; no explicit flush',
+	}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------
+def main():
+	args = parse()
+	if args.impl == 'reference':
+		reference_arm(args)
+		return
+	rank = int(os.environ.get('RANK', '0'))
+	local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+	world = int(os.environ.get('WORLD_SIZE', '1'))
+	assert torch.cuda.is_available(), 'bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU arm)'
+	torch.cuda.set_device(local_rank)
+	dev = torch.device('cuda', local_rank)
+	if world > 1:
+		torch.distributed.init_process_group('nccl', device_id=dev)
+	pkg = importlib.import_module('seq2seq_abcd-vae_b200')
+	learning = importlib.import_module('seq2seq_abcd-vae_b200.learning')
+	L = pkg._lib
+	from oracle import cases as CS
+
+	lengths, bs, x_host, off_host = make_batch(args.batch, args.bins, rank)
+	learner = learning.Learner(args.bins, 256, 256, 256, CFG['K'], CFG['f'], None, encoder_rnn_type=args.rnn,
+								decoder_rnn_type=args.rnn, device=str(dev), seed=1111)
+	# identical deterministic weights on every rank (and in the CPU arm)
+	for i, m in enumerate(learner._modules()):
+		m.load_state_dict({k: v.to(dev) for k, v in CS.det_state(m, 500 + i).items()})
+	learner.setup_optimizer(1.0, 0.0, gradient_clip=1.0, patience=0)
+	learner.feature_sampler.train()
+	x_pin, off_pin = x_host.pin_memory(), off_host.pin_memory()
+	x_dev, off_dev = x_pin.to(dev), off_pin.to(dev)
+	packed = torch.nn.utils.rnn.PackedSequence(x_dev, bs)
+	packed_off = torch.nn.utils.rnn.PackedSequence(off_dev, bs)
+	gb = args.batch * world
+
+	def step_resident():
+		return learner.train_step(packed, packed_off, None, CFG['N_data'], args.pretrain, global_batch_size=gb)[0]
+
+	x_stage, off_stage = torch.empty_like(x_dev), torch.empty_like(off_dev)
+	loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+	def step_e2e():
+		x_stage.copy_(x_pin, non_blocking=True)
+		off_stage.copy_(off_pin, non_blocking=True)
+		p = torch.nn.utils.rnn.PackedSequence(x_stage, bs)
+		po = torch.nn.utils.rnn.PackedSequence(off_stage, bs)
+		loss = learner.train_step(p, po, None, CFG['N_data'], args.pretrain, global_batch_size=gb)[0]
+		loss_host.copy_(loss.detach(), non_blocking=True)
+		torch.cuda.current_stream().synchronize()
+		return loss_host
+
+	def barrier():
+		if world > 1:
+			torch.distributed.barrier()
+		torch.cuda.synchronize()
+
+	def timed(fn, steps):
+		barrier()
+		e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+		e0.record()
+		for _ in range(steps):
+			fn()
+		e1.record()
+		barrier()
+		ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+		if world > 1:
+			torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+		return float(ms.item())
+
+	warm = max(args.warmup, 3)
+	for _ in range(warm):
+		step_resident()
+	clocks = ClockSampler(local_rank)
+	if rank == 0:
+		clocks.start()
+	launches0 = L.load().abcd_launch_count()
+	total_ms = timed(step_resident, args.steps)
+	launches = L.load().abcd_launch_count() - launches0
+	clock_info = clocks.stop() if rank == 0 else None
+	ms_per_step = total_ms / args.steps
+	value = gb / (ms_per_step * 1e-3)
+
+	for _ in range(2):
+		step_e2e()
+	e2e_ms = timed(step_e2e, args.steps) / args.steps
+	e2e_value = gb / (e2e_ms * 1e-3)
+	h2d = x_pin.numel() * 4 + off_pin.numel() * 4
+	d2h = 4
+
+	# kernel-group timing pass (CUDA events recorded by the library on the launching stream)
+	L.profile_enable(True)
+	prof_steps = min(args.steps, 10)
+	barrier()
+	for _ in range(prof_steps):
+		step_resident()
+	barrier()
+	L.profile_enable(False)
+	prof = L.profile_read_all()
+	groups = {k: {'ms_per_step': v[0] / prof_steps, 'launches_per_step': v[1] / prof_steps} for k, v in prof.items() if v[1]}
+	peaks = {}
+	try:
+		peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+	except (OSError, ValueError):
+		pass
+	sumT = int(lengths.sum())
+	g = 4 if args.rnn == 'LSTM' else 3
+	F, H, M = args.bins, 256, 256
+	kernel_flops = {   # algorithmic FLOPs per launch of each persistent kernel (DESIGN.md "Kernels")
+		'enc_fwd_kernel': sumT * 2 * (2 * g * H * H),
+		'enc_bwd_kernel': sumT * 2 * (2 * g * H * H),
+		'dec_fwd_kernel': sumT * 2 * (g * H * (F + H) + 2 * H * M + 2 * M * F),
+		'dec_bwd_kernel': sumT * 2 * (g * H * (F + H) + 2 * H * M + 2 * M * F),
+	}
+	dom = max((k for k in groups if k in kernel_flops), key=lambda k: groups[k]['ms_per_step'], default=None)
+	roofline = None
+	if dom is not None:
+		dur = groups[dom]['ms_per_step'] / max(groups[dom]['launches_per_step'], 1) * 1e-3
+		achieved = kernel_flops[dom] / dur / 1e12
+		peak = peaks.get('bf16_tflops_sustained', 1400.0)
+		roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+					'traffic': None, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1400 (B200_PROFILING.md)',
+					'note': 'fp32 FFMA kernel (fp32-exact mode); fraction is of the measured bf16 tensor peak; fp32 FFMA peak is ~72 TFLOP/s',
+					'frac_of_fp32_ffma_peak': achieved / 72.0, 'avg_launch_ms': dur * 1e3}
+
+	cpu_baseline = None
+	if rank == 0 and not args.no_cpu_baseline:
+		cval, cdt, _ = run_cpu(args, args.cpu_steps, 1)
+		cpu_baseline = {'value': cval, 'unit': 'segments/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+						'sample': '1 warm-up + {} timed full steps of the same B={} batch on the host cores ({:.2f} s/step)'.format(args.cpu_steps, args.batch, cdt)}
+	if rank == 0:
+		line = {
+			'metric': METRIC, 'value': value, 'unit': 'segments/s', 'n_gpus': world, 'steps': args.steps, 'warmup': warm,
+			'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+			'data': 'synthetic', 'config': workload_config(args, lengths, world), 'clocks': clock_info,
+			'e2e': {'value': e2e_value, 'unit': 'segments/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms},
+			'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+			'kernel_groups': groups,
+			'train_flops_per_step': flops_per_step(lengths, args.bins, rnn=args.rnn),
+			'achieved_tflops_whole_step': flops_per_step(lengths, args.bins, rnn=args.rnn) / (ms_per_step * 1e-3) / 1e12,
+		}
+		print(json.dumps(line), flush=True)
+	if world > 1:
+		torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+	main()

@@ -85,6 +85,17 @@ int abcd_init(int device);                 /* requires compute capability 10.x; 
 const char* abcd_last_error(void);
 const char* abcd_version(void);
 
+/* co-resident 16-CTA clusters of a persistent kernel (0 enc_fwd, 1 enc_bwd, 2 dec_fwd, 3 dec_bwd) for output size F */
+int abcd_max_active_clusters(int which, int F);
+/* kernel launches enqueued by this library since load (what bench.py reports as gpu_launches) */
+long long abcd_launch_count(void);
+/* optional CUDA-event timing per kernel group on the launching stream (off by default; used by bench.py for the
+ * roofline numbers).  abcd_profile_read synchronises the group's events, returns their summed duration and clears. */
+int abcd_profile_groups(void);
+const char* abcd_profile_name(int id);
+void abcd_profile_enable(int on);
+int abcd_profile_read(int id, float* total_ms, int* count);
+
 /* ---- front end: data_utils.STFT.__call__ + log_and_normalize (data_utils.py:131-139, learning.py:466) */
 int abcd_stft_logamp(const void* wav, int wav_is_int16, int64_t n_samples,
                      const int32_t* seg_onset, const int32_t* seg_nsamp, /* [B] sample index / sample count, batch order */

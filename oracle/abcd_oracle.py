@@ -203,6 +203,51 @@ def encoder_forward(seqs, P, rnn_type='LSTM', bidirectional=True):
 	return torch.stack(outs)
 
 
+def encoder_forward_batched(data, batch_sizes, P, rnn_type='LSTM', bidirectional=True):
+	"""Same arithmetic as encoder_forward, organised the way the reference's nn.LSTM/GRU runs it on a
+	PackedSequence: one batched cell step per time index over the active prefix of the batch (used for the CPU
+	baseline timing; checked against the per-sequence version in tests/test_cpu_oracle.py)."""
+	H = P['weight_hh_l0'].shape[1]
+	B, T = batch_sizes[0], len(batch_sizes)
+	offs = [0]
+	for n in batch_sizes:
+		offs.append(offs[-1] + n)
+	per_dir = []
+	for suffix in ('', '_reverse'):
+		if suffix and not bidirectional:
+			continue
+		w_ih, w_hh = P['weight_ih_l0' + suffix], P['weight_hh_l0' + suffix]
+		b_ih, b_hh = P['bias_ih_l0' + suffix], P['bias_hh_l0' + suffix]
+		xp_all = data @ w_ih.t() + b_ih
+		h = data.new_zeros(0, H); c = data.new_zeros(0, H)
+		finals_h, finals_c = [], []
+		order = range(T) if not suffix else range(T - 1, -1, -1)
+		for t in order:
+			bs = batch_sizes[t]
+			if not suffix:
+				if t == 0:
+					h = data.new_zeros(bs, H); c = data.new_zeros(bs, H)
+				elif bs < h.shape[0]:   # rows bs.. finished at t-1
+					finals_h.append(h[bs:]); finals_c.append(c[bs:])
+					h = h[:bs]; c = c[:bs]
+			else:
+				if bs > h.shape[0]:     # rows start at their own last frame with a zero state
+					pad = data.new_zeros(bs - h.shape[0], H)
+					h = torch.cat([h, pad]); c = torch.cat([c, pad])
+			xp = xp_all[offs[t]:offs[t] + bs]
+			if rnn_type == 'LSTM':
+				h, c = lstm_step(xp, h, c, w_hh, b_hh)
+			else:
+				h = gru_step(xp, h, w_hh, b_hh)
+		if not suffix:
+			finals_h.append(h); finals_c.append(c)
+			hf = torch.cat(finals_h[::-1]); cf = torch.cat(finals_c[::-1])
+		else:
+			hf, cf = h, c
+		per_dir.append(torch.cat([hf, cf], dim=-1) if rnn_type == 'LSTM' else hf)
+	return torch.cat(per_dir, dim=-1)
+
+
 def mlp(x, P, prefix):
 	"""Linear -> Tanh -> Linear (model.py:326-334)."""
 	h = torch.tanh(x @ P[prefix + 'whole_network.0.weight'].t() + P[prefix + 'whole_network.0.bias'])
@@ -342,14 +387,17 @@ def clip_and_sgd(params, grads, lr, max_norm, momentum=0.0, bufs=None):
 # one full training step (learning.py:147-163)
 # ---------------------------------------------------------------------------------------------------
 def train_step(enc_P, smp_P, dec_P, seqs, eps, gumbel, entire_data_size, is_pretraining, tau=1.0, rnn_type='LSTM',
-				prior_concentration=1.0, speaker=None, global_batch=None):
+				prior_concentration=1.0, speaker=None, global_batch=None, batched=False):
 	"""Forward + backward of one batch; returns dict(losses, logits, grads per module)."""
 	leaves = {}
 	for name, P in (('encoder', enc_P), ('feature_sampler', smp_P), ('decoder', dec_P)):
 		leaves[name] = {k: v.clone().requires_grad_(v.dtype.is_floating_point and k != 'prior_concentration') for k, v in P.items()}
 	data, bs, _ = pack(seqs)
 	enc_keys = {k[len('rnn.'):]: v for k, v in leaves['encoder'].items()}
-	last_hidden = encoder_forward(seqs, enc_keys, rnn_type)
+	if batched:
+		last_hidden = encoder_forward_batched(data, bs, enc_keys, rnn_type)
+	else:
+		last_hidden = encoder_forward(seqs, enc_keys, rnn_type)
 	logits = sampler_logits(last_hidden, leaves['feature_sampler'])
 	feats, y = sampler_sample(logits, leaves['feature_sampler'], is_pretraining, tau, gumbel)
 	kl = sampler_kl(logits, leaves['feature_sampler'], entire_data_size, prior_concentration)

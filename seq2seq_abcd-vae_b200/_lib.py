@@ -69,6 +69,12 @@ SIGNATURES = {
 	'abcd_init': (C.c_int, [C.c_int]),
 	'abcd_last_error': (C.c_char_p, []),
 	'abcd_version': (C.c_char_p, []),
+	'abcd_max_active_clusters': (C.c_int, [C.c_int, C.c_int]),
+	'abcd_launch_count': (C.c_longlong, []),
+	'abcd_profile_groups': (C.c_int, []),
+	'abcd_profile_name': (C.c_char_p, [C.c_int]),
+	'abcd_profile_enable': (None, [C.c_int]),
+	'abcd_profile_read': (C.c_int, [C.c_int, P(C.c_float), P(C.c_int)]),
 	'abcd_stft_logamp': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_i32p, c_i32p, P(PackedT), C.c_int, C.c_int, C.c_int,
 								c_f32p, C.c_float, C.c_float, c_f32p, C.c_int64, C.c_void_p]),
 	'abcd_enc_workspace_bytes': (C.c_size_t, [C.c_int] * 6),
@@ -164,6 +170,21 @@ def call(name, *args):
 	lib = load()
 	LAUNCH_COUNT += 1
 	check(getattr(lib, name)(*args), name)
+
+
+def profile_enable(on):
+	load().abcd_profile_enable(int(bool(on)))
+
+
+def profile_read_all():
+	"""{kernel group: (total milliseconds, launches)} of the spans recorded since the last read."""
+	lib = load()
+	out = {}
+	for i in range(lib.abcd_profile_groups()):
+		ms, n = C.c_float(0), C.c_int(0)
+		check(lib.abcd_profile_read(i, C.byref(ms), C.byref(n)), 'abcd_profile_read')
+		out[lib.abcd_profile_name(i).decode()] = (ms.value, n.value)
+	return out
 
 
 class Packed(object):

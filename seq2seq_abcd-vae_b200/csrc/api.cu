@@ -7,12 +7,51 @@
 #include "sgemm.cuh"
 #include "stft.cuh"
 
+int enc_max_clusters(int which, int* out);
+int dec_max_clusters(int which, int F, int* out);
+
 static thread_local char g_err[1024] = "";
 void abcd_set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ---- launch accounting and per-kernel-group event timing ---------------------------------------------
+#include <atomic>
+#include <mutex>
+#include <vector>
+static std::atomic<long long> g_launches{0};
+void abcd_note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+struct ProfSpan { cudaEvent_t a, b; };
+static std::vector<ProfSpan> g_spans[PROF_COUNT];
+static std::vector<cudaEvent_t> g_open[PROF_COUNT];
+static const char* const g_prof_names[PROF_COUNT] = {
+    "enc_fwd_kernel", "enc_bwd_kernel", "dec_fwd_kernel", "dec_bwd_kernel", "sgemm+colsum", "rowwise", "clip_sgd",
+    "stft_logamp", "philox"};
+
+void abcd_prof_begin(int id, cudaStream_t s) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    g_open[id].push_back(e);
+}
+void abcd_prof_end(int id, cudaStream_t s) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_open[id].empty()) return;
+    cudaEvent_t a = g_open[id].back();
+    g_open[id].pop_back();
+    cudaEvent_t b;
+    if (cudaEventCreate(&b) != cudaSuccess) { cudaEventDestroy(a); return; }
+    cudaEventRecord(b, s);
+    g_spans[id].push_back(ProfSpan{a, b});
 }
 
 static PackedMeta to_meta(const abcd_packed_t* pk) {
@@ -60,6 +99,34 @@ extern "C" {
 
 const char* abcd_last_error(void) { return g_err; }
 const char* abcd_version(void) { return "abcd_b200 0.1 (sm_100a, fp32 FFMA cluster-persistent recurrences)"; }
+
+// which: 0 enc_fwd, 1 enc_bwd, 2 dec_fwd, 3 dec_bwd -> number of co-resident clusters (or negative error)
+int abcd_max_active_clusters(int which, int F) {
+    int n = 0;
+    int rc = which < 2 ? enc_max_clusters(which, &n) : dec_max_clusters(which - 2, F, &n);
+    return rc == ABCD_OK ? n : rc;
+}
+long long abcd_launch_count(void) { return g_launches.load(); }
+int abcd_profile_groups(void) { return PROF_COUNT; }
+const char* abcd_profile_name(int id) { return (id >= 0 && id < PROF_COUNT) ? g_prof_names[id] : ""; }
+void abcd_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
+// Synchronises the recorded events, returns total milliseconds and span count of a group, and clears it.
+int abcd_profile_read(int id, float* total_ms, int* count) {
+    if (id < 0 || id >= PROF_COUNT) return ABCD_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    float tot = 0.f;
+    int n = 0;
+    for (auto& sp : g_spans[id]) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { tot += ms; ++n; }
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    g_spans[id].clear();
+    if (total_ms) *total_ms = tot;
+    if (count) *count = n;
+    return ABCD_OK;
+}
 
 int abcd_init(int device) {
     CUDA_TRY(cudaSetDevice(device));

@@ -42,6 +42,26 @@ void abcd_set_error(const char* fmt, ...);
         if (_r != ABCD_OK) return _r; \
     } while (0)
 
+// launch accounting + optional per-kernel-group CUDA-event timing (api.cu)
+void abcd_note_launch(int n);
+#define KERNEL_CHECK()                    \
+    do {                                  \
+        abcd_note_launch(1);              \
+        CUDA_TRY(cudaGetLastError());     \
+    } while (0)
+
+enum ProfId {
+    PROF_ENC_FWD = 0, PROF_ENC_BWD, PROF_DEC_FWD, PROF_DEC_BWD, PROF_GEMM, PROF_ROWWISE, PROF_OPTIM, PROF_STFT,
+    PROF_NOISE, PROF_COUNT
+};
+void abcd_prof_begin(int id, cudaStream_t s);
+void abcd_prof_end(int id, cudaStream_t s);
+struct ProfScope {
+    int id; cudaStream_t s;
+    ProfScope(int id_, cudaStream_t s_) : id(id_), s(s_) { abcd_prof_begin(id, s); }
+    ~ProfScope() { abcd_prof_end(id, s); }
+};
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Bump allocator over a caller-owned workspace blob (the library never allocates device memory).

@@ -17,8 +17,7 @@ using namespace rnn;
 
 namespace {
 
-constexpr int DEC_KC = 64;
-constexpr int DEC_LDA = DEC_KC + 4;
+constexpr size_t SMEM_MAX = 232448;   // 227 KB of dynamic shared memory per CTA on sm_100
 constexpr float LOG_2PI = 1.8378770664093453f;
 
 __host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
@@ -26,6 +25,7 @@ __host__ __device__ inline int xcols_per_cta(int F) { return (F + CL - 1) / CL; 
 
 struct DecK {
     int cell, F, Fp, n_tiles, B, T_max;
+    int kc;   // staged K-chunk of this launch (largest of 128/64/32 that fits beside the resident weights)
     int ld_eps, ld_gt;
     const int* batch_sizes; const int* offsets; const int* lengths;
     // parameters
@@ -52,10 +52,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
     float* Wg = smem;                         // [Fp+H][U*4]
     float* W1 = Wg + (Fp + H) * (U * 4);      // [H][2U]
     float* W3 = W1 + H * (2 * U);             // [2M][NC3]
-    float* stage0 = W3 + 2 * M * NC3;
-    float* stage1 = stage0 + ROWS * DEC_LDA;
-    float* red = stage1 + ROWS * DEC_LDA;     // 40 floats
-    const Stage st{stage0, stage1, DEC_LDA, DEC_KC};
+    const Stage st = make_stage(W3 + 2 * M * NC3, p.kc);
+    float* red = W3 + 2 * M * NC3 + stage_floats(p.kc);   // 40 floats
 
     const int tid = threadIdx.x;
     const int rank = (int)cluster_ctarank();
@@ -152,7 +150,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
             zero_acc(acc);
             auto rpx = [=](int r) -> const float* { return Xall + (prev_base + tile + (long)n_tiles * r) * Fp; };
             auto rph = [=](int r) -> const float* { return Hall + (prev_base + tile + (long)n_tiles * r) * ABCD_H; };
-            phase_gemm(acc, st, Fp, rpx, H, rph, na, Wg, U * 4, tm1, 1, tid);
+            phase_gemm<NTHREADS>(acc, st,Fp, rpx, H, rph, na, Wg, U * 4, tm1, 1, tid);
 #pragma unroll
             for (int i = 0; i < RT; ++i) {
                 int r = tm1.rg + i * RG;
@@ -188,7 +186,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
             float acc[RT][4];
             zero_acc(acc);
             auto rph = [=](int r) -> const float* { return Hall + ((long)B + off_t + tile + (long)n_tiles * r) * ABCD_H; };
-            phase_gemm(acc, st, H, rph, 0, NullRow(), na, W1, 2 * U, tm2, KS2, tid);
+            phase_gemm<NTHREADS>(acc, st,H, rph, 0, NullRow(), na, W1, 2 * U, tm2, KS2, tid);
             if (tm2.active && tm2.ks == 0) {
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
@@ -210,7 +208,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
             float acc[RT][4];
             zero_acc(acc);
             auto rph = [=](int r) -> const float* { return Hid + (off_t + tile + (long)n_tiles * r) * (2 * ABCD_M); };
-            phase_gemm(acc, st, 2 * M, rph, 0, NullRow(), na, W3, NC3, tm3, KS3, tid);
+            phase_gemm<NTHREADS>(acc, st,2 * M, rph, 0, NullRow(), na, W3, NC3, tm3, KS3, tid);
             if (tm3.active && tm3.ks == 0) {
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
@@ -258,9 +256,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
     float* WB1 = WB2 + 2 * M * U;             // [4H][NCB1]
     float* dh_sm = WB1 + 4 * H * NCB1;        // [ROWS][U]
     float* dc_sm = dh_sm + ROWS * U;          // [ROWS][U]
-    float* stage0 = dc_sm + ROWS * U;
-    float* stage1 = stage0 + ROWS * DEC_LDA;
-    const Stage st{stage0, stage1, DEC_LDA, DEC_KC};
+    const Stage st = make_stage(dc_sm + ROWS * U, p.kc);
 
     const int tid = threadIdx.x;
     const int rank = (int)cluster_ctarank();
@@ -323,7 +319,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
             float acc[RT][4];
             zero_acc(acc);
             auto rp = [=](int r) -> const float* { return dML + (off_t + tile + (long)n_tiles * r) * (2 * Fp); };
-            phase_gemm(acc, st, 2 * Fp, rp, 0, NullRow(), na, WB3, 2 * U, tm3, KS3, tid);
+            phase_gemm<NTHREADS>(acc, st,2 * Fp, rp, 0, NullRow(), na, WB3, 2 * U, tm3, KS3, tid);
             if (tm3.active && tm3.ks == 0) {
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
@@ -347,7 +343,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
             float acc[RT][4];
             zero_acc(acc);
             auto rp = [=](int r) -> const float* { return dHidPre + (off_t + tile + (long)n_tiles * r) * (2 * ABCD_M); };
-            phase_gemm(acc, st, 2 * M, rp, 0, NullRow(), na, WB2, U, tm2, KS2, tid);
+            phase_gemm<NTHREADS>(acc, st,2 * M, rp, 0, NullRow(), na, WB2, U, tm2, KS2, tid);
             if (tm2.active && tm2.ks == 0) {
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
@@ -403,7 +399,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
             float acc[RT][4];
             zero_acc(acc);
             auto rp = [=](int r) -> const float* { return dG + (off_t + tile + (long)n_tiles * r) * (4 * ABCD_H); };
-            phase_gemm(acc, st, 4 * H, rp, 0, NullRow(), na, WB1, NCB1, tm1, KS1, tid);
+            phase_gemm<NTHREADS>(acc, st,4 * H, rp, 0, NullRow(), na, WB1, NCB1, tm1, KS1, tid);
             if (tm1.active && tm1.ks == 0) {
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
@@ -540,14 +536,23 @@ __global__ void unpad_copy_kernel(long rows, int F, int ld_src, const float* __r
     }
 }
 
-size_t dec_fwd_smem(int F) {
+size_t dec_fwd_fixed_floats(int F) {   // resident weights + reduction scratch
     int Fp = pad4(F), XC = xcols_per_cta(F), NC3 = ((XC + 1) / 2) * 4;
-    return (size_t)((Fp + ABCD_H) * U * 4 + ABCD_H * 2 * U + 2 * ABCD_M * NC3 + 2 * ROWS * DEC_LDA + 64) * sizeof(float);
+    return (size_t)((Fp + ABCD_H) * U * 4 + ABCD_H * 2 * U + 2 * ABCD_M * NC3 + 64);
 }
-size_t dec_bwd_smem(int F) {
+size_t dec_bwd_fixed_floats(int F) {   // resident weights + dh/dc carries
     int Fp = pad4(F), XC = xcols_per_cta(F), NCB1 = U + pad4(XC);
-    return (size_t)(2 * Fp * 2 * U + 2 * ABCD_M * U + 4 * ABCD_H * NCB1 + 2 * ROWS * U + 2 * ROWS * DEC_LDA) * sizeof(float);
+    return (size_t)(2 * Fp * 2 * U + 2 * ABCD_M * U + 4 * ABCD_H * NCB1 + 2 * ROWS * U);
 }
+int pick_kc(size_t fixed_floats) {
+    for (int kc : {128, 64, 32})
+        if ((fixed_floats + stage_floats(kc)) * sizeof(float) <= SMEM_MAX) return kc;
+    return 0;
+}
+int dec_fwd_kc(int F) { return pick_kc(dec_fwd_fixed_floats(F)); }
+int dec_bwd_kc(int F) { return pick_kc(dec_bwd_fixed_floats(F)); }
+size_t dec_fwd_smem(int F) { return (dec_fwd_fixed_floats(F) + stage_floats(dec_fwd_kc(F))) * sizeof(float); }
+size_t dec_bwd_smem(int F) { return (dec_bwd_fixed_floats(F) + stage_floats(dec_bwd_kc(F))) * sizeof(float); }
 constexpr int DEC_MAX_F = 129;
 
 template <class K>
@@ -562,6 +567,7 @@ int launch_cluster_dec(K kernel, int n_clusters, size_t smem, cudaStream_t strea
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    abcd_note_launch(1);
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, params));
     return ABCD_OK;
 }
@@ -641,11 +647,17 @@ int check_dec(const DecParams& P) {
 
 }  // namespace
 
+int rnn_max_active_clusters(const void* fn, size_t smem, int cluster, int threads, int* out);
+int dec_max_clusters(int which, int F, int* out) {
+    const void* fn = which == 0 ? (const void*)dec_fwd_kernel<0> : (const void*)dec_bwd_kernel<0>;
+    return rnn_max_active_clusters(fn, which == 0 ? dec_fwd_smem(F) : dec_bwd_smem(F), CL, NTHREADS, out);
+}
+
 int dec_init() {
-    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0>, dec_fwd_smem(DEC_MAX_F)));
-    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1>, dec_fwd_smem(DEC_MAX_F)));
-    TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<0>, dec_bwd_smem(DEC_MAX_F)));
-    TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<1>, dec_bwd_smem(DEC_MAX_F)));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0>, SMEM_MAX));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1>, SMEM_MAX));
+    TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<0>, SMEM_MAX));
+    TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<1>, SMEM_MAX));
     return ABCD_OK;
 }
 
@@ -673,16 +685,21 @@ int dec_forward(const DecParams& P, const PackedMeta& pk, const float* feat_in, 
     g.C = w.hc0; g.ldc = hc; g.bias = P.b_f2h;
     TRY(sgemm_launch(g, stream));
     split_hc0_kernel<<<(pk.B * H + 255) / 256, 256, 0, stream>>>(P.cell, pk.B, w.hc0, w.Hall, w.Call);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     CUDA_TRY(cudaMemsetAsync(w.Xall, 0, (size_t)(pk.B + pk.sumT) * Fp * sizeof(float), stream));
 
     DecK k = make_k(P, pk, w);
     k.eps = eps; k.ld_eps = ld_eps; k.gt = gt; k.ld_gt = ld_gt;
-    if (P.cell == 0) TRY(launch_cluster_dec(dec_fwd_kernel<0>, n_tiles, dec_fwd_smem(P.F), stream, k));
-    else TRY(launch_cluster_dec(dec_fwd_kernel<1>, n_tiles, dec_fwd_smem(P.F), stream, k));
+    k.kc = dec_fwd_kc(P.F);
+    ARG_CHECK(k.kc > 0, "decoder: weights for output_size %d do not fit in shared memory", P.F);
+    {
+        ProfScope ps(PROF_DEC_FWD, stream);
+        if (P.cell == 0) TRY(launch_cluster_dec(dec_fwd_kernel<0>, n_tiles, dec_fwd_smem(P.F), stream, k));
+        else TRY(launch_cluster_dec(dec_fwd_kernel<1>, n_tiles, dec_fwd_smem(P.F), stream, k));
+    }
     if (gt && losses) {
         final_sum_kernel<<<1, 256, 0, stream>>>(w.nll_partial, n_tiles * CL, losses + 0);
-        CUDA_TRY(cudaGetLastError());
+        KERNEL_CHECK();
     }
     // offset predictor over all frames (model.py:191)
     g = gemm_args_zero();
@@ -692,17 +709,17 @@ int dec_forward(const DecParams& P, const PackedMeta& pk, const float* feat_in, 
     g.C = w.HidOff; g.ldc = M; g.bias = P.off_b1; g.act = 1;
     TRY(sgemm_launch(g, stream));
     offset_head_kernel<<<BCE_BLOCKS, 256, 0, stream>>>(pk.sumT, w.HidOff, P.off_w2, P.off_b2, is_offset, w.OffLogit, w.bce_partial);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     if (is_offset && losses) {
         final_sum_kernel<<<1, 256, 0, stream>>>(w.bce_partial, BCE_BLOCKS, losses + 1);
-        CUDA_TRY(cudaGetLastError());
+        KERNEL_CHECK();
     }
     const int cp_blocks = 592;
     if (out_x) unpad_copy_kernel<<<cp_blocks, 256, 0, stream>>>(pk.sumT, P.F, Fp, w.Xall + (size_t)pk.B * Fp, out_x);
     if (out_mean) unpad_copy_kernel<<<cp_blocks, 256, 0, stream>>>(pk.sumT, P.F, Fp, w.Mean, out_mean);
     if (out_logvar) unpad_copy_kernel<<<cp_blocks, 256, 0, stream>>>(pk.sumT, P.F, Fp, w.Lv, out_logvar);
     if (out_offset_logit) CUDA_TRY(cudaMemcpyAsync(out_offset_logit, w.OffLogit, (size_t)pk.sumT * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     return ABCD_OK;
 }
 
@@ -715,15 +732,16 @@ int dec_backward(const DecParams& P, const DecGrads& G, const PackedMeta& pk, co
     const int hc = P.cell == 0 ? 2 * H : H;
     DecWs w = dec_carve(ws, ws_bytes, P.cell, P.F, P.fin, pk.B, pk.sumT);
     if (w.bytes > ws_bytes) { abcd_set_error("decoder bwd: workspace too small"); return ABCD_ERR_WORKSPACE; }
+    ColsumScratch colsum_scratch(w.partials, w.partial_floats);
     const int n_tiles = (pk.B + ROWS - 1) / ROWS;
     const int sumT = pk.sumT;
     const float* Hfr = w.Hall + (size_t)pk.B * H;   // h of frame n
 
     // ---- loss-head gradients over all frames ----
     nll_grad_kernel<<<592, 256, 0, stream>>>(sumT, F, Fp, w.Mean, w.Lv, gt, ld_gt, g_losses, w.dML);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     offset_head_bwd_kernel<<<592, 256, 0, stream>>>(sumT, w.HidOff, P.off_w2, w.OffLogit, is_offset, g_losses, w.dLogit, w.dHidOffPre);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     GemmArgs g = gemm_args_zero();   // dHoff = dHidOffPre * off_w1
     g.M = sumT; g.N = H; g.K = M;
     g.A = w.dHidOffPre; g.lda = M; g.a_kmajor = 1;
@@ -734,12 +752,17 @@ int dec_backward(const DecParams& P, const DecGrads& G, const PackedMeta& pk, co
     // ---- BPTT ----
     DecK k = make_k(P, pk, w);
     k.eps = eps; k.ld_eps = ld_eps; k.gt = gt; k.ld_gt = ld_gt;
-    if (P.cell == 0) TRY(launch_cluster_dec(dec_bwd_kernel<0>, n_tiles, dec_bwd_smem(P.F), stream, k));
-    else TRY(launch_cluster_dec(dec_bwd_kernel<1>, n_tiles, dec_bwd_smem(P.F), stream, k));
+    k.kc = dec_bwd_kc(P.F);
+    ARG_CHECK(k.kc > 0, "decoder bwd: weights for output_size %d do not fit in shared memory", P.F);
+    {
+        ProfScope ps(PROF_DEC_BWD, stream);
+        if (P.cell == 0) TRY(launch_cluster_dec(dec_bwd_kernel<0>, n_tiles, dec_bwd_smem(P.F), stream, k));
+        else TRY(launch_cluster_dec(dec_bwd_kernel<1>, n_tiles, dec_bwd_smem(P.F), stream, k));
+    }
 
     // ---- weight gradients: reductions over all packed frames ----
     dec_prev_index_kernel<<<min(pk.T_max, 592), 128, 0, stream>>>(pk.T_max, pk.B, pk.batch_sizes, pk.offsets, w.prev);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     auto tn = [&](int Mo, int No, const float* A, long lda, const float* Bm, long ldb, const int* gather, GateMap md,
                   float* C, long ldc, int Kred) -> int {
         GemmArgs q = gemm_args_zero();

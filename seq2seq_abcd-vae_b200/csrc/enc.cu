@@ -14,8 +14,13 @@ using namespace rnn;
 
 namespace {
 
-constexpr int ENC_KC = 128;
-constexpr int ENC_LDA = ENC_KC + 4;
+// The encoder runs 8-CTA clusters (32 hidden units and 512 threads per CTA): 2 directions x 7 row tiles = 14
+// clusters are resident together, where 16-CTA clusters would need two waves.
+constexpr int ENC_CL = 8;
+constexpr int ENC_U = ABCD_H / ENC_CL;
+constexpr int ENC_NT = RG * ENC_U;
+constexpr int ENC_KC_FWD = 128;
+constexpr int ENC_KC_BWD = 64;
 
 // -------------------------------------------------------------------------------------------------
 // small helper kernels
@@ -61,12 +66,11 @@ struct EncFwdK {
 };
 
 template <int CELL>
-__global__ void __launch_bounds__(NTHREADS, 1) enc_fwd_kernel(EncFwdK p) {
+__global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
+    constexpr int CL = ENC_CL, U = ENC_U, NTHREADS = ENC_NT;   // 8-CTA clusters, 32 units per CTA, 512 threads
     extern __shared__ __align__(16) float smem[];
     float* Wsm = smem;                          // [H][U*4]
-    float* stage0 = Wsm + ABCD_H * (U * 4);
-    float* stage1 = stage0 + ROWS * ENC_LDA;
-    const Stage st{stage0, stage1, ENC_LDA, ENC_KC};
+    const Stage st = make_stage(Wsm + ABCD_H * (U * 4), ENC_KC_FWD);
 
     const int tid = threadIdx.x;
     const int rank = (int)cluster_ctarank();
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) enc_fwd_kernel(EncFwdK p) {
                 long row = save ? (long)off_prev + b : (long)((s - 1) & 1) * B + b;
                 return hs + row * ABCD_H;
             };
-            phase_gemm(acc, st, H, rp, 0, NullRow(), na, Wsm, U * 4, tm, 1, tid);
+            phase_gemm<ENC_NT>(acc, st, H, rp, 0, NullRow(), na, Wsm, U * 4, tm, 1, tid);
         }
 #pragma unroll
         for (int i = 0; i < RT; ++i) {
@@ -194,15 +198,14 @@ struct EncBwdK {
 };
 
 template <int CELL>
-__global__ void __launch_bounds__(NTHREADS, 1) enc_bwd_kernel(EncBwdK p) {
+__global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
+    constexpr int CL = ENC_CL, U = ENC_U, NTHREADS = ENC_NT;
     extern __shared__ __align__(16) float smem[];
     const int H = ABCD_H;
     float* Wsm = smem;                       // [4H][U]: Wsm[uu*4+slot][j] = W_hh[gate(slot)*H+uu][u0+j]
     float* dh_sm = Wsm + 4 * H * U;          // [ROWS][U] recurrent dh carried to the next (earlier) step
     float* dc_sm = dh_sm + ROWS * U;         // [ROWS][U] LSTM: dc carry; GRU: direct dh*z carry
-    float* stage0 = dc_sm + ROWS * U;
-    float* stage1 = stage0 + ROWS * ENC_LDA;
-    const Stage st{stage0, stage1, ENC_LDA, ENC_KC};
+    const Stage st = make_stage(dc_sm + ROWS * U, ENC_KC_BWD);
 
     const int tid = threadIdx.x;
     const int rank = (int)cluster_ctarank();
@@ -230,8 +233,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) enc_bwd_kernel(EncBwdK p) {
         int b = tile + p.n_tiles * (prg + i * RG);
         len[i] = b < p.B ? p.lengths[b] : 0;
     }
-    const ThreadMap tm = make_map(tid, U / 4, pick_ks(U / 4));
-    const int KS = pick_ks(U / 4);
+    const int KS = pick_ks(U / 4, NTHREADS);
+    const ThreadMap tm = make_map(tid, U / 4, KS);
     const int Tt = p.lengths[tile];
     const float* gs = p.gs[dir];
     const float* cs = p.cs[dir];
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) enc_bwd_kernel(EncBwdK p) {
             zero_acc(acc);
             const int n_tiles = p.n_tiles;
             auto rp = [=](int r) -> const float* { return dg + ((long)off_t + tile + (long)n_tiles * r) * (4 * ABCD_H); };
-            phase_gemm(acc, st, 4 * H, rp, 0, NullRow(), na_src, Wsm, U, tm, KS, tid);
+            phase_gemm<ENC_NT>(acc, st, 4 * H, rp, 0, NullRow(), na_src, Wsm, U, tm, KS, tid);
             if (tm.active && tm.ks == 0) {
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
@@ -309,21 +312,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) enc_bwd_kernel(EncBwdK p) {
     }
 }
 
-size_t enc_fwd_smem() { return (size_t)(ABCD_H * U * 4 + 2 * ROWS * ENC_LDA) * sizeof(float); }
-size_t enc_bwd_smem() { return (size_t)(4 * ABCD_H * U + 2 * ROWS * U + 2 * ROWS * ENC_LDA) * sizeof(float); }
+size_t enc_fwd_smem() { return (size_t)(ABCD_H * ENC_U * 4 + stage_floats(ENC_KC_FWD)) * sizeof(float); }
+size_t enc_bwd_smem() { return (size_t)(4 * ABCD_H * ENC_U + 2 * ROWS * ENC_U + stage_floats(ENC_KC_BWD)) * sizeof(float); }
 
 template <class K, class P>
 int launch_cluster(K kernel, int n_clusters, size_t smem, cudaStream_t stream, const P& params) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(n_clusters * CL);
-    cfg.blockDim = dim3(NTHREADS);
+    cfg.gridDim = dim3(n_clusters * ENC_CL);
+    cfg.blockDim = dim3(ENC_NT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = ENC_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    abcd_note_launch(1);
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, params));
     return ABCD_OK;
 }
@@ -334,6 +338,25 @@ int rnn_prepare_kernel(const void* fn, size_t smem) {
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     return ABCD_OK;
+}
+
+// How many clusters of `fn` can be resident at once (diagnostics; DESIGN.md "cluster residency").
+int rnn_max_active_clusters(const void* fn, size_t smem, int cluster, int threads, int* out) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(cluster * 64);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveClusters(out, fn, &cfg));
+    return ABCD_OK;
+}
+int enc_max_clusters(int which, int* out) {
+    const void* fn = which == 0 ? (const void*)enc_fwd_kernel<0> : (const void*)enc_bwd_kernel<0>;
+    return rnn_max_active_clusters(fn, which == 0 ? enc_fwd_smem() : enc_bwd_smem(), ENC_CL, ENC_NT, out);
 }
 
 int enc_init() {
@@ -410,7 +433,7 @@ int enc_forward(const EncParams& P, const PackedMeta& pk, const float* x, int ld
     k.out = last_hidden;
     for (int d = 0; d < ndirs; ++d) {
         combine_bias_kernel<<<(4 * H + 255) / 256, 256, 0, stream>>>(P.cell, P.b_ih[d], P.b_hh[d], w.bias_comb[d]);
-        CUDA_TRY(cudaGetLastError());
+        KERNEL_CHECK();
         GemmArgs g = gemm_args_zero();
         g.M = pk.sumT; g.N = 4 * H; g.K = P.F;
         g.A = x; g.lda = ldx; g.a_kmajor = 1;
@@ -423,8 +446,11 @@ int enc_forward(const EncParams& P, const PackedMeta& pk, const float* x, int ld
         k.xproj[d] = w.xproj[d]; k.hs[d] = w.hs[d]; k.gs[d] = w.gs[d]; k.cs[d] = w.cs[d];
     }
     (void)ngates;
-    if (P.cell == 0) TRY(launch_cluster(enc_fwd_kernel<0>, n_tiles * ndirs, enc_fwd_smem(), stream, k));
-    else TRY(launch_cluster(enc_fwd_kernel<1>, n_tiles * ndirs, enc_fwd_smem(), stream, k));
+    {
+        ProfScope ps(PROF_ENC_FWD, stream);
+        if (P.cell == 0) TRY(launch_cluster(enc_fwd_kernel<0>, n_tiles * ndirs, enc_fwd_smem(), stream, k));
+        else TRY(launch_cluster(enc_fwd_kernel<1>, n_tiles * ndirs, enc_fwd_smem(), stream, k));
+    }
     return ABCD_OK;
 }
 
@@ -435,6 +461,7 @@ int enc_backward(const EncParams& P, const EncGrads& G, const PackedMeta& pk, co
     const int H = ABCD_H;
     EncWs w = enc_carve(ws, ws_bytes, P.cell, P.F, pk.B, pk.sumT, ndirs, 1);
     if (w.bytes > ws_bytes) { abcd_set_error("encoder bwd: workspace too small"); return ABCD_ERR_WORKSPACE; }
+    ColsumScratch colsum_scratch(w.partials, w.partial_floats);
     const int n_tiles = (pk.B + ROWS - 1) / ROWS;
 
     EncBwdK k;
@@ -446,11 +473,14 @@ int enc_backward(const EncParams& P, const EncGrads& G, const PackedMeta& pk, co
     for (int d = 0; d < ndirs; ++d) {
         k.w_hh[d] = P.w_hh[d]; k.hs[d] = w.hs[d]; k.gs[d] = w.gs[d]; k.cs[d] = w.cs[d]; k.dg[d] = w.dg[d];
     }
-    if (P.cell == 0) TRY(launch_cluster(enc_bwd_kernel<0>, n_tiles * ndirs, enc_bwd_smem(), stream, k));
-    else TRY(launch_cluster(enc_bwd_kernel<1>, n_tiles * ndirs, enc_bwd_smem(), stream, k));
+    {
+        ProfScope ps(PROF_ENC_BWD, stream);
+        if (P.cell == 0) TRY(launch_cluster(enc_bwd_kernel<0>, n_tiles * ndirs, enc_bwd_smem(), stream, k));
+        else TRY(launch_cluster(enc_bwd_kernel<1>, n_tiles * ndirs, enc_bwd_smem(), stream, k));
+    }
 
     prev_index_kernel<<<min(pk.T_max, 592), 128, 0, stream>>>(pk.T_max, pk.batch_sizes, pk.offsets, w.prev_fwd, w.prev_bwd);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     for (int d = 0; d < ndirs; ++d) {
         const GateMap map_ih = P.cell == 0 ? gate_map(H, 0, 1, 2, 3) : gate_map(H, 0, 1, 2, -1);
         const GateMap map_hh = P.cell == 0 ? gate_map(H, 0, 1, 2, 3) : gate_map(H, 0, 1, -1, 2);

@@ -126,20 +126,22 @@ int gradnorm_clip_sgd(float* params, float* grads, float* momentum_buf, long n, 
     ARG_CHECK(((uintptr_t)params % 16 == 0) && ((uintptr_t)grads % 16 == 0) && (!momentum_buf || (uintptr_t)momentum_buf % 16 == 0),
               "gradnorm_clip_sgd: arenas must be 16-byte aligned");
     if (n <= 0) return ABCD_OK;
+    ProfScope ps(PROF_OPTIM, stream);
     sumsq_kernel<<<OPT_BLOCKS, OPT_THREADS, 0, stream>>>(grads, n, partial);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     clip_sgd_kernel<<<OPT_BLOCKS, OPT_THREADS, 0, stream>>>(params, grads, momentum_buf, n, lr, momentum, max_norm,
                                                           zero_grads, partial, OPT_BLOCKS, norm_out);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     return ABCD_OK;
 }
 
 int philox_fill(float* out, long n, unsigned long long seed, unsigned long long offset, int kind, cudaStream_t stream) {
     if (n <= 0) return ABCD_OK;
+    ProfScope ps(PROF_NOISE, stream);
     long n4 = (n + 3) >> 2;
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     philox_kernel<<<blocks, 256, 0, stream>>>(out, n, (uint64_t)seed, (uint64_t)offset, kind);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     return ABCD_OK;
 }

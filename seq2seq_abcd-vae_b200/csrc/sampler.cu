@@ -350,7 +350,7 @@ int mlp_backward(const MlpParams& P, const MlpGrads& G, int rows, const float* x
     g.C = scratch; g.ldc = P.hidden;
     TRY(sgemm_launch(g, stream));
     tanh_bwd_kernel<<<ROW_BLOCKS * 2, 256, 0, stream>>>((long)rows * P.hidden, scratch, hid);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     g = gemm_args_zero();            // dW1 += dpre^T x
     g.M = P.hidden; g.N = P.in; g.K = rows;
     g.A = scratch; g.lda = P.hidden; g.a_kmajor = 0;
@@ -411,7 +411,7 @@ int sampler_sample_forward(const SamplerParams& P, int B, const float* logits, i
                            float* y, float* features, cudaStream_t stream) {
     ARG_CHECK(mode == 0 || noise, "sampler: Gumbel mode needs a noise buffer");
     sample_rows_kernel<<<ROW_BLOCKS, 256, 0, stream>>>(B, P.K, logits, mode, mode ? 1.f / tau : 1.f, noise, y);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     GemmArgs g = gemm_args_zero();   // features = y codebook^T
     g.M = B; g.N = P.f; g.K = P.K;
     g.A = y; g.lda = P.K; g.a_kmajor = 1;
@@ -438,7 +438,7 @@ int sampler_sample_backward(const SamplerParams& P, const SamplerGrads& G, int B
     g.C = dy; g.ldc = P.K;
     TRY(sgemm_launch(g, stream));
     sample_rows_bwd_kernel<<<ROW_BLOCKS, 256, 0, stream>>>(B, P.K, y, dy, mode ? 1.f / tau : 1.f, dlogits);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     return ABCD_OK;
 }
 
@@ -456,11 +456,11 @@ int sampler_kl_forward(const SamplerParams& P, int B, const float* logits, float
     float *E, *s, *Q, *partial; double* prior;
     kl_ws(ws, P.K, &E, &s, &Q, &partial, &prior);
     dirichlet_kernel<<<1, 256, 0, stream>>>(P.K, P.shape_logits, P.prior_c, n_data, E, s, prior);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     kl_rows_kernel<<<ROW_BLOCKS, 256, 0, stream>>>(B, P.K, logits, E, partial);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     kl_final_kernel<<<1, 256, 0, stream>>>(ROW_BLOCKS, partial, prior, (float)B / n_data, kl_out);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     return ABCD_OK;
 }
 
@@ -470,38 +470,38 @@ int sampler_kl_backward(const SamplerParams& P, const SamplerGrads& G, int B, co
     kl_ws(ws, P.K, &E, &s, &Q, &partial, &prior);
     CUDA_TRY(cudaMemsetAsync(Q, 0, (size_t)P.K * sizeof(float), stream));
     kl_rows_bwd_kernel<<<ROW_BLOCKS, 256, 0, stream>>>(B, P.K, logits, E, g_kl, dlogits, Q);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     kl_shape_bwd_kernel<<<1, 256, 0, stream>>>(P.K, B, s, Q, P.prior_c, n_data, g_kl, G.shape_logits);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     return ABCD_OK;
 }
 
 int sampler_stats(int B, int K, const float* logits, const float* shape_logits, float* scratch_K, float* out3,
                   cudaStream_t stream) {
     stats_kernel<<<1, 256, 0, stream>>>(B, K, logits, shape_logits, scratch_K, out3);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     return ABCD_OK;
 }
 
 int softmax_argmax(int B, int K, const float* logits, float* probs, int* argmax, cudaStream_t stream) {
     softmax_argmax_kernel<<<ROW_BLOCKS, 256, 0, stream>>>(B, K, logits, probs, argmax);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     return ABCD_OK;
 }
 
 int gauss_latent_forward(long n, const float* mean, const float* lv, const float* eps, float* z, float* kl_out,
                          float* partial /*ROW_BLOCKS floats*/, cudaStream_t stream) {
     gauss_fwd_kernel<<<ROW_BLOCKS, 256, 0, stream>>>(n, mean, lv, eps, z, partial);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     if (kl_out) {
         sum_partials_kernel<<<1, 256, 0, stream>>>(ROW_BLOCKS, partial, kl_out);
-        CUDA_TRY(cudaGetLastError());
+        KERNEL_CHECK();
     }
     return ABCD_OK;
 }
 int gauss_latent_backward(long n, const float* mean, const float* lv, const float* eps, const float* dz,
                           const float* g_kl, float* dmean, float* dlv, cudaStream_t stream) {
     gauss_bwd_kernel<<<ROW_BLOCKS, 256, 0, stream>>>(n, mean, lv, eps, dz, g_kl, dmean, dlv);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     return ABCD_OK;
 }

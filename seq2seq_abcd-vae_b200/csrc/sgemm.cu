@@ -201,21 +201,43 @@ sgemm_kernel(GemmArgs g, int a_vec, int b_vec) {
     for (int i = 0; i < TM; ++i) {
         const int m = m0 + (i / 4) * (TYN * 4) + ty * 4 + (i % 4);
         if (m >= g.M) continue;
+        const int mrow = ksplit > 1 ? m : gate_src_row(g.m_dst, m);
+        if (mrow < 0) continue;
 #pragma unroll
-        for (int j = 0; j < TN; ++j) {
-            const int n = n0 + (j / 4) * (TXN * 4) + tx * 4 + (j % 4);
-            if (n >= g.N) continue;
+        for (int gq = 0; gq < NG; ++gq) {
+            const int nb = n0 + gq * (TXN * 4) + tx * 4;   // 4 consecutive output columns
+            if (nb >= g.N) continue;
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = acc[i][gq * 4 + q];
+            float* dst;
             if (ksplit > 1) {
-                g.partials[((long)blockIdx.z * g.M + m) * g.N + n] = acc[i][j];
+                dst = g.partials + ((long)blockIdx.z * g.M + m) * g.N + nb;
             } else {
-                int mrow = gate_src_row(g.m_dst, m);
-                if (mrow < 0) continue;
-                float v = g.alpha * acc[i][j];
-                if (g.bias) v += g.bias_on_m ? g.bias[mrow] : g.bias[gate_src_row(g.b_nsrc, n) < 0 ? 0 : gate_src_row(g.b_nsrc, n)];
-                if (g.act == 1) v = tanhf(v);
-                float* dst = g.C + (long)mrow * g.ldc + n;
-                if (g.accumulate) v += *dst;
-                *dst = v;
+                dst = g.C + (long)mrow * g.ldc + nb;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float t = g.alpha * v[q];
+                    if (g.bias && nb + q < g.N) {
+                        int bi = g.bias_on_m ? mrow : gate_src_row(g.b_nsrc, nb + q);
+                        t += g.bias[bi < 0 ? 0 : bi];
+                    }
+                    if (g.act == 1) t = tanhf(t);
+                    v[q] = t;
+                }
+            }
+            const bool vec = (nb + 3 < g.N) && (((uintptr_t)dst & 15) == 0);
+            if (vec) {
+                float4 o = make_float4(v[0], v[1], v[2], v[3]);
+                if (ksplit == 1 && g.accumulate) {
+                    float4 old = *reinterpret_cast<const float4*>(dst);
+                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *reinterpret_cast<float4*>(dst) = o;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (nb + q < g.N) dst[q] = (ksplit == 1 && g.accumulate) ? dst[q] + v[q] : v[q];
             }
         }
     }
@@ -241,26 +263,46 @@ __global__ void splitk_reduce_kernel(GemmArgs g) {
     }
 }
 
+// Column sums (bias gradients).  blockIdx.x: 32-column strip, blockIdx.y: row split; 8 warps stride the rows of
+// the split, deterministic tree reduce in shared memory.  With gridDim.y > 1 the per-split sums go to
+// scratch[y][cols] and colsum_finish_kernel adds them in a fixed order.
 __global__ void colsum_kernel(const float* __restrict__ A, long lda, int rows, int cols, float alpha,
-                              float* __restrict__ out, int accumulate, GateMap dst) {
-    // one block per 32 columns, 8 warps striding rows; deterministic tree reduce in shared memory
+                              float* __restrict__ out, int accumulate, GateMap dst, float* __restrict__ scratch) {
     __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int w = threadIdx.x >> 5;
+    const int per = (rows + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
     float s = 0.f;
     if (c < cols)
-        for (int r = w; r < rows; r += 8) s += A[(long)r * lda + c];
+        for (int r = r0 + w; r < r1; r += 8) s += A[(long)r * lda + c];
     red[w][threadIdx.x & 31] = s;
     __syncthreads();
     if (w == 0 && c < cols) {
         float t = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
-        int d = gate_src_row(dst, c);
-        if (d >= 0) {
-            t *= alpha;
-            out[d] = accumulate ? out[d] + t : t;
+        if (gridDim.y > 1) {
+            scratch[(long)blockIdx.y * cols + c] = t;
+        } else {
+            int d = gate_src_row(dst, c);
+            if (d >= 0) {
+                t *= alpha;
+                out[d] = accumulate ? out[d] + t : t;
+            }
         }
+    }
+}
+__global__ void colsum_finish_kernel(const float* __restrict__ scratch, int nsplit, int cols, float alpha,
+                                     float* __restrict__ out, int accumulate, GateMap dst) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float t = 0.f;
+    for (int y = 0; y < nsplit; ++y) t += scratch[(long)y * cols + c];
+    int d = gate_src_row(dst, c);
+    if (d >= 0) {
+        t *= alpha;
+        out[d] = accumulate ? out[d] + t : t;
     }
 }
 
@@ -275,11 +317,18 @@ int launch_cfg(const GemmArgs& g, int a_vec, int b_vec, cudaStream_t stream) {
         abcd_set_error("sgemm: (A m-major, B k-major) layout is not on the path");
         return ABCD_ERR_UNSUPPORTED;
     }
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     return ABCD_OK;
 }
 
 }  // namespace
+
+// 128x128 tiles only when they alone fill the GPU; otherwise 64x64 tiles (4x the CTAs, shorter K loops per CTA)
+static bool use_small_tiles(int M, int N, int splits) {
+    if (M <= 64 || N <= 64) return true;
+    long big = (long)((M + 127) / 128) * ((N + 127) / 128);
+    return big * splits < 74;
+}
 
 int sgemm_pick_splits(int M, int N, int K) {
     long tiles = (long)((M + 127) / 128) * ((N + 127) / 128);
@@ -299,10 +348,11 @@ int sgemm_launch(const GemmArgs& gin, cudaStream_t stream) {
     ARG_CHECK(g.splits == 1 || g.partials, "sgemm: split-K needs a partials workspace");
     ARG_CHECK(!(g.b_kgather && g.b_kmajor), "sgemm: k-gather needs n-major B");
     ARG_CHECK(!(g.b_nsrc.enabled && !g.b_kmajor), "sgemm: n source map needs k-major B");
+    ProfScope ps(PROF_GEMM, stream);
     const int a_vec = ((uintptr_t)g.A % 16 == 0) && (g.lda % 4 == 0);
     const int b_vec = ((uintptr_t)g.B % 16 == 0) && (g.ldb % 4 == 0);
     int r;
-    if (g.M <= 64 || g.N <= 64) r = launch_cfg<64, 64, 4, 4>(g, a_vec, b_vec, stream);
+    if (use_small_tiles(g.M, g.N, g.splits)) r = launch_cfg<64, 64, 4, 4>(g, a_vec, b_vec, stream);
     else r = launch_cfg<128, 128, 8, 8>(g, a_vec, b_vec, stream);
     if (r != ABCD_OK) return r;
     if (g.splits > 1) {
@@ -310,15 +360,36 @@ int sgemm_launch(const GemmArgs& gin, cudaStream_t stream) {
         int blocks = (int)((total + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
         splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(g);
-        CUDA_TRY(cudaGetLastError());
+        KERNEL_CHECK();
     }
     return ABCD_OK;
 }
 
+static thread_local float* t_colsum_scratch = nullptr;
+static thread_local size_t t_colsum_floats = 0;
+ColsumScratch::ColsumScratch(float* p, size_t floats) { t_colsum_scratch = p; t_colsum_floats = floats; }
+ColsumScratch::~ColsumScratch() { t_colsum_scratch = nullptr; t_colsum_floats = 0; }
+
 int colsum_launch(const float* A, long lda, int rows, int cols, float alpha, float* out, int accumulate,
                   GateMap dst, cudaStream_t stream) {
+    float* scratch = t_colsum_scratch;
+    const size_t scratch_floats = t_colsum_floats;
     if (cols <= 0) return ABCD_OK;
-    colsum_kernel<<<(cols + 31) / 32, 256, 0, stream>>>(A, lda, rows, cols, alpha, out, accumulate, dst);
-    CUDA_TRY(cudaGetLastError());
+    ProfScope ps(PROF_GEMM, stream);
+    const int strips = (cols + 31) / 32;
+    // enough row splits to cover the GPU (~4 CTAs/SM), at least 64 rows per split
+    int nsplit = 1;
+    if (scratch) {
+        nsplit = (148 * 4 + strips - 1) / strips;
+        if (nsplit > rows / 64) nsplit = rows / 64;
+        if ((size_t)nsplit * cols > scratch_floats) nsplit = (int)(scratch_floats / cols);
+        if (nsplit < 1) nsplit = 1;
+    }
+    colsum_kernel<<<dim3(strips, nsplit), 256, 0, stream>>>(A, lda, rows, cols, alpha, out, accumulate, dst, scratch);
+    KERNEL_CHECK();
+    if (nsplit > 1) {
+        colsum_finish_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(scratch, nsplit, cols, alpha, out, accumulate, dst);
+        KERNEL_CHECK();
+    }
     return ABCD_OK;
 }

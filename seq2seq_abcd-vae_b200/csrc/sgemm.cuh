@@ -54,5 +54,11 @@ int sgemm_launch(const GemmArgs& g, cudaStream_t stream);
 int sgemm_pick_splits(int M, int N, int K);
 
 // out[c] (+)= alpha * sum_r A[r*lda + c]  (bias gradients), with optional gate map on the column index.
+// A caller-owned scratch buffer (see ColsumScratch) enables a row-split two-pass reduction for tall inputs.
 int colsum_launch(const float* A, long lda, int rows, int cols, float alpha, float* out, int accumulate,
                   GateMap dst, cudaStream_t stream);
+// RAII: lends `floats` floats of the caller's workspace to colsum_launch calls made by this thread in this scope.
+struct ColsumScratch {
+    ColsumScratch(float* p, size_t floats);
+    ~ColsumScratch();
+};

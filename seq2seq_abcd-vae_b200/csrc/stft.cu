@@ -81,6 +81,7 @@ int stft_logamp(const void* wav, int is_i16, long n_samples, const int* onset, c
     ARG_CHECK(n_fft >= 2 && n_fft <= 4096 && hop >= 1, "stft: n_fft %d / hop %d unsupported", n_fft, hop);
     ARG_CHECK(wav && onset && nsamp && offsets && window && out, "stft: null argument");
     if (sumT <= 0) return ABCD_OK;
+    ProfScope ps(PROF_STFT, stream);
     StftK k;
     k.wav = wav; k.is_i16 = is_i16; k.n_samples = n_samples; k.onset = onset; k.nsamp = nsamp;
     k.offsets = offsets; k.T_max = T_max; k.sumT = sumT; k.B = B;
@@ -89,6 +90,6 @@ int stft_logamp(const void* wav, int is_i16, long n_samples, const int* onset, c
     int blocks = sumT < 148 * 16 ? sumT : 148 * 16;
     size_t smem = (size_t)3 * n_fft * sizeof(float);
     stft_logamp_kernel<<<blocks, 128, smem, stream>>>(k);
-    CUDA_TRY(cudaGetLastError());
+    KERNEL_CHECK();
     return ABCD_OK;
 }

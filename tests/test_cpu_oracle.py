@@ -121,3 +121,21 @@ def test_det_generators_are_stable():
 	np.testing.assert_allclose(u, O.det_uniform((4,), 123))
 	assert 0.0 < u.min() and u.max() < 1.0
 	assert len(set(np.round(u, 12))) == 4
+
+
+def test_batched_oracle_equals_per_sequence_oracle(abcd):
+	"""The time-major batched restatement (CPU-baseline timing path) is the same function."""
+	for name in ('train_lstm_gumbel', 'train_gru_speaker'):
+		cfg = CS.TRAIN_CASES[name]
+		mods = CS.build_modules(abcd.model, cfg)
+		enc_sd, smp_sd, dec_sd, seqs, eps, gumbel, speaker = CS.build_case(cfg, mods)
+		dt = torch.float64
+		cast = lambda d: {k: (v.to(dt) if v.dtype.is_floating_point else v) for k, v in d.items()}
+		args = (cast(enc_sd), cast(smp_sd), cast(dec_sd), [s.to(dt) for s in seqs], eps.to(dt), gumbel.to(dt),
+				cfg['N_data'], cfg['pretrain'], cfg['tau'], cfg['rnn'], 1.0, speaker)
+		a = O.train_step(*args)
+		b = O.train_step(*args, batched=True)
+		assert abs(a['loss'].item() - b['loss'].item()) < 1e-10 * abs(a['loss'].item())
+		for m in a['grads']:
+			for k in a['grads'][m]:
+				assert torch.allclose(a['grads'][m][k], b['grads'][m][k], atol=1e-10), (m, k)

@@ -1,0 +1,54 @@
+# coding: utf-8
+"""GPU diagnostics: cluster residency and per-kernel-group timing of one training step at several batch sizes.
+    python tools/diag.py [B ...]"""
+import importlib
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+	pkg = importlib.import_module('seq2seq_abcd-vae_b200')
+	learning = importlib.import_module('seq2seq_abcd-vae_b200.learning')
+	L = pkg._lib
+	from oracle import cases as CS
+	dev = torch.device('cuda', 0)
+	L.ensure_device(dev)
+	lib = L.load()
+	print('max active clusters (enc_fwd, enc_bwd, dec_fwd, dec_bwd) F=65:', [lib.abcd_max_active_clusters(i, 65) for i in range(4)],
+		' F=129:', [lib.abcd_max_active_clusters(i, 129) for i in range(4)])
+	sizes = [int(a) for a in sys.argv[1:]] or [64, 128, 256, 512]
+	for B in sizes:
+		lengths, bs, x, off = bench.make_batch(B, 65, 0)
+		learner = learning.Learner(65, 256, 256, 256, 128, 256, None, device='cuda:0')
+		for i, m in enumerate(learner._modules()):
+			m.load_state_dict({k: v.to(dev) for k, v in CS.det_state(m, 500 + i).items()})
+		learner.setup_optimizer(1.0, 0.0, gradient_clip=1.0)
+		p = torch.nn.utils.rnn.PackedSequence(x.to(dev), bs)
+		po = torch.nn.utils.rnn.PackedSequence(off.to(dev), bs)
+		for _ in range(3):
+			learner.train_step(p, po, None, 100000, False)
+		torch.cuda.synchronize()
+		L.profile_enable(True)
+		n = 5
+		e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+		e0.record()
+		for _ in range(n):
+			learner.train_step(p, po, None, 100000, False)
+		e1.record()
+		torch.cuda.synchronize()
+		L.profile_enable(False)
+		prof = L.profile_read_all()
+		T = int(lengths.max())
+		print('B={} sumT={} T_max={} step {:.2f} ms :: '.format(B, int(lengths.sum()), T, e0.elapsed_time(e1) / n) +
+			', '.join('{} {:.3f} ms ({:.1f} us/step)'.format(k, v[0] / n, v[0] / n / T * 1e3) for k, v in prof.items() if v[1]))
+
+
+if __name__ == '__main__':
+	main()
