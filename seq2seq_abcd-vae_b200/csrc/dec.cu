@@ -207,6 +207,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
         {
             float acc[RT][4];
             zero_acc(acc);
+            // noise and targets of this step's frames are fetched before the GEMM so their latency hides behind it
+            float ev[RT][2], gv[RT][2];
+            if (tm3.active && tm3.ks == 0) {
+#pragma unroll
+                for (int i = 0; i < RT; ++i) {
+                    int r = tm3.rg + i * RG;
+                    long frame = off_t + tile + (long)n_tiles * r;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        int c = xc0 + 2 * tm3.cg + j;
+                        bool ok = r < na && c < xc1;
+                        ev[i][j] = ok ? __ldg(p.eps + frame * p.ld_eps + c) : 0.f;
+                        gv[i][j] = (ok && p.gt) ? __ldg(p.gt + frame * p.ld_gt + c) : 0.f;
+                    }
+                }
+            }
             auto rph = [=](int r) -> const float* { return Hid + (off_t + tile + (long)n_tiles * r) * (2 * ABCD_M); };
             phase_gemm<NTHREADS>(acc, st,2 * M, rph, 0, NullRow(), na, W3, NC3, tm3, KS3, tid);
             if (tm3.active && tm3.ks == 0) {
@@ -221,13 +237,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
                         if (c >= xc1) continue;
                         float mean = acc[i][j] + bias3[j];
                         float lv = acc[i][2 + j] + bias3[2 + j];
-                        float e = p.eps[frame * p.ld_eps + c];
-                        float x = mean + expf(0.5f * lv) * e;
+                        float x = mean + expf(0.5f * lv) * ev[i][j];
                         p.Mean[frame * Fp + c] = mean;
                         p.Lv[frame * Fp + c] = lv;
                         p.Xall[((long)B + frame) * Fp + c] = x;
                         if (p.gt) {
-                            float d = p.gt[frame * p.ld_gt + c] - mean;
+                            float d = gv[i][j] - mean;
                             nll += 0.5f * (LOG_2PI + lv + d * expf(-lv) * d);
                         }
                     }
@@ -329,7 +344,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
                     int col = tm3.cg * 4;
                     int which = col / U, uu = col % U;
                     long o = frame * (2 * M) + which * M + u0 + uu;
-                    float4 hd = *reinterpret_cast<const float4*>(p.Hid + o);
+                    float4 hd = __ldg(reinterpret_cast<const float4*>(p.Hid + o));
                     float4 v = make_float4(acc[i][0] * (1.f - hd.x * hd.x), acc[i][1] * (1.f - hd.y * hd.y),
                                            acc[i][2] * (1.f - hd.z * hd.z), acc[i][3] * (1.f - hd.w * hd.w));
                     *reinterpret_cast<float4*>(p.dHidPre + o) = v;
@@ -342,6 +357,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
         {
             float acc[RT][4];
             zero_acc(acc);
+            // saved forward activations for the gate-gradient step: fetched now, consumed after the GEMM
+            float4 g4v[RT];
+            float cv[RT], pv[RT], hov[RT];
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+                int r = prg + i * RG;
+                g4v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                cv[i] = pv[i] = hov[i] = 0.f;
+                if (r >= na) continue;
+                long b = tile + (long)n_tiles * r;
+                long frame = off_t + b;
+                long prow = prev_base + b;
+                g4v[i] = __ldg(reinterpret_cast<const float4*>(p.Gs + frame * (4 * H) + unit * 4));
+                hov[i] = __ldg(p.dHoff + frame * H + unit);
+                if (CELL == 0) {
+                    cv[i] = __ldg(p.Call + ((long)B + frame) * H + unit);
+                    pv[i] = __ldg(p.Call + prow * H + unit);
+                } else {
+                    pv[i] = __ldg(p.Hall + prow * H + unit);
+                }
+            }
             auto rp = [=](int r) -> const float* { return dHidPre + (off_t + tile + (long)n_tiles * r) * (2 * ABCD_M); };
             phase_gemm<NTHREADS>(acc, st,2 * M, rp, 0, NullRow(), na, WB2, U, tm2, KS2, tid);
             if (tm2.active && tm2.ks == 0) {
@@ -360,16 +396,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
             for (int i = 0; i < RT; ++i) {
                 int r = prg + i * RG;
                 if (r >= na) continue;
-                long b = tile + (long)n_tiles * r;
-                long frame = off_t + b;
-                long prow = prev_base + b;
-                float dh = dh_sm[r * U + pu] + p.dHoff[frame * H + unit];
+                long frame = off_t + tile + (long)n_tiles * r;
+                float dh = dh_sm[r * U + pu] + hov[i];
                 float carry = dc_sm[r * U + pu];
-                const float4 g4 = *reinterpret_cast<const float4*>(p.Gs + frame * (4 * H) + unit * 4);
+                const float4 g4 = g4v[i];
                 float4 dgv;
                 if (CELL == 0) {
-                    float c = p.Call[((long)B + frame) * H + unit];
-                    float c_prev = p.Call[prow * H + unit];
+                    float c = cv[i];
+                    float c_prev = pv[i];
                     float tc = tanhf(c);
                     float ig = g4.x, fg = g4.y, gg = g4.z, og = g4.w;
                     float dc = carry + dh * og * (1.f - tc * tc);
@@ -380,7 +414,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
                     dc_sm[r * U + pu] = dc * fg;
                 } else {
                     dh += carry;
-                    float h_prev = p.Hall[prow * H + unit];
+                    float h_prev = pv[i];
                     float rg_ = g4.x, zg = g4.y, ng = g4.z, hn = g4.w;
                     float dn_pre = dh * (1.f - zg) * (1.f - ng * ng);
                     dgv.x = dn_pre * hn * rg_ * (1.f - rg_);
@@ -409,16 +443,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
                         *reinterpret_cast<float4*>(dh_sm + r * U + tm1.cg * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
                     } else if (t > 0) {
                         long pf = p.offsets[t - 1] + tile + (long)n_tiles * r;   // frame that produced x_t
+                        // loads of the 4 columns first, then the read-modify-writes (one round trip per row slot)
+                        float lvv[4], evv[4], m0[4], m1[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            int q = (tm1.cg - U / 4) * 4 + j;
+                            int c = xc0 + q;
+                            bool ok = q < XC && c < xc1;
+                            lvv[j] = ok ? __ldg(p.Lv + pf * Fp + c) : 0.f;
+                            evv[j] = ok ? __ldg(p.eps + pf * p.ld_eps + c) : 0.f;
+                            m0[j] = ok ? p.dML[pf * (2 * Fp) + c] : 0.f;
+                            m1[j] = ok ? p.dML[pf * (2 * Fp) + Fp + c] : 0.f;
+                        }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             int q = (tm1.cg - U / 4) * 4 + j;
                             int c = xc0 + q;
                             if (q < XC && c < xc1) {
                                 float dx = acc[i][j];
-                                float lv = p.Lv[pf * Fp + c];
-                                float e = p.eps[pf * p.ld_eps + c];
-                                p.dML[pf * (2 * Fp) + c] += dx;
-                                p.dML[pf * (2 * Fp) + Fp + c] += dx * 0.5f * expf(0.5f * lv) * e;
+                                p.dML[pf * (2 * Fp) + c] = m0[j] + dx;
+                                p.dML[pf * (2 * Fp) + Fp + c] = m1[j] + dx * 0.5f * expf(0.5f * lvv[j]) * evv[j];
                             }
                         }
                     }

@@ -252,23 +252,45 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
         if (dir == 0) { na_src = t > 0 ? na : 0; off_src = t > 0 ? p.offsets[t - 1] : 0; }
         else { na_src = (t + 1 < Tt) ? active_rows(p.batch_sizes[t + 1], tile, p.n_tiles) : 0; off_src = (t + 1 < Tt) ? p.offsets[t + 1] : 0; }
 
+        // gather every saved activation this thread needs first (independent loads in flight together), then
+        // compute and store: interleaving them row by row would serialise one memory round trip per row
+        float4 g4v[RT];
+        float cv[RT], pv[RT], doh[RT], doc[RT];
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            int r = prg + i * RG;
+            g4v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            cv[i] = pv[i] = doh[i] = doc[i] = 0.f;
+            if (r >= na) continue;
+            long b = tile + p.n_tiles * r;
+            long frame = off_t + b;
+            g4v[i] = __ldg(reinterpret_cast<const float4*>(gs + frame * (4 * H) + unit * 4));
+            const bool is_final = dir == 0 ? (t == len[i] - 1) : (t == 0);
+            const float* dout = p.d_out + b * p.out_ld;
+            if (CELL == 0) {
+                cv[i] = __ldg(cs + frame * H + unit);
+                if (r < na_src) pv[i] = __ldg(cs + ((long)off_src + b) * H + unit);
+                if (is_final) { doh[i] = __ldg(dout + dir * 2 * H + unit); doc[i] = __ldg(dout + dir * 2 * H + H + unit); }
+            } else {
+                if (r < na_src) pv[i] = __ldg(hs + ((long)off_src + b) * H + unit);
+                if (is_final) doh[i] = __ldg(dout + dir * H + unit);
+            }
+        }
 #pragma unroll
         for (int i = 0; i < RT; ++i) {
             int r = prg + i * RG;
             if (r >= na) continue;
             long b = tile + p.n_tiles * r;
             long frame = off_t + b;
-            const bool is_final = dir == 0 ? (t == len[i] - 1) : (t == 0);
             float dh = dh_sm[r * U + pu];
             float carry = dc_sm[r * U + pu];
-            const float* dout = p.d_out + b * p.out_ld;
-            const float4 g4 = *reinterpret_cast<const float4*>(gs + frame * (4 * H) + unit * 4);
+            const float4 g4 = g4v[i];
             float4 dgv;
             if (CELL == 0) {
                 float dc = carry;
-                if (is_final) { dh += dout[dir * 2 * H + unit]; dc += dout[dir * 2 * H + H + unit]; }
-                float c = cs[frame * H + unit];
-                float c_prev = r < na_src ? cs[((long)off_src + b) * H + unit] : 0.f;
+                dh += doh[i]; dc += doc[i];
+                float c = cv[i];
+                float c_prev = pv[i];
                 float tc = tanhf(c);
                 float ig = g4.x, fg = g4.y, gg = g4.z, og = g4.w;
                 dc += dh * og * (1.f - tc * tc);
@@ -278,9 +300,8 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
                 dgv.w = dh * tc * og * (1.f - og);
                 dc_sm[r * U + pu] = dc * fg;
             } else {
-                dh += carry;
-                if (is_final) dh += dout[dir * H + unit];
-                float h_prev = r < na_src ? hs[((long)off_src + b) * H + unit] : 0.f;
+                dh += carry + doh[i];
+                float h_prev = pv[i];
                 float rg_ = g4.x, zg = g4.y, ng = g4.z, hn = g4.w;
                 float dn_pre = dh * (1.f - zg) * (1.f - ng * ng);
                 dgv.x = dn_pre * hn * rg_ * (1.f - rg_);

@@ -61,8 +61,19 @@ struct Stage {
 __host__ __device__ inline Stage make_stage(float* base, int kc) {
     Stage s;
     s.kc = kc; s.lda = kc + 4;
-    s.lg_ppr = kc == 128 ? 5 : (kc == 64 ? 4 : 3);
-    s.buf0 = base; s.buf1 = base + ROWS * s.lda;
+    s.lg_ppr = kc == 256 ? 6 : (kc == 128 ? 5 : (kc == 64 ? 4 : 3));
+    s.buf0 = base; s.buf1 = base + ROWS * (kc + 4);
+    return s;
+}
+// As rows retire, the same two buffers hold fewer rows of longer K-chunks (fewer chunk boundaries per phase):
+// the chunk doubles while `rows` staged rows of it still fit in one buffer sized for ROWS rows of st.kc.
+__device__ __forceinline__ Stage grow_stage(const Stage& st, int rows, int K) {
+    Stage s = st;
+    const int cap = ROWS * (st.kc + 4);
+    while (s.kc < 256 && s.kc < K && rows * (2 * s.kc + 4) <= cap) {
+        s.kc *= 2; s.lg_ppr += 1;
+    }
+    s.lda = s.kc + 4;
     return s;
 }
 __host__ __device__ inline size_t stage_floats(int kc) { return (size_t)2 * ROWS * (kc + 4); }
@@ -167,12 +178,13 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[RT][4], const float* As, 
 // hold the full sums for rows rg + i*RG (i < RT) and columns cg*4 .. cg*4+3.  Ends with a CTA barrier, so the
 // staging buffers may be reused immediately.
 template <int NT, class RP0, class RP1>
-__device__ __forceinline__ void phase_gemm(float (&acc)[RT][4], const Stage& st, int K0, RP0 rp0, int K1,
+__device__ __forceinline__ void phase_gemm(float (&acc)[RT][4], const Stage& st_full, int K0, RP0 rp0, int K1,
                                            RP1 rp1, int nrows, const float* Wsm, int ldw, const ThreadMap& tm,
                                            int KS, int tid) {
     const int K = K0 + K1;
-    const int nch = (K + st.kc - 1) / st.kc;
     const int nslots = (nrows + RG - 1) / RG;
+    const Stage st = grow_stage(st_full, nslots * RG, K);   // the multiply reads whole 16-row slots
+    const int nch = (K + st.kc - 1) / st.kc;
     const float* Wcol = Wsm + tm.cg * 4;
     stage_chunk<NT>(st.buf0, st, 0, min(st.kc, K), nrows, K0, rp0, rp1, tid);
     cp_async_commit();
