@@ -1,0 +1,54 @@
+# coding: utf-8
+"""Turn ncu outputs brought back in gpurun_out/ into small text summaries under profiles/ (tracked).
+    python tools/summarize_profiles.py <launches.csv> <report.ncu-rep> <tag>"""
+import csv
+import re
+import subprocess
+import sys
+
+KEYS = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__cluster_size', 'launch__block_size',
+		'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+		'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+		'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+		'lts__t_bytes.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__inst_executed.sum',
+		'smsp__pcsamp_warps_issue_stalled_short_scoreboard', 'smsp__pcsamp_warps_issue_stalled_long_scoreboard',
+		'smsp__pcsamp_warps_issue_stalled_barrier', 'smsp__pcsamp_warps_issue_stalled_membar', 'smsp__pcsamp_warps_issue_stalled_wait',
+		'smsp__pcsamp_warps_issue_stalled_selected', 'smsp__pcsamp_warps_issue_stalled_not_selected', 'smsp__pcsamp_sample_count']
+
+
+def launches(path, out):
+	rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
+	agg, total = {}, 0.0
+	for r in rows:
+		name = re.sub(r'\(.*', '', r[4]).replace('void <unnamed>::', '').replace('void at::native::', 'at::')[:64]
+		if 'elementwise' in name:
+			name = 'torch elementwise (autograd accumulation / fills)'
+		us = float(r[14]) / 1000.0
+		a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += us
+		total += us
+	out.write('launch list: {} launches, {:.1f} us total (ncu gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare shares)\n'.format(len(rows), total))
+	for k, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+		out.write('  {:<66s} x{:<4d} {:>10.1f} us  {:5.1f}%\n'.format(k, c, v, 100 * v / total))
+
+
+def raw(rep, out):
+	txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+	rows = list(csv.reader(txt.splitlines()))
+	hdr = rows[0]; idx = {h: i for i, h in enumerate(hdr)}
+	units = rows[1]
+	for r in rows[2:]:
+		out.write('\nkernel: {}\n'.format(r[idx['Kernel Name']]))
+		for k in KEYS:
+			if k in idx:
+				out.write('  {:<72s} {} {}\n'.format(k, r[idx[k]], units[idx[k]]))
+
+
+if __name__ == '__main__':
+	ll, rep, tag = sys.argv[1:4]
+	with open('profiles/{}.txt'.format(tag), 'w') as f:
+		f.write('# {} -- summarised by tools/summarize_profiles.py\n'.format(tag))
+		if ll != '-':
+			launches(ll, f)
+		if rep != '-':
+			raw(rep, f)
+	print(open('profiles/{}.txt'.format(tag)).read()[:3000])
