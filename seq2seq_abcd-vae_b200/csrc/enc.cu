@@ -37,6 +37,14 @@ __global__ void combine_bias_kernel(int cell, const float* __restrict__ b_ih, co
     out[i] = v;
 }
 
+__global__ void pad_rows_kernel(long rows, int F, int Fpad, const float* __restrict__ src, int ld_src, float* __restrict__ dst) {
+    long total = rows * Fpad;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        long n = idx / Fpad; int c = (int)(idx % Fpad);
+        dst[idx] = c < F ? src[n * ld_src + c] : 0.f;
+    }
+}
+
 // prev_fwd[n]: packed index of the same sequence at t-1 (or -1); prev_bwd[n]: at t+1 (or -1)
 __global__ void prev_index_kernel(int T_max, const int* __restrict__ batch_sizes, const int* __restrict__ offsets,
                                   int* __restrict__ prev_fwd, int* __restrict__ prev_bwd) {
@@ -398,6 +406,7 @@ struct EncWs {
     float* dg[2];
     int* prev_fwd;
     int* prev_bwd;
+    float* xpad;      // [sumT][pad4(F)] copy of the input with 16-byte aligned rows (bulk-copy friendly)
     float* partials;
     size_t partial_floats;
     size_t bytes;
@@ -422,6 +431,7 @@ static EncWs enc_carve(void* base, size_t cap, int cell, int F, int B, int sumT,
         for (int d = 0; d < ndirs; ++d) w.dg[d] = w.xproj[d];
         w.prev_fwd = a.take<int>(sumT);
         w.prev_bwd = a.take<int>(sumT);
+        w.xpad = a.take<float>((size_t)sumT * ((F + 3) & ~3));
         int s1 = sgemm_pick_splits(4 * H, H, sumT), s2 = sgemm_pick_splits(4 * H, F, sumT);
         w.partial_floats = (size_t)4 * H * ((size_t)s1 * H > (size_t)s2 * F ? (size_t)s1 * H : (size_t)s2 * F);
         w.partials = a.take<float>(w.partial_floats);
@@ -515,7 +525,14 @@ int enc_backward(const EncParams& P, const EncGrads& G, const PackedMeta& pk, co
         g.splits = sgemm_pick_splits(g.M, g.N, g.K); g.partials = w.partials;
         TRY(sgemm_launch(g, stream));
         // dW_ih += dG^T * X
-        g.N = P.F; g.B = x; g.ldb = ldx; g.b_kgather = nullptr;
+        // the input rows are re-homed with a 16-byte aligned pitch so the tensor-core path can bulk-copy them
+        const int Fpad = (P.F + 3) & ~3;
+        if (d == 0 && (ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0)) {
+            pad_rows_kernel<<<592, 256, 0, stream>>>(pk.sumT, P.F, Fpad, x, ldx, w.xpad);
+            KERNEL_CHECK();
+        }
+        const bool use_pad = (ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0);
+        g.N = P.F; g.B = use_pad ? w.xpad : x; g.ldb = use_pad ? Fpad : ldx; g.b_kgather = nullptr;
         g.m_dst = map_ih; g.C = G.w_ih[d]; g.ldc = P.F;
         g.splits = sgemm_pick_splits(g.M, g.N, g.K);
         TRY(sgemm_launch(g, stream));

@@ -7,6 +7,7 @@
 // sequence) and split-K with a deterministic second-pass reduce.  Gate maps let the recurrent kernels keep
 // their unit-major interleaved gate order while parameters/gradients stay in PyTorch's gate-major order
 // (reference layouts: torch.nn.LSTM/GRU weight_ih_l0 [4H|3H, F], ABCD-VAE/modules/model.py:53).
+#include <stdlib.h>
 #include "sgemm.cuh"
 
 namespace {
@@ -330,7 +331,23 @@ static bool use_small_tiles(int M, int N, int splits) {
     return big * splits < 74;
 }
 
+bool umma_tn_eligible(const GemmArgs& g);
+int umma_tn_pick_splits(int M, int K);
+int umma_tn_launch(const GemmArgs& g, int splits, cudaStream_t stream);
+
+// ABCD_UMMA=0 forces the FFMA path for every GEMM (A/B comparisons, debugging)
+static bool umma_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ABCD_UMMA");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// Split-K factor for the reduction-over-frames (TN) GEMMs; callers size their partials buffer with it.
 int sgemm_pick_splits(int M, int N, int K) {
+    if (umma_enabled() && M % 128 == 0 && N <= 256 && K >= 256) return umma_tn_pick_splits(M, K);
     long tiles = (long)((M + 127) / 128) * ((N + 127) / 128);
     if (M <= 64 || N <= 64) tiles = (long)((M + 63) / 64) * ((N + 63) / 64);
     int ktiles = (K + BK - 1) / BK;
@@ -349,6 +366,16 @@ int sgemm_launch(const GemmArgs& gin, cudaStream_t stream) {
     ARG_CHECK(!(g.b_kgather && g.b_kmajor), "sgemm: k-gather needs n-major B");
     ARG_CHECK(!(g.b_nsrc.enabled && !g.b_kmajor), "sgemm: n source map needs k-major B");
     ProfScope ps(PROF_GEMM, stream);
+    if (umma_enabled() && umma_tn_eligible(g)) {
+        // tensor-core path (tcgen05 3xTF32): partial tiles per split, then the common reduce/epilogue kernel
+        TRY(umma_tn_launch(g, g.splits, stream));
+        long total = (long)g.M * g.N;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(g);
+        KERNEL_CHECK();
+        return ABCD_OK;
+    }
     const int a_vec = ((uintptr_t)g.A % 16 == 0) && (g.lda % 4 == 0);
     const int b_vec = ((uintptr_t)g.B % 16 == 0) && (g.ldb % 4 == 0);
     int r;
