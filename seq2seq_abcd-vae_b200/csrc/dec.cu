@@ -17,6 +17,8 @@ using namespace rnn;
 
 namespace {
 
+constexpr int DEC_NC3 = 20;    // P3 weight-slice pitch: 2 mean + 2 log-var columns for up to 5 pairs of x columns per CTA
+constexpr int DEC_NCB1 = 28;   // B1 weight-slice pitch: 16 h columns + up to 12 x columns per CTA
 constexpr size_t SMEM_MAX = 232448;   // 227 KB of dynamic shared memory per CTA on sm_100
 constexpr float LOG_2PI = 1.8378770664093453f;
 
@@ -42,18 +44,18 @@ struct DecK {
 // -------------------------------------------------------------------------------------------------
 // forward
 // -------------------------------------------------------------------------------------------------
-template <int CELL>
+template <int CELL, int KC>
 __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
     extern __shared__ __align__(16) float smem[];
     const int H = ABCD_H, M = ABCD_M;
     const int F = p.F, Fp = p.Fp;
     const int XC = xcols_per_cta(F);
-    const int ncg3 = (XC + 1) / 2, NC3 = ncg3 * 4;
+    constexpr int NC3 = DEC_NC3, ncg3 = DEC_NC3 / 4;
     float* Wg = smem;                         // [Fp+H][U*4]
     float* W1 = Wg + (Fp + H) * (U * 4);      // [H][2U]
     float* W3 = W1 + H * (2 * U);             // [2M][NC3]
-    const Stage st = make_stage(W3 + 2 * M * NC3, p.kc);
-    float* red = W3 + 2 * M * NC3 + stage_floats(p.kc);   // 40 floats
+    const Stage st = make_stage(W3 + 2 * M * NC3, KC);
+    float* red = W3 + 2 * M * NC3 + stage_floats(KC);   // 40 floats
 
     const int tid = threadIdx.x;
     const int rank = (int)cluster_ctarank();
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
             zero_acc(acc);
             auto rpx = [=](int r) -> const float* { return Xall + (prev_base + tile + (long)n_tiles * r) * Fp; };
             auto rph = [=](int r) -> const float* { return Hall + (prev_base + tile + (long)n_tiles * r) * ABCD_H; };
-            phase_gemm<NTHREADS>(acc, st,Fp, rpx, H, rph, na, Wg, U * 4, tm1, 1, tid);
+            phase_gemm<NTHREADS, KC, U * 4>(acc, st, Fp, rpx, H, rph, na, Wg, tm1, 1, tid);
 #pragma unroll
             for (int i = 0; i < RT; ++i) {
                 int r = tm1.rg + i * RG;
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
             float acc[RT][4];
             zero_acc(acc);
             auto rph = [=](int r) -> const float* { return Hall + ((long)B + off_t + tile + (long)n_tiles * r) * ABCD_H; };
-            phase_gemm<NTHREADS>(acc, st,H, rph, 0, NullRow(), na, W1, 2 * U, tm2, KS2, tid);
+            phase_gemm<NTHREADS, KC, 2 * U>(acc, st, H, rph, 0, NullRow(), na, W1, tm2, KS2, tid);
             if (tm2.active && tm2.ks == 0) {
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
                 }
             }
             auto rph = [=](int r) -> const float* { return Hid + (off_t + tile + (long)n_tiles * r) * (2 * ABCD_M); };
-            phase_gemm<NTHREADS>(acc, st,2 * M, rph, 0, NullRow(), na, W3, NC3, tm3, KS3, tid);
+            phase_gemm<NTHREADS, KC, DEC_NC3>(acc, st, 2 * M, rph, 0, NullRow(), na, W3, tm3, KS3, tid);
             if (tm3.active && tm3.ks == 0) {
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
@@ -258,20 +260,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
 // -------------------------------------------------------------------------------------------------
 // backward
 // -------------------------------------------------------------------------------------------------
-template <int CELL>
+template <int CELL, int KC>
 __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
     extern __shared__ __align__(16) float smem[];
     const int H = ABCD_H, M = ABCD_M;
     const int F = p.F, Fp = p.Fp;
     const int XC = xcols_per_cta(F);
-    const int NCX = pad4(XC);
-    const int NCB1 = U + NCX;
+    constexpr int NCB1 = DEC_NCB1;
     float* WB3 = smem;                        // [2Fp][2U]
     float* WB2 = WB3 + 2 * Fp * (2 * U);      // [2M][U]
     float* WB1 = WB2 + 2 * M * U;             // [4H][NCB1]
     float* dh_sm = WB1 + 4 * H * NCB1;        // [ROWS][U]
     float* dc_sm = dh_sm + ROWS * U;          // [ROWS][U]
-    const Stage st = make_stage(dc_sm + ROWS * U, p.kc);
+    const Stage st = make_stage(dc_sm + ROWS * U, KC);
 
     const int tid = threadIdx.x;
     const int rank = (int)cluster_ctarank();
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
             float acc[RT][4];
             zero_acc(acc);
             auto rp = [=](int r) -> const float* { return dML + (off_t + tile + (long)n_tiles * r) * (2 * Fp); };
-            phase_gemm<NTHREADS>(acc, st,2 * Fp, rp, 0, NullRow(), na, WB3, 2 * U, tm3, KS3, tid);
+            phase_gemm<NTHREADS, KC, 2 * U>(acc, st, 2 * Fp, rp, 0, NullRow(), na, WB3, tm3, KS3, tid);
             if (tm3.active && tm3.ks == 0) {
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
                 }
             }
             auto rp = [=](int r) -> const float* { return dHidPre + (off_t + tile + (long)n_tiles * r) * (2 * ABCD_M); };
-            phase_gemm<NTHREADS>(acc, st,2 * M, rp, 0, NullRow(), na, WB2, U, tm2, KS2, tid);
+            phase_gemm<NTHREADS, KC, U>(acc, st, 2 * M, rp, 0, NullRow(), na, WB2, tm2, KS2, tid);
             if (tm2.active && tm2.ks == 0) {
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
@@ -433,7 +434,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
             float acc[RT][4];
             zero_acc(acc);
             auto rp = [=](int r) -> const float* { return dG + (off_t + tile + (long)n_tiles * r) * (4 * ABCD_H); };
-            phase_gemm<NTHREADS>(acc, st,4 * H, rp, 0, NullRow(), na, WB1, NCB1, tm1, KS1, tid);
+            phase_gemm<NTHREADS, KC, DEC_NCB1>(acc, st, 4 * H, rp, 0, NullRow(), na, WB1, tm1, KS1, tid);
             if (tm1.active && tm1.ks == 0) {
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
@@ -581,15 +582,15 @@ __global__ void unpad_copy_kernel(long rows, int F, int ld_src, const float* __r
 }
 
 size_t dec_fwd_fixed_floats(int F) {   // resident weights + reduction scratch
-    int Fp = pad4(F), XC = xcols_per_cta(F), NC3 = ((XC + 1) / 2) * 4;
-    return (size_t)((Fp + ABCD_H) * U * 4 + ABCD_H * 2 * U + 2 * ABCD_M * NC3 + 64);
+    int Fp = pad4(F);
+    return (size_t)((Fp + ABCD_H) * U * 4 + ABCD_H * 2 * U + 2 * ABCD_M * DEC_NC3 + 64);
 }
 size_t dec_bwd_fixed_floats(int F) {   // resident weights + dh/dc carries
-    int Fp = pad4(F), XC = xcols_per_cta(F), NCB1 = U + pad4(XC);
-    return (size_t)(2 * Fp * 2 * U + 2 * ABCD_M * U + 4 * ABCD_H * NCB1 + 2 * ROWS * U);
+    int Fp = pad4(F);
+    return (size_t)(2 * Fp * 2 * U + 2 * ABCD_M * U + 4 * ABCD_H * DEC_NCB1 + 2 * ROWS * U);
 }
 int pick_kc(size_t fixed_floats) {
-    for (int kc : {128, 64, 32})
+    for (int kc : {64, 32})
         if ((fixed_floats + stage_floats(kc)) * sizeof(float) <= SMEM_MAX) return kc;
     return 0;
 }
@@ -693,15 +694,20 @@ int check_dec(const DecParams& P) {
 
 int rnn_max_active_clusters(const void* fn, size_t smem, int cluster, int threads, int* out);
 int dec_max_clusters(int which, int F, int* out) {
-    const void* fn = which == 0 ? (const void*)dec_fwd_kernel<0> : (const void*)dec_bwd_kernel<0>;
+    const void* fn = which == 0 ? (dec_fwd_kc(F) == 64 ? (const void*)dec_fwd_kernel<0, 64> : (const void*)dec_fwd_kernel<0, 32>)
+                                : (dec_bwd_kc(F) == 64 ? (const void*)dec_bwd_kernel<0, 64> : (const void*)dec_bwd_kernel<0, 32>);
     return rnn_max_active_clusters(fn, which == 0 ? dec_fwd_smem(F) : dec_bwd_smem(F), CL, NTHREADS, out);
 }
 
 int dec_init() {
-    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0>, SMEM_MAX));
-    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1>, SMEM_MAX));
-    TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<0>, SMEM_MAX));
-    TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<1>, SMEM_MAX));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0, 64>, SMEM_MAX));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1, 64>, SMEM_MAX));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0, 32>, SMEM_MAX));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1, 32>, SMEM_MAX));
+    TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<0, 64>, SMEM_MAX));
+    TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<1, 64>, SMEM_MAX));
+    TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<0, 32>, SMEM_MAX));
+    TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<1, 32>, SMEM_MAX));
     return ABCD_OK;
 }
 
@@ -738,8 +744,14 @@ int dec_forward(const DecParams& P, const PackedMeta& pk, const float* feat_in, 
     ARG_CHECK(k.kc > 0, "decoder: weights for output_size %d do not fit in shared memory", P.F);
     {
         ProfScope ps(PROF_DEC_FWD, stream);
-        if (P.cell == 0) TRY(launch_cluster_dec(dec_fwd_kernel<0>, n_tiles, dec_fwd_smem(P.F), stream, k));
-        else TRY(launch_cluster_dec(dec_fwd_kernel<1>, n_tiles, dec_fwd_smem(P.F), stream, k));
+        const size_t sm = dec_fwd_smem(P.F);
+        if (k.kc == 64) {
+            if (P.cell == 0) TRY(launch_cluster_dec(dec_fwd_kernel<0, 64>, n_tiles, sm, stream, k));
+            else TRY(launch_cluster_dec(dec_fwd_kernel<1, 64>, n_tiles, sm, stream, k));
+        } else {
+            if (P.cell == 0) TRY(launch_cluster_dec(dec_fwd_kernel<0, 32>, n_tiles, sm, stream, k));
+            else TRY(launch_cluster_dec(dec_fwd_kernel<1, 32>, n_tiles, sm, stream, k));
+        }
     }
     if (gt && losses) {
         final_sum_kernel<<<1, 256, 0, stream>>>(w.nll_partial, n_tiles * CL, losses + 0);
@@ -800,8 +812,14 @@ int dec_backward(const DecParams& P, const DecGrads& G, const PackedMeta& pk, co
     ARG_CHECK(k.kc > 0, "decoder bwd: weights for output_size %d do not fit in shared memory", P.F);
     {
         ProfScope ps(PROF_DEC_BWD, stream);
-        if (P.cell == 0) TRY(launch_cluster_dec(dec_bwd_kernel<0>, n_tiles, dec_bwd_smem(P.F), stream, k));
-        else TRY(launch_cluster_dec(dec_bwd_kernel<1>, n_tiles, dec_bwd_smem(P.F), stream, k));
+        const size_t sm = dec_bwd_smem(P.F);
+        if (k.kc == 64) {
+            if (P.cell == 0) TRY(launch_cluster_dec(dec_bwd_kernel<0, 64>, n_tiles, sm, stream, k));
+            else TRY(launch_cluster_dec(dec_bwd_kernel<1, 64>, n_tiles, sm, stream, k));
+        } else {
+            if (P.cell == 0) TRY(launch_cluster_dec(dec_bwd_kernel<0, 32>, n_tiles, sm, stream, k));
+            else TRY(launch_cluster_dec(dec_bwd_kernel<1, 32>, n_tiles, sm, stream, k));
+        }
     }
 
     // ---- weight gradients: reductions over all packed frames ----

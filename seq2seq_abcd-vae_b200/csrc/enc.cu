@@ -6,6 +6,7 @@
 //         + one persistent cluster kernel per launch that runs both directions concurrently.
 // Backward = persistent BPTT kernel producing pre-activation gate gradients for every frame
 //         + weight/bias gradients as large TN GEMMs over all frames.
+#include <stdlib.h>
 #include "rnn_common.cuh"
 #include "sgemm.cuh"
 #include "enc.cuh"
@@ -18,7 +19,7 @@ namespace {
 // clusters are resident together, where 16-CTA clusters would need two waves.
 constexpr int ENC_CL = 8;
 constexpr int ENC_U = ABCD_H / ENC_CL;
-constexpr int ENC_NT = RG * ENC_U;
+constexpr int ENC_NT = NRG * ENC_U;
 constexpr int ENC_KC_FWD = 128;
 constexpr int ENC_KC_BWD = 64;
 
@@ -61,8 +62,11 @@ __global__ void prev_index_kernel(int T_max, const int* __restrict__ batch_sizes
 // -------------------------------------------------------------------------------------------------
 // forward
 // -------------------------------------------------------------------------------------------------
+__device__ unsigned long long g_enc_timing[10];
+
 struct EncFwdK {
     int n_tiles, B, ndirs, save, out_ld;
+    int timing;   // debug: accumulate per-phase clock cycles of CTA 0 into g_enc_timing
     const int* batch_sizes; const int* offsets; const int* lengths;
     const float* w_hh[2];
     const float* b_hh[2];
@@ -119,7 +123,11 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
     float* hs = p.hs[dir];
     __syncthreads();
 
+    unsigned long long tacc[5] = {0, 0, 0, 0, 0};
+    unsigned long long pg[5] = {0, 0, 0, 0, 0};
+    const bool timing = p.timing && blockIdx.x == 0 && tid == 0;
     for (int s = 0; s < Tt; ++s) {
+        long long c0 = timing ? clock64() : 0;
         const int t = dir == 0 ? s : Tt - 1 - s;
         const int na = active_rows(p.batch_sizes[t], tile, p.n_tiles);
         const int off_t = p.offsets[t];
@@ -141,6 +149,7 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
         }
         float acc[RT][4];
         zero_acc(acc);
+        long long c1 = timing ? clock64() : 0;
         if (na_prev > 0) {
             const int n_tiles = p.n_tiles, B = p.B, save = p.save;
             auto rp = [=](int r) -> const float* {
@@ -149,8 +158,9 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
                 long row = save ? (long)off_prev + b : (long)((s - 1) & 1) * B + b;
                 return hs + row * ABCD_H;
             };
-            phase_gemm<ENC_NT>(acc, st, H, rp, 0, NullRow(), na, Wsm, U * 4, tm, 1, tid);
+            phase_gemm<ENC_NT, ENC_KC_FWD, ENC_U * 4>(acc, st, H, rp, 0, NullRow(), na, Wsm, tm, 1, tid, timing ? pg : nullptr);
         }
+        long long c2 = timing ? clock64() : 0;
 #pragma unroll
         for (int i = 0; i < RT; ++i) {
             int r = tm.rg + i * RG;
@@ -189,8 +199,14 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
                 else o[dir * H + unit] = h;
             }
         }
+        long long c3 = timing ? clock64() : 0;
         cluster_sync_all();
+        if (timing) {
+            long long c4 = clock64();
+            tacc[0] += c1 - c0; tacc[1] += c2 - c1; tacc[2] += c3 - c2; tacc[3] += c4 - c3; tacc[4] += 1;
+        }
     }
+    if (timing) for (int i = 0; i < 5; ++i) { g_enc_timing[i] = tacc[i]; g_enc_timing[5 + i] = pg[i]; }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -327,7 +343,7 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
             zero_acc(acc);
             const int n_tiles = p.n_tiles;
             auto rp = [=](int r) -> const float* { return dg + ((long)off_t + tile + (long)n_tiles * r) * (4 * ABCD_H); };
-            phase_gemm<ENC_NT>(acc, st, 4 * H, rp, 0, NullRow(), na_src, Wsm, U, tm, KS, tid);
+            phase_gemm<ENC_NT, ENC_KC_BWD, ENC_U>(acc, st, 4 * H, rp, 0, NullRow(), na_src, Wsm, tm, KS, tid);
             if (tm.active && tm.ks == 0) {
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
@@ -386,6 +402,11 @@ int rnn_max_active_clusters(const void* fn, size_t smem, int cluster, int thread
 int enc_max_clusters(int which, int* out) {
     const void* fn = which == 0 ? (const void*)enc_fwd_kernel<0> : (const void*)enc_bwd_kernel<0>;
     return rnn_max_active_clusters(fn, which == 0 ? enc_fwd_smem() : enc_bwd_smem(), ENC_CL, ENC_NT, out);
+}
+
+int enc_read_timing(unsigned long long* out5) {
+    CUDA_TRY(cudaMemcpyFromSymbol(out5, g_enc_timing, 10 * sizeof(unsigned long long)));
+    return ABCD_OK;
 }
 
 int enc_init() {
@@ -459,6 +480,7 @@ int enc_forward(const EncParams& P, const PackedMeta& pk, const float* x, int ld
     EncFwdK k;
     memset(&k, 0, sizeof(k));
     k.n_tiles = n_tiles; k.B = pk.B; k.ndirs = ndirs; k.save = save;
+    k.timing = getenv("ABCD_TIMING") != nullptr;
     k.out_ld = ndirs * H * (P.cell == 0 ? 2 : 1);
     k.batch_sizes = pk.batch_sizes; k.offsets = pk.offsets; k.lengths = pk.lengths;
     k.out = last_hidden;

@@ -23,57 +23,49 @@ namespace rnn {
 constexpr int CL = 16;             // CTAs per cluster (decoder; the encoder kernels use 8)
 constexpr int U = ABCD_H / CL;     // hidden units per CTA
 constexpr int RT = 5;              // rows per thread
-constexpr int RG = 16;             // row groups; thread rg owns rows rg + i*RG
-constexpr int ROWS = RT * RG;      // rows (segments) per tile
+constexpr int NRG = 16;            // row groups
+constexpr int RG = NRG;            // thread of row group rg owns the interleaved rows rg + i*RG (i < RT): retiring
+                                   // segments thin every row group evenly, so all warps keep equal work
+constexpr int ROWS = RT * NRG;     // rows (segments) per tile
 constexpr int NTHREADS = 256;
 
 struct ThreadMap {
     int cg, rg, ks;   // column group (4 columns), row group, K-split index
     bool active;
 };
-// Threads of a warp share as few distinct A rows (2) and as many contiguous W columns (16 groups) as possible.
+// Lane assignment.  A warp covers 8 column groups x 4 row groups when the phase has a multiple of 8 column groups:
+// its weight-fragment load is then 128 contiguous bytes (one shared-memory wavefront, where 16 groups x 2 rows
+// would need two) and its activation-fragment load is 4 rows x 16 B (one wavefront; the row pitch is 4 banks).
+// Other column-group counts use the plain (cg fastest) order, which already mixes several row groups per warp.
 __device__ __forceinline__ ThreadMap make_map(int tid, int ncg, int KS) {
     ThreadMap m;
-    if (ncg <= 16) {
+    if ((ncg & 7) == 0) {
+        const int lane = tid & 31, w = tid >> 5;
+        const int ncg_hi = ncg >> 3;           // warps along the column groups
+        m.cg = (w % ncg_hi) * 8 + (lane & 7);
+        m.rg = ((w / ncg_hi) % (NRG / 4)) * 4 + (lane >> 3);
+        m.ks = w / (ncg_hi * (NRG / 4));
+    } else {
         m.cg = tid % ncg;
-        m.rg = (tid / ncg) % RG;
-        m.ks = tid / (ncg * RG);
-    } else {   // ncg == 32 (8-CTA encoder clusters, 512 threads): column groups split in two halves of 16
-        m.cg = (tid & 15) + 16 * (tid / (16 * RG));
-        m.rg = (tid >> 4) % RG;
-        m.ks = 0;
+        m.rg = (tid / ncg) % NRG;
+        m.ks = tid / (ncg * NRG);
     }
     m.active = m.ks < KS;
     return m;
 }
 __host__ __device__ inline int pick_ks(int ncg, int nthreads = NTHREADS) {
-    int ks = nthreads / (ncg * RG);
+    int ks = nthreads / (ncg * NRG);
     return ks < 1 ? 1 : ks;
 }
 
 struct Stage {
     float* buf0;
     float* buf1;
-    int lda;     // kc + 4 floats
-    int kc;      // K-chunk: 32, 64 or 128
-    int lg_ppr;  // log2(kc / 4): 16-byte pieces per staged row
 };
+// Two staging buffers of ROWS rows x (kc + 4) floats (the 4-float pad makes the row pitch 4 banks mod 32).
 __host__ __device__ inline Stage make_stage(float* base, int kc) {
     Stage s;
-    s.kc = kc; s.lda = kc + 4;
-    s.lg_ppr = kc == 256 ? 6 : (kc == 128 ? 5 : (kc == 64 ? 4 : 3));
     s.buf0 = base; s.buf1 = base + ROWS * (kc + 4);
-    return s;
-}
-// As rows retire, the same two buffers hold fewer rows of longer K-chunks (fewer chunk boundaries per phase):
-// the chunk doubles while `rows` staged rows of it still fit in one buffer sized for ROWS rows of st.kc.
-__device__ __forceinline__ Stage grow_stage(const Stage& st, int rows, int K) {
-    Stage s = st;
-    const int cap = ROWS * (st.kc + 4);
-    while (s.kc < 256 && s.kc < K && rows * (2 * s.kc + 4) <= cap) {
-        s.kc *= 2; s.lg_ppr += 1;
-    }
-    s.lda = s.kc + 4;
     return s;
 }
 __host__ __device__ inline size_t stage_floats(int kc) { return (size_t)2 * ROWS * (kc + 4); }
@@ -84,41 +76,43 @@ __device__ __forceinline__ void zero_acc(float (&acc)[RT][4]) {
 }
 
 // A row r of the tile is the concatenation [rp0(r)[0,K0) | rp1(r)[0,K1)] (a null pointer means zeros).
-// K0 and K1 are multiples of 4 and all row pointers are 16-byte aligned.
-template <int NT, class RP0, class RP1>
-__device__ __forceinline__ void stage_chunk(float* dst, const Stage& st, int k_begin, int k_len, int nrows, int K0,
+// K0 and K1 are multiples of 4 and all row pointers are 16-byte aligned.  KC = staged K-chunk (32/64/128).
+template <int NT, int KC, class RP0, class RP1>
+__device__ __forceinline__ void stage_chunk(float* dst, int k_begin, int k_len, int nrows, int K0,
                                             RP0 rp0, RP1 rp1, int tid) {
-    const int ppr_mask = (1 << st.lg_ppr) - 1;
-    const int total = nrows << st.lg_ppr;
+    constexpr int LG = KC == 128 ? 5 : (KC == 64 ? 4 : 3);   // log2 of 16-byte pieces per staged row
+    constexpr int LDA = KC + 4;
+    const int total = nrows << LG;
     for (int idx = tid; idx < total; idx += NT) {
-        const int r = idx >> st.lg_ppr, p4 = (idx & ppr_mask) * 4;
+        const int r = idx >> LG, p4 = (idx & ((1 << LG) - 1)) * 4;
         if (p4 >= k_len) continue;
         const int k = k_begin + p4;
         const float* src;
         if (k < K0) { src = rp0(r); if (src) src += k; }
         else { src = rp1(r); if (src) src += (k - K0); }
-        float* d = dst + r * st.lda + p4;
+        float* d = dst + r * LDA + p4;
         if (src) cp_async16(d, src);
         else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
-// Inner product over k4 in [k4_begin, k4_end) for the first NS row slots of this thread, branch-free: the
-// shared-memory fragments of step k4+1 are fetched while step k4 is multiplied (register double buffering), so
-// the LDS latency hides behind 16*NS FFMAs.
+// Inner product over n k-quads for the first NS row slots of this thread, branch-free.  All shared-memory
+// strides are compile-time (LDA = staged row pitch, LDW = weight-slice row pitch), so every fragment load is
+// [pointer + immediate]; the fragments of quad q+1 are fetched while quad q is multiplied (register double
+// buffering), so the LDS latency hides behind 16*NS FFMAs.
 template <int NS>
 struct Frag {
     float4 w[4];
     float4 a[NS];
 };
-template <int NS>
-__device__ __forceinline__ void load_frag(Frag<NS>& f, const float* a_rg, int lda, const float* w, int ldw) {
+template <int NS, int LDA, int LDW>
+__device__ __forceinline__ void load_frag(Frag<NS>& f, const float* a_rg, const float* w) {
     f.w[0] = *reinterpret_cast<const float4*>(w);
-    f.w[1] = *reinterpret_cast<const float4*>(w + ldw);
-    f.w[2] = *reinterpret_cast<const float4*>(w + 2 * ldw);
-    f.w[3] = *reinterpret_cast<const float4*>(w + 3 * ldw);
+    f.w[1] = *reinterpret_cast<const float4*>(w + LDW);
+    f.w[2] = *reinterpret_cast<const float4*>(w + 2 * LDW);
+    f.w[3] = *reinterpret_cast<const float4*>(w + 3 * LDW);
 #pragma unroll
-    for (int i = 0; i < NS; ++i) f.a[i] = *reinterpret_cast<const float4*>(a_rg + i * RG * lda);
+    for (int i = 0; i < NS; ++i) f.a[i] = *reinterpret_cast<const float4*>(a_rg + i * RG * LDA);
 }
 template <int NS>
 __device__ __forceinline__ void fma_frag(float (&acc)[RT][4], const Frag<NS>& f) {
@@ -135,82 +129,88 @@ __device__ __forceinline__ void fma_frag(float (&acc)[RT][4], const Frag<NS>& f)
         acc[i][2] = fmaf(a.w, f.w[3].z, acc[i][2]); acc[i][3] = fmaf(a.w, f.w[3].w, acc[i][3]);
     }
 }
-template <int NS>
-__device__ __forceinline__ void mma_range(float (&acc)[RT][4], const float* a_rg /* &As[rg][k4_begin*4] */, int lda,
-                                          const float* w /* &Wsm[k_begin + k4_begin*4][cg*4] */, int ldw, int n) {
+template <int NS, int LDA, int LDW>
+__device__ __forceinline__ void mma_range(float (&acc)[RT][4], const float* a_rg /* &As[rg][k4_begin*4] */,
+                                          const float* w /* &Wsm[k_begin + k4_begin*4][cg*4] */, int n) {
     if (n <= 0) return;
-    const int wstep = 4 * ldw;
     Frag<NS> f0, f1;
-    load_frag<NS>(f0, a_rg, lda, w, ldw);
+    load_frag<NS, LDA, LDW>(f0, a_rg, w);
     int it = 0;
     for (; it + 2 <= n; it += 2) {
-        load_frag<NS>(f1, a_rg + 4, lda, w + wstep, ldw);
+        load_frag<NS, LDA, LDW>(f1, a_rg + 4, w + 4 * LDW);
         fma_frag<NS>(acc, f0);
-        a_rg += 8; w += 2 * wstep;
-        // the prefetch past the end of the range stays inside the staging row / weight slice padding rules:
-        // it is only issued when another step follows
-        if (it + 2 < n) load_frag<NS>(f0, a_rg, lda, w, ldw);
+        a_rg += 8; w += 8 * LDW;
+        if (it + 2 < n) load_frag<NS, LDA, LDW>(f0, a_rg, w);   // only when another quad follows
         fma_frag<NS>(acc, f1);
     }
     if (it < n) fma_frag<NS>(acc, f0);
 }
 
 // One K-chunk.  K-splits own contiguous k ranges of the chunk.
-__device__ __forceinline__ void mma_chunk(float (&acc)[RT][4], const float* As, int lda, int k_len,
-                                          const float* Wk /* &Wsm[k_begin][cg*4] */, int ldw, const ThreadMap& tm,
+template <int KC, int LDW>
+__device__ __forceinline__ void mma_chunk(float (&acc)[RT][4], const float* As, int k_len,
+                                          const float* Wk /* &Wsm[k_begin][cg*4] */, const ThreadMap& tm,
                                           int KS, int nslots) {
+    constexpr int LDA = KC + 4;
     const int nk4 = k_len >> 2;
     const int per = (nk4 + KS - 1) / KS;
     const int b = tm.ks * per;
     const int n = min(per, nk4 - b);
-    const float* a_rg = As + tm.rg * lda + b * 4;
-    const float* w = Wk + (long)(b * 4) * ldw;
+    const float* a_rg = As + tm.rg * LDA + b * 4;
+    const float* w = Wk + (b * 4) * LDW;
     switch (nslots) {
-        case 1: mma_range<1>(acc, a_rg, lda, w, ldw, n); break;
-        case 2: mma_range<2>(acc, a_rg, lda, w, ldw, n); break;
-        case 3: mma_range<3>(acc, a_rg, lda, w, ldw, n); break;
-        case 4: mma_range<4>(acc, a_rg, lda, w, ldw, n); break;
-        default: mma_range<RT>(acc, a_rg, lda, w, ldw, n); break;
+        case 1: mma_range<1, LDA, LDW>(acc, a_rg, w, n); break;
+        case 2: mma_range<2, LDA, LDW>(acc, a_rg, w, n); break;
+        case 3: mma_range<3, LDA, LDW>(acc, a_rg, w, n); break;
+        case 4: mma_range<4, LDA, LDW>(acc, a_rg, w, n); break;
+        default: mma_range<RT, LDA, LDW>(acc, a_rg, w, n); break;
     }
 }
 
-// acc += A[rows, K0+K1] * Wsm[K0+K1, ncols] for this thread's tile.  On return the threads with ks == 0
+// acc += A[rows, K0+K1] * Wsm[K0+K1, LDW] for this thread's tile.  On return the threads with ks == 0
 // hold the full sums for rows rg + i*RG (i < RT) and columns cg*4 .. cg*4+3.  Ends with a CTA barrier, so the
-// staging buffers may be reused immediately.
-template <int NT, class RP0, class RP1>
-__device__ __forceinline__ void phase_gemm(float (&acc)[RT][4], const Stage& st_full, int K0, RP0 rp0, int K1,
-                                           RP1 rp1, int nrows, const float* Wsm, int ldw, const ThreadMap& tm,
-                                           int KS, int tid) {
+// staging buffers may be reused immediately.  `dbg` (optional) accumulates clock cycles of the calling thread:
+// [0] staging issue, [1] wait + barrier, [2] multiply, [3] chunks, [4] tail barrier.
+template <int NT, int KC, int LDW, class RP0, class RP1>
+__device__ __forceinline__ void phase_gemm(float (&acc)[RT][4], const Stage& st, int K0, RP0 rp0, int K1,
+                                           RP1 rp1, int nrows, const float* Wsm, const ThreadMap& tm,
+                                           int KS, int tid, unsigned long long* dbg = nullptr) {
     const int K = K0 + K1;
-    const int nslots = (nrows + RG - 1) / RG;
-    const Stage st = grow_stage(st_full, nslots * RG, K);   // the multiply reads whole 16-row slots
-    const int nch = (K + st.kc - 1) / st.kc;
+    const int nslots = (nrows + RG - 1) / RG;   // active 16-row slots (uniform over the CTA)
+    const int nch = (K + KC - 1) / KC;
     const float* Wcol = Wsm + tm.cg * 4;
-    stage_chunk<NT>(st.buf0, st, 0, min(st.kc, K), nrows, K0, rp0, rp1, tid);
+    long long d0 = dbg ? clock64() : 0;
+    stage_chunk<NT, KC>(st.buf0, 0, min(KC, K), nrows, K0, rp0, rp1, tid);
     cp_async_commit();
+    if (dbg) { long long d1 = clock64(); dbg[0] += d1 - d0; }
     for (int c = 0; c < nch; ++c) {
+        long long e0 = dbg ? clock64() : 0;
         cp_async_wait<0>();
         __syncthreads();   // chunk c visible to all; everyone is done with chunk c-1's buffer
+        long long e1 = dbg ? clock64() : 0;
         if (c + 1 < nch) {
-            const int kb = (c + 1) * st.kc;
-            stage_chunk<NT>((c & 1) ? st.buf0 : st.buf1, st, kb, min(st.kc, K - kb), nrows, K0, rp0, rp1, tid);
+            const int kb = (c + 1) * KC;
+            stage_chunk<NT, KC>((c & 1) ? st.buf0 : st.buf1, kb, min(KC, K - kb), nrows, K0, rp0, rp1, tid);
             cp_async_commit();
         }
+        long long e2 = dbg ? clock64() : 0;
         if (tm.active) {
-            const int kb = c * st.kc;
-            mma_chunk(acc, (c & 1) ? st.buf1 : st.buf0, st.lda, min(st.kc, K - kb), Wcol + (long)kb * ldw, ldw, tm, KS, nslots);
+            const int kb = c * KC;
+            mma_chunk<KC, LDW>(acc, (c & 1) ? st.buf1 : st.buf0, min(KC, K - kb), Wcol + kb * LDW, tm, KS, nslots);
         }
+        if (dbg) { long long e3 = clock64(); dbg[1] += e1 - e0; dbg[0] += e2 - e1; dbg[2] += e3 - e2; dbg[3] += 1; }
     }
+    long long f0 = dbg ? clock64() : 0;
     __syncthreads();
+    if (dbg) dbg[4] += clock64() - f0;
     if (KS > 1) {
         // cross-split reduction through the (now idle) staging buffers
         float* scratch = st.buf0;
-        const int ncols = ldw;   // scratch row pitch: one row of the weight slice
         if (tm.active && tm.ks > 0) {
 #pragma unroll
             for (int i = 0; i < RT; ++i)
                 if (i < nslots)
-                    *reinterpret_cast<float4*>(scratch + ((tm.ks - 1) * ROWS + tm.rg + i * RG) * ncols + tm.cg * 4) =
+                    *reinterpret_cast<float4*>(scratch + ((tm.ks - 1) * ROWS + tm.rg + i * RG) * LDW + tm.cg * 4) =
                         make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         }
         __syncthreads();
@@ -219,7 +219,7 @@ __device__ __forceinline__ void phase_gemm(float (&acc)[RT][4], const Stage& st_
 #pragma unroll
                 for (int i = 0; i < RT; ++i)
                     if (i < nslots) {
-                        float4 v = *reinterpret_cast<const float4*>(scratch + ((s - 1) * ROWS + tm.rg + i * RG) * ncols + tm.cg * 4);
+                        float4 v = *reinterpret_cast<const float4*>(scratch + ((s - 1) * ROWS + tm.rg + i * RG) * LDW + tm.cg * 4);
                         acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
                     }
             }

@@ -52,3 +52,18 @@ def main():
 
 if __name__ == '__main__':
 	main()
+
+
+def enc_timing():
+	import ctypes as C
+	pkg = importlib.import_module('seq2seq_abcd-vae_b200')
+	out = (C.c_ulonglong * 10)()
+	pkg._lib.load().abcd_debug_enc_timing(out)
+	v = list(out)
+	if v[4]:
+		print('enc_fwd CTA0 cycles/step: setup %.0f gemm %.0f epilogue %.0f barrier %.0f (steps %d)' % (v[0] / v[4], v[1] / v[4], v[2] / v[4], v[3] / v[4], v[4]))
+		print("   phase_gemm per step: stage-issue %.0f wait+sync %.0f mma %.0f tail-sync %.0f chunks/step %.2f" % (v[5] / v[4], v[6] / v[4], v[7] / v[4], v[9] / v[4], v[8] / v[4]))
+
+
+if os.environ.get('ABCD_TIMING'):
+	enc_timing()
