@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
     }
 
     // ---- per-thread constants for the three phases ----
-    const ThreadMap tm1 = make_map(tid, U, 1);
+    const int KS1 = pick_ks_fit(U, U * 4, KC);
+    const ThreadMap tm1 = make_map(tid, U, KS1);
     const int unit = u0 + tm1.cg;
     float bias1[4];
     if (CELL == 0) {
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
         bias1[2] = p.b_ih[2 * H + unit];
         bias1[3] = p.b_hh[2 * H + unit];
     }
-    const int KS2 = pick_ks(2 * U / 4);
+    const int KS2 = pick_ks_fit(2 * U / 4, 2 * U, KC);
     const ThreadMap tm2 = make_map(tid, 2 * U / 4, KS2);
     float bias2[4];
 #pragma unroll
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
         int col = tm2.cg * 4 + j;
         bias2[j] = p.em_b1[col / U][u0 + col % U];
     }
-    const int KS3 = pick_ks(ncg3);
+    const int KS3 = pick_ks_fit(ncg3, DEC_NC3, KC);
     const ThreadMap tm3 = make_map(tid, ncg3, KS3);
     float bias3[4];
 #pragma unroll
@@ -152,11 +153,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
             zero_acc(acc);
             auto rpx = [=](int r) -> const float* { return Xall + (prev_base + tile + (long)n_tiles * r) * Fp; };
             auto rph = [=](int r) -> const float* { return Hall + (prev_base + tile + (long)n_tiles * r) * ABCD_H; };
-            phase_gemm<NTHREADS, KC, U * 4>(acc, st, Fp, rpx, H, rph, na, Wg, tm1, 1, tid);
+            phase_gemm<NTHREADS, KC, U * 4>(acc, st, Fp, rpx, H, rph, na, Wg, tm1, KS1, tid);
 #pragma unroll
             for (int i = 0; i < RT; ++i) {
                 int r = tm1.rg + i * RG;
-                if (r >= na) continue;
+                if (r >= na || tm1.ks != 0) continue;
                 long frame = off_t + tile + (long)n_tiles * r;
                 float h;
                 if (CELL == 0) {
@@ -310,13 +311,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
     }
     for (int idx = tid; idx < ROWS * U; idx += NTHREADS) { dh_sm[idx] = 0.f; dc_sm[idx] = 0.f; }
 
-    const int KS3 = pick_ks(2 * U / 4);
+    const int KS3 = pick_ks_fit(2 * U / 4, 2 * U, KC);
     const ThreadMap tm3 = make_map(tid, 2 * U / 4, KS3);
-    const int KS2 = pick_ks(U / 4);
+    const int KS2 = pick_ks_fit(U / 4, U, KC);
     const ThreadMap tm2 = make_map(tid, U / 4, KS2);
     const int ncg1 = NCB1 / 4;
-    const int KS1 = pick_ks(ncg1);
+    const int KS1 = pick_ks_fit(ncg1, DEC_NCB1, KC);
     const ThreadMap tm1 = make_map(tid, ncg1, KS1);
+    constexpr int PRG = NTHREADS / U;   // pointwise mapping: 16 row groups x 16 units, rows prg + i*PRG
     const int pu = tid % U, prg = tid / U;
     const int unit = u0 + pu;
 
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
             float cv[RT], pv[RT], hov[RT];
 #pragma unroll
             for (int i = 0; i < RT; ++i) {
-                int r = prg + i * RG;
+                int r = prg + i * PRG;
                 g4v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 cv[i] = pv[i] = hov[i] = 0.f;
                 if (r >= na) continue;
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
             __syncthreads();
 #pragma unroll
             for (int i = 0; i < RT; ++i) {
-                int r = prg + i * RG;
+                int r = prg + i * PRG;
                 if (r >= na) continue;
                 long frame = off_t + tile + (long)n_tiles * r;
                 float dh = dh_sm[r * U + pu] + hov[i];
@@ -474,9 +476,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
     }
     // gradient w.r.t. the initial state produced by feature2hidden (h0 = even, c0 = odd columns; model.py:100)
     for (int i = 0; i < RT; ++i) {
-        int r = prg + i * RG;
+        int r = prg + i * PRG;
         long b = tile + (long)n_tiles * r;
-        if (b >= B) continue;
+        if (b >= B || r >= ROWS) continue;
         if (CELL == 0) {
             p.dHC0[b * (2 * H) + 2 * unit] = dh_sm[r * U + pu];
             p.dHC0[b * (2 * H) + 2 * unit + 1] = dc_sm[r * U + pu];

@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
         int b = tile + p.n_tiles * (prg + i * RG);
         len[i] = b < p.B ? p.lengths[b] : 0;
     }
-    const int KS = pick_ks(U / 4, NTHREADS);
+    const int KS = pick_ks_fit(U / 4, U, ENC_KC_BWD, NTHREADS);
     const ThreadMap tm = make_map(tid, U / 4, KS);
     const int Tt = p.lengths[tile];
     const float* gs = p.gs[dir];

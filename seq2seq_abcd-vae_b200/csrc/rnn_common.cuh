@@ -22,8 +22,8 @@ namespace rnn {
 
 constexpr int CL = 16;             // CTAs per cluster (decoder; the encoder kernels use 8)
 constexpr int U = ABCD_H / CL;     // hidden units per CTA
-constexpr int RT = 5;              // rows per thread
-constexpr int NRG = 16;            // row groups
+constexpr int RT = 10;             // rows per thread (more FFMAs per LDS.128: an LDS.128 costs 4 smem-pipe cycles per warp)
+constexpr int NRG = 8;             // row groups
 constexpr int RG = NRG;            // thread of row group rg owns the interleaved rows rg + i*RG (i < RT): retiring
                                    // segments thin every row group evenly, so all warps keep equal work
 constexpr int ROWS = RT * NRG;     // rows (segments) per tile
@@ -69,6 +69,12 @@ __host__ __device__ inline Stage make_stage(float* base, int kc) {
     return s;
 }
 __host__ __device__ inline size_t stage_floats(int kc) { return (size_t)2 * ROWS * (kc + 4); }
+// K-split factor of a phase whose cross-split reduction scratch ((KS-1) x ROWS x ldw floats) must fit in the staging buffers
+__host__ __device__ inline int pick_ks_fit(int ncg, int ldw, int kc, int nthreads = NTHREADS) {
+    int ks = pick_ks(ncg, nthreads);
+    int cap = 1 + (int)(stage_floats(kc) / (size_t)(ROWS * ldw));
+    return ks < cap ? ks : cap;
+}
 
 __device__ __forceinline__ void zero_acc(float (&acc)[RT][4]) {
 #pragma unroll
@@ -163,6 +169,11 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[RT][4], const float* As, 
         case 2: mma_range<2, LDA, LDW>(acc, a_rg, w, n); break;
         case 3: mma_range<3, LDA, LDW>(acc, a_rg, w, n); break;
         case 4: mma_range<4, LDA, LDW>(acc, a_rg, w, n); break;
+        case 5: mma_range<5, LDA, LDW>(acc, a_rg, w, n); break;
+        case 6: mma_range<6, LDA, LDW>(acc, a_rg, w, n); break;
+        case 7: mma_range<7, LDA, LDW>(acc, a_rg, w, n); break;
+        case 8: mma_range<8, LDA, LDW>(acc, a_rg, w, n); break;
+        case 9: mma_range<9, LDA, LDW>(acc, a_rg, w, n); break;
         default: mma_range<RT, LDA, LDW>(acc, a_rg, w, n); break;
     }
 }
