@@ -35,8 +35,8 @@ CFG = dict(rnn='LSTM', F=65, K=128, f=256, H=256, M=256, B=512, N_data=100000)
 def parse():
 	p = argparse.ArgumentParser()
 	p.add_argument('--gpus', type=int, default=1)
-	p.add_argument('--steps', type=int, default=20)
-	p.add_argument('--warmup', type=int, default=5)
+	p.add_argument('--steps', type=int, default=100)
+	p.add_argument('--warmup', type=int, default=10)
 	p.add_argument('--impl', type=str, default='b200', choices=['b200', 'reference'])
 	p.add_argument('--batch', type=int, default=CFG['B'], help='segments per GPU')
 	p.add_argument('--bins', type=int, default=CFG['F'])
@@ -76,7 +76,7 @@ def flops_per_step(lengths, F, H=256, M=256, K=128, f=256, rnn='LSTM'):
 
 
 class ClockSampler(object):
-	"""nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+	"""nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
 
 	def __init__(self, gpu_index):
 		self.rows = []
@@ -86,7 +86,7 @@ class ClockSampler(object):
 	def start(self):
 		q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 		try:
-			self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '200'],
+			self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '50'],
 										stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
 			self.thread = threading.Thread(target=self._read, daemon=True)
 			self.thread.start()
@@ -166,7 +166,7 @@ def reference_arm(args):
 	rank = int(os.environ.get('RANK', '0'))
 	if rank != 0:
 		return
-	steps, warmup = max(1, min(args.steps, 5)), max(0, min(args.warmup, 1))
+	steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
 	val, dt, lengths = run_cpu(args, steps, warmup)
 	cores = torch.get_num_threads()
 	sample = '{} warm-up + {} timed full steps of the B={} batch (sumT={})'.format(warmup, steps, args.batch, int(lengths.sum()))
@@ -317,6 +317,16 @@ def main():
 					'note': 'fp32 FFMA kernel (fp32-exact mode); fraction is of the measured bf16 tensor peak; fp32 FFMA peak is ~72 TFLOP/s',
 					'frac_of_fp32_ffma_peak': achieved / 72.0, 'avg_launch_ms': dur * 1e3}
 
+	n_params = learner.arena.numel
+	hbm_peak = peaks.get('hbm_gbs', 6650.0)
+	other = {}
+	if 'clip_sgd' in groups:
+		gbs = n_params * 16 / (groups['clip_sgd']['ms_per_step'] * 1e-3) / 1e9   # 16 B/param: 4 norm read + 8 read + 4 write
+		other['clip_sgd'] = {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
+							'note': '27 MB arena, L2-resident between the norm and step passes'}
+	if 'philox' in groups:
+		gbs = (sumT * F + args.batch * CFG['K']) * 4 / (groups['philox']['ms_per_step'] * 1e-3) / 1e9
+		other['philox'] = {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak}
 	cpu_baseline = None
 	if rank == 0 and not args.no_cpu_baseline:
 		cval, cdt, _ = run_cpu(args, args.cpu_steps, 1)
@@ -329,7 +339,7 @@ def main():
 			'data': 'synthetic', 'config': workload_config(args, lengths, world), 'clocks': clock_info,
 			'e2e': {'value': e2e_value, 'unit': 'segments/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms},
 			'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu_baseline,
-			'kernel_groups': groups,
+			'kernel_groups': groups, 'rooflines_other': other,
 			'train_flops_per_step': flops_per_step(lengths, args.bins, rnn=args.rnn),
 			'achieved_tflops_whole_step': flops_per_step(lengths, args.bins, rnn=args.rnn) / (ms_per_step * 1e-3) / 1e12,
 		}
