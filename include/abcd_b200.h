@@ -87,8 +87,13 @@ const char* abcd_version(void);
 
 /* co-resident 16-CTA clusters of a persistent kernel (0 enc_fwd, 1 enc_bwd, 2 dec_fwd, 3 dec_bwd) for output size F */
 int abcd_max_active_clusters(int which, int F);
-/* debug (env ABCD_TIMING=1): per-phase clock cycles of CTA 0 of the last enc_fwd launch (setup, gemm, epilogue, barrier, steps) */
-int abcd_debug_enc_timing(unsigned long long* out5);
+/* debug (env ABCD_TIMING=1): per-phase clock cycles of CTA 0 of the last enc_fwd launch: out10[0..4] = setup, gemm,
+ * epilogue, barrier, steps; out10[5..9] = breakdown of the gemm phase */
+int abcd_debug_enc_timing(unsigned long long* out10);
+/* Encoder forward recurrence (model.py:60-66) on the tensor cores (tcgen05 kind::tf32, 3xTF32 split, fp32-grade) instead
+ * of the FFMA path.  on = 1/0; -1 only queries.  Returns the previous setting.  Initial value: env ABCD_RNN_TC (default 0:
+ * the FFMA path is currently the faster one). */
+int abcd_set_rnn_tensorcore(int on);
 /* kernel launches enqueued by this library since load (what bench.py reports as gpu_launches) */
 long long abcd_launch_count(void);
 /* optional CUDA-event timing per kernel group on the launching stream (off by default; used by bench.py for the

@@ -39,6 +39,7 @@ struct DecK {
     float* nll_partial;   // [gridDim.x]
     // backward only
     float* dML; float* dHidPre; float* dG; const float* dHoff; float* dHC0;
+    float* dbias;   // [n_tiles][4H]: per-tile column sums of dG (recurrent bias gradients), interleaved layout
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -325,6 +326,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
     const int Tt = p.lengths[tile];
     const int n_tiles = p.n_tiles, B = p.B;
     const float* dML = p.dML; const float* dHidPre = p.dHidPre; const float* dG = p.dG;
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);   // this thread's share of sum(dG) over rows and steps
     __syncthreads();
 
     for (int t = Tt - 1; t >= 0; --t) {
@@ -427,6 +429,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
                     dc_sm[r * U + pu] = dh * zg;
                 }
                 *reinterpret_cast<float4*>(p.dG + frame * (4 * H) + unit * 4) = dgv;
+                bsum.x += dgv.x; bsum.y += dgv.y; bsum.z += dgv.z; bsum.w += dgv.w;
             }
         }
         cluster_sync_all();
@@ -484,6 +487,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
             p.dHC0[b * (2 * H) + 2 * unit + 1] = dc_sm[r * U + pu];
         } else {
             p.dHC0[b * H + unit] = dh_sm[r * U + pu] + dc_sm[r * U + pu];
+        }
+    }
+    // recurrent bias gradients: fixed-order reduction over the row groups, one row of partial sums per tile
+    {
+        float4* red = reinterpret_cast<float4*>(st.buf0);
+        red[prg * U + pu] = bsum;
+        __syncthreads();
+        if (tid < U) {
+            float4 a = red[tid];
+            for (int g = 1; g < PRG; ++g) {
+                const float4 b = red[g * U + tid];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            *reinterpret_cast<float4*>(p.dbias + (long)tile * (4 * H) + (u0 + tid) * 4) = a;
         }
     }
 }
@@ -621,7 +638,7 @@ int launch_cluster_dec(K kernel, int n_clusters, size_t smem, cudaStream_t strea
 
 struct DecWs {
     float *hc0, *Hall, *Call, *Xall, *Gs, *Hid, *Mean, *Lv, *HidOff, *OffLogit, *nll_partial, *bce_partial;
-    float *dML, *dHidPre, *dG, *dHoff, *dHidOffPre, *dLogit, *dHC0, *partials;
+    float *dML, *dHidPre, *dG, *dHoff, *dHidOffPre, *dLogit, *dHC0, *dbias, *partials;
     int* prev;
     size_t partial_floats;
     size_t bytes;
@@ -654,6 +671,7 @@ DecWs dec_carve(void* base, size_t cap, int cell, int F, int fin, int B, int sum
     w.dHidOffPre = a.take<float>((size_t)sumT * M);
     w.dLogit = a.take<float>((size_t)sumT);
     w.dHC0 = a.take<float>((size_t)B * hc);
+    w.dbias = a.take<float>((size_t)n_tiles * 4 * H);
     w.prev = a.take<int>((size_t)sumT);
     // largest split-K partial: dW_hh / dW_ih ([4H] x [H|F]) or MLP weights ([M] x [H])
     size_t mx = 0;
@@ -680,7 +698,7 @@ DecK make_k(const DecParams& P, const PackedMeta& pk, const DecWs& w) {
     for (int i = 0; i < 2; ++i) { k.em_w1[i] = P.em_w1[i]; k.em_b1[i] = P.em_b1[i]; k.em_w2[i] = P.em_w2[i]; k.em_b2[i] = P.em_b2[i]; }
     k.Hall = w.Hall; k.Call = w.Call; k.Xall = w.Xall; k.Gs = w.Gs; k.Hid = w.Hid; k.Mean = w.Mean; k.Lv = w.Lv;
     k.nll_partial = w.nll_partial;
-    k.dML = w.dML; k.dHidPre = w.dHidPre; k.dG = w.dG; k.dHoff = w.dHoff; k.dHC0 = w.dHC0;
+    k.dML = w.dML; k.dHidPre = w.dHidPre; k.dG = w.dG; k.dHoff = w.dHoff; k.dHC0 = w.dHC0; k.dbias = w.dbias;
     return k;
 }
 
@@ -842,8 +860,9 @@ int dec_backward(const DecParams& P, const DecGrads& G, const PackedMeta& pk, co
     const GateMap map_hh = P.cell == 0 ? gate_map(H, 0, 1, 2, 3) : gate_map(H, 0, 1, -1, 2);
     TRY(tn(4 * H, F, w.dG, 4 * H, w.Xall, Fp, w.prev, map_ih, G.w_ih, F, sumT));
     TRY(tn(4 * H, H, w.dG, 4 * H, w.Hall, H, w.prev, map_hh, G.w_hh, H, sumT));
-    TRY(colsum_launch(w.dG, 4 * H, sumT, 4 * H, 1.f, G.b_ih, 1, map_ih, stream));
-    TRY(colsum_launch(w.dG, 4 * H, sumT, 4 * H, 1.f, G.b_hh, 1, map_hh, stream));
+    // the BPTT kernel already reduced dG over the frames of every tile
+    TRY(colsum_launch(w.dbias, 4 * H, (pk.B + ROWS - 1) / ROWS, 4 * H, 1.f, G.b_ih, 1, map_ih, stream));
+    TRY(colsum_launch(w.dbias, 4 * H, (pk.B + ROWS - 1) / ROWS, 4 * H, 1.f, G.b_hh, 1, map_hh, stream));
     for (int i = 0; i < 2; ++i) {
         TRY(tn(M, H, w.dHidPre + i * M, 2 * M, Hfr, H, nullptr, gate_map_none(), G.em_w1[i], H, sumT));
         TRY(colsum_launch(w.dHidPre + i * M, 2 * M, sumT, M, 1.f, G.em_b1[i], 1, gate_map_none(), stream));

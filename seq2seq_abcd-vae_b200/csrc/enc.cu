@@ -8,6 +8,7 @@
 //         + weight/bias gradients as large TN GEMMs over all frames.
 #include <stdlib.h>
 #include "rnn_common.cuh"
+#include "rnn_tc.cuh"
 #include "sgemm.cuh"
 #include "enc.cuh"
 
@@ -77,14 +78,24 @@ struct EncFwdK {
     float* out;              // [B][out_ld]
 };
 
-template <int CELL>
+// TC = true: the per-step gate contraction runs on the tensor cores (rnn_tc.cuh); shared memory is then
+// [operand tiles][W_hh slice][raw staging ring] instead of [W_hh slice][staging buffers].
+template <int CELL, bool TC>
 __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
-    constexpr int CL = ENC_CL, U = ENC_U, NTHREADS = ENC_NT;   // 8-CTA clusters, 32 units per CTA, 512 threads
-    extern __shared__ __align__(16) float smem[];
-    float* Wsm = smem;                          // [H][U*4]
+    constexpr int CL = ENC_CL, U = ENC_U, NTHREADS = ENC_NT;   // 8-CTA clusters, 32 units per CTA, 256 threads
+    extern __shared__ __align__(1024) float smem[];
+    using TS = TcShape<ENC_U * 4>;
+    float* Wsm = TC ? smem + TS::TILE_BYTES / 4 : smem;        // [H][U*4]
     const Stage st = make_stage(Wsm + ABCD_H * (U * 4), ENC_KC_FWD);
+    __shared__ uint64_t tc_bars[3];
+    __shared__ uint32_t tc_tmem_slot;
+    TcCtx tc;
 
     const int tid = threadIdx.x;
+    if (TC) {
+        if ((umma::smem_u32(smem) & 1023u) != 0) __trap();      // operand tiles need 1024-byte alignment
+        tc_init<TS::TMEM_COLS>(tc, reinterpret_cast<char*>(smem), Wsm + ABCD_H * (U * 4), tc_bars, &tc_tmem_slot, tid);
+    }
     const int rank = (int)cluster_ctarank();
     const int cid = blockIdx.x / CL;
     const int tile = cid % p.n_tiles, dir = cid / p.n_tiles;
@@ -125,7 +136,7 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
 
     unsigned long long tacc[5] = {0, 0, 0, 0, 0};
     unsigned long long pg[5] = {0, 0, 0, 0, 0};
-    const bool timing = p.timing && blockIdx.x == 0 && tid == 0;
+    const bool timing = p.timing && blockIdx.x == 0 && tid == ((TC && p.timing == 1) ? 32 : 0);
     for (int s = 0; s < Tt; ++s) {
         long long c0 = timing ? clock64() : 0;
         const int t = dir == 0 ? s : Tt - 1 - s;
@@ -158,7 +169,8 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
                 long row = save ? (long)off_prev + b : (long)((s - 1) & 1) * B + b;
                 return hs + row * ABCD_H;
             };
-            phase_gemm<ENC_NT, ENC_KC_FWD, ENC_U * 4>(acc, st, H, rp, 0, NullRow(), na, Wsm, tm, 1, tid, timing ? pg : nullptr);
+            if (TC) phase_gemm_tc<ENC_NT, ENC_U * 4, ENC_U * 4>(acc, tc, H, rp, 0, NullRow(), na, Wsm, tm, tid, timing ? pg : nullptr);
+            else phase_gemm<ENC_NT, ENC_KC_FWD, ENC_U * 4>(acc, st, H, rp, 0, NullRow(), na, Wsm, tm, 1, tid, timing ? pg : nullptr);
         }
         long long c2 = timing ? clock64() : 0;
 #pragma unroll
@@ -207,6 +219,7 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
         }
     }
     if (timing) for (int i = 0; i < 5; ++i) { g_enc_timing[i] = tacc[i]; g_enc_timing[5 + i] = pg[i]; }
+    if (TC) tc_fini<TS::TMEM_COLS>(tc, tid);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -219,6 +232,7 @@ struct EncBwdK {
     const float* hs[2]; const float* gs[2]; const float* cs[2];
     const float* d_out;   // [B][out_ld]
     float* dg[2];         // [sumT][4H]
+    float* dbias[2];      // [n_tiles][4H]: per-tile column sums of dg (bias gradients), interleaved layout
 };
 
 template <int CELL>
@@ -264,6 +278,7 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
     const float* cs = p.cs[dir];
     const float* hs = p.hs[dir];
     float* dg = p.dg[dir];
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);   // this thread's share of the bias gradient (sum of dG over rows and steps)
     __syncthreads();
 
     for (int s = 0; s < Tt; ++s) {
@@ -335,6 +350,7 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
                 dc_sm[r * U + pu] = dh * zg;
             }
             *reinterpret_cast<float4*>(dg + frame * (4 * H) + unit * 4) = dgv;
+            bsum.x += dgv.x; bsum.y += dgv.y; bsum.z += dgv.z; bsum.w += dgv.w;
         }
         cluster_sync_all();
         // dh_prev[rows, my units] = dG[rows, 4H] * W_hh[4H, my units]; only rows that have a previous frame
@@ -355,9 +371,32 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
         }
         __syncthreads();
     }
+    // bias gradients: fixed-order reduction over the row groups, one row of partial sums per tile
+    {
+        float4* red = reinterpret_cast<float4*>(st.buf0);
+        red[prg * U + pu] = bsum;
+        __syncthreads();
+        if (tid < U) {
+            float4 a = red[tid];
+            for (int g = 1; g < NTHREADS / U; ++g) {
+                const float4 b = red[g * U + tid];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            *reinterpret_cast<float4*>(p.dbias[dir] + (long)tile * (4 * H) + (u0 + tid) * 4) = a;
+        }
+    }
 }
 
-size_t enc_fwd_smem() { return (size_t)(ABCD_H * ENC_U * 4 + stage_floats(ENC_KC_FWD)) * sizeof(float); }
+size_t enc_fwd_smem(bool tc) {
+    if (tc) return (size_t)TcShape<ENC_U * 4>::TILE_BYTES + (size_t)ABCD_H * ENC_U * 4 * sizeof(float) + tc_raw_bytes();
+    return (size_t)(ABCD_H * ENC_U * 4 + stage_floats(ENC_KC_FWD)) * sizeof(float);
+}
+// tensor-core recurrence: env ABCD_RNN_TC=1 or abcd_set_rnn_tensorcore(1)
+int g_rnn_tc = -1;
+bool rnn_use_tc() {
+    if (g_rnn_tc < 0) { const char* e = getenv("ABCD_RNN_TC"); g_rnn_tc = (e && e[0] == '1') ? 1 : 0; }
+    return g_rnn_tc == 1;
+}
 size_t enc_bwd_smem() { return (size_t)(4 * ABCD_H * ENC_U + 2 * ROWS * ENC_U + stage_floats(ENC_KC_BWD)) * sizeof(float); }
 
 template <class K, class P>
@@ -400,8 +439,15 @@ int rnn_max_active_clusters(const void* fn, size_t smem, int cluster, int thread
     return ABCD_OK;
 }
 int enc_max_clusters(int which, int* out) {
-    const void* fn = which == 0 ? (const void*)enc_fwd_kernel<0> : (const void*)enc_bwd_kernel<0>;
-    return rnn_max_active_clusters(fn, which == 0 ? enc_fwd_smem() : enc_bwd_smem(), ENC_CL, ENC_NT, out);
+    const bool tc = rnn_use_tc();
+    const void* fn = which == 0 ? (tc ? (const void*)enc_fwd_kernel<0, true> : (const void*)enc_fwd_kernel<0, false>) : (const void*)enc_bwd_kernel<0>;
+    return rnn_max_active_clusters(fn, which == 0 ? enc_fwd_smem(tc) : enc_bwd_smem(), ENC_CL, ENC_NT, out);
+}
+
+int rnn_set_tc(int on) {
+    const int prev = rnn_use_tc() ? 1 : 0;
+    if (on == 0 || on == 1) g_rnn_tc = on;
+    return prev;
 }
 
 int enc_read_timing(unsigned long long* out5) {
@@ -410,8 +456,10 @@ int enc_read_timing(unsigned long long* out5) {
 }
 
 int enc_init() {
-    TRY(rnn_prepare_kernel((const void*)enc_fwd_kernel<0>, enc_fwd_smem()));
-    TRY(rnn_prepare_kernel((const void*)enc_fwd_kernel<1>, enc_fwd_smem()));
+    TRY(rnn_prepare_kernel((const void*)enc_fwd_kernel<0, false>, enc_fwd_smem(false)));
+    TRY(rnn_prepare_kernel((const void*)enc_fwd_kernel<1, false>, enc_fwd_smem(false)));
+    TRY(rnn_prepare_kernel((const void*)enc_fwd_kernel<0, true>, enc_fwd_smem(true)));
+    TRY(rnn_prepare_kernel((const void*)enc_fwd_kernel<1, true>, enc_fwd_smem(true)));
     TRY(rnn_prepare_kernel((const void*)enc_bwd_kernel<0>, enc_bwd_smem()));
     TRY(rnn_prepare_kernel((const void*)enc_bwd_kernel<1>, enc_bwd_smem()));
     return ABCD_OK;
@@ -425,6 +473,7 @@ struct EncWs {
     float* gs[2];
     float* cs[2];
     float* dg[2];
+    float* dbias[2];
     int* prev_fwd;
     int* prev_bwd;
     float* xpad;      // [sumT][pad4(F)] copy of the input with 16-byte aligned rows (bulk-copy friendly)
@@ -450,6 +499,7 @@ static EncWs enc_carve(void* base, size_t cap, int cell, int F, int B, int sumT,
     if (save) {
         // dG aliases xproj (dead after the forward recurrence) -- both [sumT][4H] per direction
         for (int d = 0; d < ndirs; ++d) w.dg[d] = w.xproj[d];
+        for (int d = 0; d < ndirs; ++d) w.dbias[d] = a.take<float>((size_t)((B + ROWS - 1) / ROWS) * 4 * H);
         w.prev_fwd = a.take<int>(sumT);
         w.prev_bwd = a.take<int>(sumT);
         w.xpad = a.take<float>((size_t)sumT * ((F + 3) & ~3));
@@ -480,7 +530,7 @@ int enc_forward(const EncParams& P, const PackedMeta& pk, const float* x, int ld
     EncFwdK k;
     memset(&k, 0, sizeof(k));
     k.n_tiles = n_tiles; k.B = pk.B; k.ndirs = ndirs; k.save = save;
-    k.timing = getenv("ABCD_TIMING") != nullptr;
+    k.timing = getenv("ABCD_TIMING") ? atoi(getenv("ABCD_TIMING")) : 0;
     k.out_ld = ndirs * H * (P.cell == 0 ? 2 : 1);
     k.batch_sizes = pk.batch_sizes; k.offsets = pk.offsets; k.lengths = pk.lengths;
     k.out = last_hidden;
@@ -501,8 +551,14 @@ int enc_forward(const EncParams& P, const PackedMeta& pk, const float* x, int ld
     (void)ngates;
     {
         ProfScope ps(PROF_ENC_FWD, stream);
-        if (P.cell == 0) TRY(launch_cluster(enc_fwd_kernel<0>, n_tiles * ndirs, enc_fwd_smem(), stream, k));
-        else TRY(launch_cluster(enc_fwd_kernel<1>, n_tiles * ndirs, enc_fwd_smem(), stream, k));
+        const bool tc = rnn_use_tc();
+        if (P.cell == 0) {
+            if (tc) TRY(launch_cluster(enc_fwd_kernel<0, true>, n_tiles * ndirs, enc_fwd_smem(true), stream, k));
+            else TRY(launch_cluster(enc_fwd_kernel<0, false>, n_tiles * ndirs, enc_fwd_smem(false), stream, k));
+        } else {
+            if (tc) TRY(launch_cluster(enc_fwd_kernel<1, true>, n_tiles * ndirs, enc_fwd_smem(true), stream, k));
+            else TRY(launch_cluster(enc_fwd_kernel<1, false>, n_tiles * ndirs, enc_fwd_smem(false), stream, k));
+        }
     }
     return ABCD_OK;
 }
@@ -524,7 +580,7 @@ int enc_backward(const EncParams& P, const EncGrads& G, const PackedMeta& pk, co
     k.batch_sizes = pk.batch_sizes; k.offsets = pk.offsets; k.lengths = pk.lengths;
     k.d_out = d_last_hidden;
     for (int d = 0; d < ndirs; ++d) {
-        k.w_hh[d] = P.w_hh[d]; k.hs[d] = w.hs[d]; k.gs[d] = w.gs[d]; k.cs[d] = w.cs[d]; k.dg[d] = w.dg[d];
+        k.w_hh[d] = P.w_hh[d]; k.hs[d] = w.hs[d]; k.gs[d] = w.gs[d]; k.cs[d] = w.cs[d]; k.dg[d] = w.dg[d]; k.dbias[d] = w.dbias[d];
     }
     {
         ProfScope ps(PROF_ENC_BWD, stream);
@@ -558,8 +614,9 @@ int enc_backward(const EncParams& P, const EncGrads& G, const PackedMeta& pk, co
         g.m_dst = map_ih; g.C = G.w_ih[d]; g.ldc = P.F;
         g.splits = sgemm_pick_splits(g.M, g.N, g.K);
         TRY(sgemm_launch(g, stream));
-        TRY(colsum_launch(w.dg[d], 4 * H, pk.sumT, 4 * H, 1.f, G.b_ih[d], 1, map_ih, stream));
-        TRY(colsum_launch(w.dg[d], 4 * H, pk.sumT, 4 * H, 1.f, G.b_hh[d], 1, map_hh, stream));
+        // bias gradients: the BPTT kernel already reduced dG over the frames of every tile
+        TRY(colsum_launch(w.dbias[d], 4 * H, n_tiles, 4 * H, 1.f, G.b_ih[d], 1, map_ih, stream));
+        TRY(colsum_launch(w.dbias[d], 4 * H, n_tiles, 4 * H, 1.f, G.b_hh[d], 1, map_hh, stream));
     }
     return ABCD_OK;
 }

@@ -1,0 +1,95 @@
+// tcgen05 (5th-gen tensor core) building blocks shared by the weight-gradient GEMM (umma_gemm.cu) and the
+// recurrent kernels' tensor-core phase (rnn_tc.cuh): shared-memory / instruction descriptors for kind::tf32 with
+// MN-major operands, mbarrier helpers and the 3xTF32 operand split.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start[0,14) LBO[16,30) SBO[32,46) version[46,48)=1
+// layout[61,64)=1 (SWIZZLE_128B_BASE32B, the only MN-major layout for 32-bit operands); byte quantities >> 4.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b_format TF32 [7,10),[10,13)=2,
+// a_major/b_major MN [15],[16]=1, n_dim [17,23)=N>>3, m_dim [24,29)=M>>4.
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    // bounded: a lost arrival traps (reported as a launch failure) instead of hanging the GPU
+    for (uint32_t spins = 0; !done; ++spins) {
+        if (spins > (1u << 24)) __trap();
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+// mbarrier arrive once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// Byte offset of element (k, mn) of an MN-major operand tile made of [KROWS k][32 mn] chunks (CHUNK_BYTES =
+// KROWS*128): rows of a chunk are 128 B apart (atoms of 4 rows are SBO = 512 B apart), chunks along MN are
+// LBO = CHUNK_BYTES apart, the 32-byte piece index inside a row is XOR-ed with k & 3.
+template <int CHUNK_BYTES>
+__device__ __forceinline__ uint32_t tile_off(int k, int mn4 /* float4 index along mn */) {
+    const int chunk = mn4 >> 3, piece = mn4 & 7;
+    const int c32 = piece >> 1, half = piece & 1;
+    return (uint32_t)(chunk * CHUNK_BYTES + k * 128 + (((c32 ^ (k & 3)) << 5) | (half << 4)));
+}
+// 3xTF32 split: hi = x with the low 13 mantissa bits cleared (exact in TF32), lo = x - hi (exact in fp32)
+__device__ __forceinline__ void split_store(char* hi_base, char* lo_base, uint32_t off, float4 v) {
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(hi_base + off) = h;
+    *reinterpret_cast<float4*>(lo_base + off) = l;
+}
+// 16 accumulator columns of this warp's 32 TMEM lanes
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+}  // namespace umma

@@ -11,9 +11,8 @@
 // row, relative to the largest output); split-K keeps that to a few hundred rows.
 //
 // Structure per CTA (256 threads, one 128-row M tile, all N <= 256 columns, one K split), 32-row K slabs:
-//   TMA engine    warp 0 issues one cp.async.bulk per operand row (512 B of A, 4N B of B, optional row gather) into a
-//                 2-slot staging ring; completion is counted on an mbarrier (expect_tx / complete_tx)
-//   all threads   wait for the slab, wait for the previous slab's MMAs (mbarrier armed by tcgen05.commit), split the
+//   all threads   cp.async (16-byte pieces, optional row gather on B) the raw fp32 rows of slab s+2 into a 2-slot
+//                 staging ring, wait for slab s and for the previous slab's MMAs (mbarrier armed by tcgen05.commit), split the
 //                 staged fp32 rows into hi and lo tiles in the canonical MN-major layout for 32-bit operands
 //                 (cute::UMMA::Layout_MN_SW128_32B_Atom: atoms of 4 k-rows x 128 B, 32-byte chunks XOR row index)
 //   fence.proxy.async + CTA barrier; the freed staging slot is refilled two slabs ahead
@@ -22,8 +21,9 @@
 //                 blocks) -> fp32 partials [split][M][N]; the common split-K reduce kernel applies alpha / gate
 //                 map / accumulate.
 // Operands whose B rows are not 16-byte aligned (the encoder's user-supplied [sumT, 65] input) take the same path
-// with plain loads into the staging ring instead of bulk copies.
+// with 4-byte cp.async pieces.
 #include "sgemm.cuh"
+#include "umma.cuh"
 
 namespace {
 
@@ -44,70 +44,10 @@ struct UmmaArgs {
     float* partials;   // [splits][M][N]
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start[0,14) LBO[16,30) SBO[32,46) version[46,48)=1
-// layout[61,64)=1 (SWIZZLE_128B_BASE32B, the only MN-major layout for 32-bit operands); byte quantities >> 4.
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr >> 4) & 0x3FFFu);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)1 << 61;
-    return d;
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b_format TF32 [7,10),[10,13)=2,
-// a_major/b_major MN [15],[16]=1, n_dim [17,23)=N>>3, m_dim [24,29)=M>>4.
-__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    }
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// byte offset of element (k, mn) of an operand tile: rows of a 32-column chunk are 128 B apart (atoms of 4 rows are
-// SBO = 512 B apart), chunks along MN are LBO = 4 KB apart, the 32-byte chunk index inside a row is XOR-ed with k & 3.
-__device__ __forceinline__ uint32_t tile_off(int k, int mn4 /* float4 index along mn */) {
-    const int chunk = mn4 >> 3, piece = mn4 & 7;
-    const int c32 = piece >> 1, half = piece & 1;
-    return (uint32_t)(chunk * UM_CHUNK_BYTES + k * 128 + (((c32 ^ (k & 3)) << 5) | (half << 4)));
-}
-__device__ __forceinline__ void split_store(char* hi_base, char* lo_base, uint32_t off, float4 v) {
-    float4 h, l;
-    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-    *reinterpret_cast<float4*>(hi_base + off) = h;
-    *reinterpret_cast<float4*>(lo_base + off) = l;
-}
+using umma::smem_u32; using umma::make_desc; using umma::make_idesc; using umma::mma_tf32; using umma::mbar_init;
+using umma::mbar_wait; using umma::split_store;
+__device__ __forceinline__ void umma_commit(uint64_t* bar) { umma::commit(bar); }
+__device__ __forceinline__ uint32_t tile_off(int k, int mn4) { return umma::tile_off<UM_CHUNK_BYTES>(k, mn4); }
 
 template <int NCH /* 32-column chunks of B: 1..8 */>
 __global__ void __launch_bounds__(UM_THREADS, 1) umma_tn_kernel(UmmaArgs g) {
@@ -122,7 +62,6 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_tn_kernel(UmmaArgs g) {
     char* b_lo = b_hi + B_TILE;
     char* stage = b_lo + B_TILE;                               // UM_STAGES x STAGE_BYTES
     __shared__ uint64_t mma_bar;
-    __shared__ uint64_t full_bar[UM_STAGES];
     __shared__ uint32_t tmem_base_sh;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -138,7 +77,6 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_tn_kernel(UmmaArgs g) {
     }
     if (tid == 0) {
         mbar_init(&mma_bar, 1);
-        for (int i = 0; i < UM_STAGES; ++i) mbar_init(&full_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");

@@ -164,7 +164,8 @@ class Learner(object):
 		emission_loss, end_loss, kl_loss, logits = self.forward_losses(packed_input, is_offset, speaker, num_strings, is_pretraining)
 		batch_size = int(packed_input.batch_sizes[0]) if global_batch_size is None else global_batch_size
 		loss = (emission_loss + end_loss + kl_loss) / batch_size
-		loss.backward()
+		with model.accumulate_into_grad():   # kernels add straight into the flat gradient arena
+			loss.backward()
 		if self.world_size > 1:
 			torch.distributed.all_reduce(self.arena.grad, op=torch.distributed.ReduceOp.SUM, group=self.process_group)
 		lr = self.optimizer.param_groups[0]['lr']

@@ -23,6 +23,43 @@ def _f32(t):
 	return t.contiguous()
 
 
+# Every backward entry point of the library ACCUMULATES parameter gradients into the buffers it is given.  Inside
+# `accumulate_into_grad()` (learning.Learner.train_step wraps loss.backward() in it) the buffers are the leaf
+# parameters' existing .grad tensors -- exactly what autograd's AccumulateGrad would do with a returned gradient, minus
+# one zero-fill and one add kernel per parameter.  Outside it (torch.autograd.grad, hooks, parameters without a .grad
+# yet) fresh zero buffers are filled and returned to autograd as usual.
+_DIRECT_GRADS = False
+
+
+class accumulate_into_grad(object):
+	def __enter__(self):
+		global _DIRECT_GRADS
+		self.prev = _DIRECT_GRADS
+		_DIRECT_GRADS = True
+		return self
+
+	def __exit__(self, *exc):
+		global _DIRECT_GRADS
+		_DIRECT_GRADS = self.prev
+		return False
+
+
+def _grad_buffers(tensors):
+	"""-> (buffers handed to the kernel, values returned to autograd) for parameter-like inputs."""
+	bufs, rets = [], []
+	for t in tensors:
+		g = t.grad if (_DIRECT_GRADS and t.is_leaf and t.requires_grad) else None
+		if (g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == t.shape and g.device == t.device
+				and not t._backward_hooks):
+			bufs.append(g)
+			rets.append(None)
+		else:
+			z = torch.zeros_like(t)
+			bufs.append(z)
+			rets.append(z)
+	return bufs, rets
+
+
 def _cell_code(rnn_type):
 	if rnn_type == 'LSTM':
 		return 0
@@ -154,13 +191,13 @@ class _MlpFn(torch.autograd.Function):
 		x, hid, w1, b1, w2, b2 = ctx.saved_tensors
 		dy = _f32(dy)
 		rows = x.shape[0]
-		grads = [torch.zeros_like(t) for t in (w1, b1, w2, b2)]
+		grads, rets = _grad_buffers((w1, b1, w2, b2))
 		dx = torch.empty_like(x)
 		scratch = torch.empty(rows * w1.shape[0], dtype=torch.float32, device=x.device)
 		p = L.MlpParamsT(w1.shape[1], w1.shape[0], w2.shape[0], L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2))
 		g = L.MlpGradsT(*[L.ptr(t) for t in grads])
 		L.call('abcd_mlp_bwd', C.byref(p), C.byref(g), rows, L.ptr(x), L.ptr(hid), L.ptr(dy), L.ptr(dx), L.ptr(scratch), L.stream_ptr())
-		return (dx,) + tuple(grads)
+		return (dx,) + tuple(rets)
 
 
 class MLP(torch.nn.Module):
@@ -255,7 +292,7 @@ class _EncoderFn(torch.autograd.Function):
 		desc = ctx.desc
 		ndirs = 2 if ctx.bidir else 1
 		d_out = _f32(d_out)
-		grads = [torch.zeros_like(p) for p in params]
+		grads, rets = _grad_buffers(params)
 		ep = L.EncParamsT()
 		ep.cell, ep.F, ep.H, ep.bidir = ctx.cell, x.shape[1], ctx.hidden, int(ctx.bidir)
 		eg = L.EncGradsT()
@@ -264,7 +301,7 @@ class _EncoderFn(torch.autograd.Function):
 			eg.w_ih[d], eg.w_hh[d], eg.b_ih[d], eg.b_hh[d] = [L.ptr(g) for g in grads[4 * d:4 * d + 4]]
 		L.call('abcd_enc_bwd', C.byref(ep), C.byref(eg), desc.ref(), L.ptr(x), x.shape[1], L.ptr(d_out),
 			L.ptr(ctx.ws), ctx.ws_bytes, L.stream_ptr())
-		return (None, None, None, None, None) + tuple(grads)
+		return (None, None, None, None, None) + tuple(rets)
 
 
 class RNN_Variational_Encoder(torch.nn.Module):
@@ -345,14 +382,14 @@ class _LogitsFn(torch.autograd.Function):
 		x, hid, xc, w1, b1, w2, b2, codebook = ctx.saved_tensors
 		dlogits = _f32(dlogits)
 		B = x.shape[0]
-		grads = [torch.zeros_like(t) for t in (w1, b1, w2, b2, codebook)]
+		grads, rets = _grad_buffers((w1, b1, w2, b2, codebook))
 		dx = torch.empty_like(x)
 		f, hidden = w2.shape[0], w1.shape[0]
 		scratch = torch.empty(B * (f + max(hidden, f)), dtype=torch.float32, device=x.device)
 		sp, sg = _sampler_structs(w1, b1, w2, b2, codebook, None, 1.0, grads + [None])
 		L.call('abcd_sampler_logits_bwd', C.byref(sp), C.byref(sg), B, L.ptr(x), L.ptr(hid), L.ptr(xc), L.ptr(dlogits),
 			L.ptr(dx), L.ptr(scratch), L.stream_ptr())
-		return (dx,) + tuple(grads)
+		return (dx,) + tuple(rets)
 
 
 class _SampleFn(torch.autograd.Function):
@@ -376,7 +413,7 @@ class _SampleFn(torch.autograd.Function):
 		y, codebook = ctx.saved_tensors
 		dfeat = _f32(dfeat)
 		B, K = y.shape
-		gcb = torch.zeros_like(codebook)
+		(gcb,), (gcb_ret,) = _grad_buffers((codebook,))
 		dlogits = torch.empty_like(y)
 		scratch = torch.empty(B * K, dtype=torch.float32, device=y.device)
 		sp = L.SamplerParamsT()
@@ -384,7 +421,7 @@ class _SampleFn(torch.autograd.Function):
 		sg = L.SamplerGradsT()
 		sg.codebook = L.ptr(gcb)
 		L.call('abcd_sampler_sample_bwd', C.byref(sp), C.byref(sg), B, L.ptr(y), ctx.mode, ctx.tau, L.ptr(dfeat), L.ptr(dlogits), L.ptr(scratch), L.stream_ptr())
-		return dlogits, gcb, None, None, None
+		return dlogits, gcb_ret, None, None, None
 
 
 class _KlFn(torch.autograd.Function):
@@ -408,13 +445,13 @@ class _KlFn(torch.autograd.Function):
 		g_kl = _f32(g_kl)
 		B, K = logits.shape
 		dlogits = torch.empty_like(logits)
-		dshape = torch.zeros_like(shape_logits)
+		(dshape,), (dshape_ret,) = _grad_buffers((shape_logits,))
 		sp = L.SamplerParamsT()
 		sp.K, sp.shape_logits, sp.prior_c = K, L.ptr(shape_logits), ctx.prior_c
 		sg = L.SamplerGradsT()
 		sg.shape_logits = L.ptr(dshape)
 		L.call('abcd_sampler_kl_bwd', C.byref(sp), C.byref(sg), B, L.ptr(logits), ctx.n_data, L.ptr(g_kl), L.ptr(dlogits), L.ptr(ws), L.stream_ptr())
-		return dlogits, dshape, None, None
+		return dlogits, dshape_ret, None, None
 
 
 class ABCDSampler(torch.nn.Module):
@@ -584,12 +621,12 @@ class _DecoderFn(torch.autograd.Function):
 			g[0] = g_em
 		if g_off is not None:
 			g[1] = g_off
-		grads = [torch.zeros_like(p) for p in params]
+		grads, rets = _grad_buffers(params)
 		d_feat = torch.empty_like(feat_in)
 		dp, dg = _dec_structs(ctx.cell, F, H, M, feat_in.shape[1], params, grads)
 		L.call('abcd_dec_bwd', C.byref(dp), C.byref(dg), ctx.desc.ref(), L.ptr(feat_in), L.ptr(eps), eps.shape[1],
 			L.ptr(gt), gt.shape[1], L.ptr(is_offset), L.ptr(g), L.ptr(d_feat), L.ptr(ctx.ws), ctx.ws_bytes, L.stream_ptr())
-		return (d_feat, None, None, None, None, None, None) + tuple(grads)
+		return (d_feat, None, None, None, None, None, None) + tuple(rets)
 
 
 class RNN_Variational_Decoder(torch.nn.Module):

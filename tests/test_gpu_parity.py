@@ -122,6 +122,40 @@ def test_encoder_large_ragged_batch_matches_oracle(abcd):
 		assert rel_to_max(got, want) < TOL
 
 
+def test_encoder_tensorcore_recurrence_matches_oracle(abcd):
+	"""Encoder forward with the per-step gate contraction on tcgen05 (kind::tf32, 3xTF32 split; rnn_tc.cuh), both the
+	training (saving) path -- checked through the full backward -- and the inference path; same fp32-grade tolerance."""
+	lib = abcd._lib.load()
+	prev = lib.abcd_set_rnn_tensorcore(1)
+	try:
+		assert lib.abcd_set_rnn_tensorcore(-1) == 1
+		for rnn, seed in (('LSTM', 21), ('GRU', 22)):
+			lengths = sorted([1, 2, 3, 5, 8, 8, 13, 21, 34, 55] * 9 + [60, 47, 3], reverse=True)   # B = 93: two row tiles
+			F = 65
+			enc = abcd.model.RNN_Variational_Encoder(F, 256, rnn_type=rnn)
+			sd = CS.det_state(enc, seed)
+			enc.load_state_dict(sd)
+			enc.cuda()
+			seqs = CS.make_inputs(lengths, F, seed)
+			packed = torch.nn.utils.rnn.pack_sequence(seqs)
+			P = {k[len('rnn.'):]: v.double() for k, v in sd.items()}
+			want = O.encoder_forward([s.double() for s in seqs], P, rnn)
+			with torch.no_grad():
+				got = enc(torch.nn.utils.rnn.PackedSequence(packed.data.cuda(), packed.batch_sizes))
+			assert rel_to_max(got, want) < TOL
+			# training path: forward saves activations, gradient of sum(out * w) w.r.t. the weights
+			wsum = torch.from_numpy(O.det_uniform(tuple(want.shape), seed + 100, -1.0, 1.0))
+			out = enc(torch.nn.utils.rnn.PackedSequence(packed.data.cuda(), packed.batch_sizes))
+			assert rel_to_max(out.detach(), want) < TOL
+			(out * wsum.float().cuda()).sum().backward()
+			Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+			(O.encoder_forward([s.double() for s in seqs], Pg, rnn) * wsum.double()).sum().backward()
+			for k, v in Pg.items():
+				assert rel_to_max(dict(enc.named_parameters())['rnn.' + k].grad, v.grad) < TOL, k
+	finally:
+		lib.abcd_set_rnn_tensorcore(prev)
+
+
 def test_encode_argmax_bit_exact(abcd):
 	"""Encoder.encode (encode.py:28-32): probabilities within tolerance, category arg-max identical."""
 	cfg = dict(rnn='LSTM', F=65, K=128, f=256)

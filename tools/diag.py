@@ -63,6 +63,7 @@ def enc_timing():
 	if v[4]:
 		print('enc_fwd CTA0 cycles/step: setup %.0f gemm %.0f epilogue %.0f barrier %.0f (steps %d)' % (v[0] / v[4], v[1] / v[4], v[2] / v[4], v[3] / v[4], v[4]))
 		print("   phase_gemm per step: stage-issue %.0f wait+sync %.0f mma %.0f tail-sync %.0f chunks/step %.2f" % (v[5] / v[4], v[6] / v[4], v[7] / v[4], v[9] / v[4], v[8] / v[4]))
+		print("   (tensor-core phase: prologue %.0f stage-wait %.0f split %.0f fence+sync %.0f issue %.0f)" % tuple(x / v[4] for x in v[5:10]))
 
 
 if os.environ.get('ABCD_TIMING'):
