@@ -36,7 +36,9 @@ struct DecK {
     // activations (see DecWs)
     float* Hall; float* Call; float* Xall; float* Gs; float* Hid; float* Mean; float* Lv;
     const float* eps; const float* gt;
+    int timing;   // debug: per-phase clock cycles of CTA 0 -> g_dec_timing
     float* nll_partial;   // [gridDim.x]
+    float* Pbuf;          // [n_tiles][CL][ROWS][2Fp] partial emission parameters exchanged inside a cluster
     // backward only
     float* dML; float* dHidPre; float* dG; const float* dHoff; float* dHC0;
     float* dbias;   // [n_tiles][4H]: per-tile column sums of dG (recurrent bias gradients), interleaved layout
@@ -45,18 +47,21 @@ struct DecK {
 // -------------------------------------------------------------------------------------------------
 // forward
 // -------------------------------------------------------------------------------------------------
+__device__ unsigned long long g_dec_timing[16];
+
 template <int CELL, int KC>
 __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
     extern __shared__ __align__(16) float smem[];
     const int H = ABCD_H, M = ABCD_M;
     const int F = p.F, Fp = p.Fp;
     const int XC = xcols_per_cta(F);
-    constexpr int NC3 = DEC_NC3, ncg3 = DEC_NC3 / 4;
+    constexpr int HSP = 2 * U + 4;            // pitch of the CTA's own hidden-layer slice kept in shared memory
     float* Wg = smem;                         // [Fp+H][U*4]
     float* W1 = Wg + (Fp + H) * (U * 4);      // [H][2U]
-    float* W3 = W1 + H * (2 * U);             // [2M][NC3]
-    const Stage st = make_stage(W3 + 2 * M * NC3, KC);
-    float* red = W3 + 2 * M * NC3 + stage_floats(KC);   // 40 floats
+    float* W2s = W1 + H * (2 * U);            // [U][2Fp]: rows of the output layers that multiply this CTA's hidden units
+    const Stage st = make_stage(W2s + U * 2 * Fp, KC);
+    float* red = W2s + U * 2 * Fp + stage_floats(KC);   // 40 floats
+    float* Hs = st.buf0;                      // [ROWS][HSP] (the staging buffers are idle between phases)
 
     const int tid = threadIdx.x;
     const int rank = (int)cluster_ctarank();
@@ -84,15 +89,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
         int which = col / U, u = col % U;
         W1[idx] = p.em_w1[which][(long)(u0 + u) * H + k];
     }
-    for (int idx = tid; idx < 2 * M * NC3; idx += NTHREADS) {
-        int col = idx % NC3, k = idx / NC3;
-        int q = col >> 2, j = col & 3;           // j: 0,1 -> mean cols; 2,3 -> log-var cols
-        int which = j >> 1;
-        int c = xc0 + 2 * q + (j & 1);
-        float v = 0.f;
-        bool in_block = which == 0 ? (k < M) : (k >= M);
-        if (in_block && c < xc1) v = p.em_w2[which][(long)c * M + (which == 0 ? k : k - M)];
-        W3[idx] = v;
+    for (int idx = tid; idx < U * 2 * Fp; idx += NTHREADS) {
+        int c = idx % (2 * Fp), kk = idx / (2 * Fp);
+        int which = c >= Fp, cc = which ? c - Fp : c;     // mean columns [0,Fp), log-variance columns [Fp,2Fp)
+        W2s[idx] = cc < F ? p.em_w2[which][(long)cc * M + u0 + kk] : 0.f;
     }
 
     // ---- per-thread constants for the three phases ----
@@ -117,14 +117,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
         int col = tm2.cg * 4 + j;
         bias2[j] = p.em_b1[col / U][u0 + col % U];
     }
-    const int KS3 = pick_ks_fit(ncg3, DEC_NC3, KC);
-    const ThreadMap tm3 = make_map(tid, ncg3, KS3);
-    float bias3[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        int c = xc0 + 2 * tm3.cg + (j & 1);
-        bias3[j] = (tm3.active && c < xc1) ? p.em_b2[j >> 1][c] : 0.f;
-    }
+    const int ncg3 = 2 * Fp / 4;                                      // column groups of the local emission GEMM
+    float* Pmine = p.Pbuf + (long)blockIdx.x * ROWS * (2 * Fp);       // this CTA's partial emission parameters
+    const float* Ptile = p.Pbuf + (long)tile * CL * ROWS * (2 * Fp);  // partials of all CTAs of the cluster
 
     // recurrent state of (row, unit) pairs owned by this thread
     float creg[RT], hreg[RT];
@@ -140,10 +135,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
     const int Tt = p.lengths[tile];
     float nll = 0.f;
     const int n_tiles = p.n_tiles, B = p.B;
-    const float* Hall = p.Hall; const float* Xall = p.Xall; const float* Hid = p.Hid;
+    const float* Hall = p.Hall; const float* Xall = p.Xall;
     __syncthreads();
+    const bool timing = p.timing && blockIdx.x == 0 && tid == 0;
+    unsigned long long tacc[16];
+    for (int i = 0; i < 16; ++i) tacc[i] = 0;
+#define DEC_TICK(slot) if (timing) { long long now_ = clock64(); tacc[slot] += now_ - tick_; tick_ = now_; }
 
     for (int t = 0; t < Tt; ++t) {
+        long long tick_ = timing ? clock64() : 0;
         const int na = active_rows(p.batch_sizes[t], tile, n_tiles);
         const long off_t = p.offsets[t];
         const long prev_base = t == 0 ? 0 : (long)B + p.offsets[t - 1];
@@ -154,7 +154,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
             zero_acc(acc);
             auto rpx = [=](int r) -> const float* { return Xall + (prev_base + tile + (long)n_tiles * r) * Fp; };
             auto rph = [=](int r) -> const float* { return Hall + (prev_base + tile + (long)n_tiles * r) * ABCD_H; };
-            phase_gemm<NTHREADS, KC, U * 4>(acc, st, Fp, rpx, H, rph, na, Wg, tm1, KS1, tid);
+            DEC_TICK(0)
+            phase_gemm<NTHREADS, KC, U * 4>(acc, st, Fp, rpx, H, rph, na, Wg, tm1, KS1, tid, timing ? tacc + 10 : nullptr);
+            DEC_TICK(1)
 #pragma unroll
             for (int i = 0; i < RT; ++i) {
                 int r = tm1.rg + i * RG;
@@ -183,7 +185,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
                 p.Hall[((long)B + frame) * H + unit] = h;
             }
         }
+        DEC_TICK(2)
         cluster_sync_all();
+        DEC_TICK(3)
 
         // ---- P2: hidden layers of the two emission MLPs ----
         {
@@ -191,6 +195,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
             zero_acc(acc);
             auto rph = [=](int r) -> const float* { return Hall + ((long)B + off_t + tile + (long)n_tiles * r) * ABCD_H; };
             phase_gemm<NTHREADS, KC, 2 * U>(acc, st, H, rph, 0, NullRow(), na, W1, tm2, KS2, tid);
+            DEC_TICK(4)
             if (tm2.active && tm2.ks == 0) {
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
@@ -202,59 +207,81 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
                     float4 v = make_float4(tanhf(acc[i][0] + bias2[0]), tanhf(acc[i][1] + bias2[1]),
                                            tanhf(acc[i][2] + bias2[2]), tanhf(acc[i][3] + bias2[3]));
                     *reinterpret_cast<float4*>(p.Hid + frame * (2 * M) + which * M + u0 + uu) = v;
+                    *reinterpret_cast<float4*>(Hs + r * HSP + col) = v;
+                }
+            }
+            __syncthreads();
+            // ---- P3a: this CTA's share of the emission parameters.  The output layers contract over the hidden
+            // units, which are partitioned over the cluster: every CTA multiplies its own 2U hidden columns (still
+            // in shared memory) by the matching rows of the output weights and publishes a partial [rows][2Fp];
+            // the owners of the x columns add the CL partials after the barrier (fixed order). ----
+            for (int item = tid; item < ncg3 * 16; item += NTHREADS) {
+                const int cg = item % ncg3, r0 = item / ncg3;   // rows r0 + 16 i
+                if (r0 >= na) continue;
+                const float* a = Hs + r0 * HSP + ((cg * 4 < Fp) ? 0 : U);
+                const float* w = W2s + cg * 4;
+                float o[5][4];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+#pragma unroll
+                for (int kq = 0; kq < U / 4; ++kq) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(w + (kq * 4 + 0) * (2 * Fp));
+                    const float4 w1 = *reinterpret_cast<const float4*>(w + (kq * 4 + 1) * (2 * Fp));
+                    const float4 w2 = *reinterpret_cast<const float4*>(w + (kq * 4 + 2) * (2 * Fp));
+                    const float4 w3 = *reinterpret_cast<const float4*>(w + (kq * 4 + 3) * (2 * Fp));
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        const float4 av = *reinterpret_cast<const float4*>(a + i * 16 * HSP + kq * 4);
+                        o[i][0] = fmaf(av.x, w0.x, o[i][0]); o[i][1] = fmaf(av.x, w0.y, o[i][1]); o[i][2] = fmaf(av.x, w0.z, o[i][2]); o[i][3] = fmaf(av.x, w0.w, o[i][3]);
+                        o[i][0] = fmaf(av.y, w1.x, o[i][0]); o[i][1] = fmaf(av.y, w1.y, o[i][1]); o[i][2] = fmaf(av.y, w1.z, o[i][2]); o[i][3] = fmaf(av.y, w1.w, o[i][3]);
+                        o[i][0] = fmaf(av.z, w2.x, o[i][0]); o[i][1] = fmaf(av.z, w2.y, o[i][1]); o[i][2] = fmaf(av.z, w2.z, o[i][2]); o[i][3] = fmaf(av.z, w2.w, o[i][3]);
+                        o[i][0] = fmaf(av.w, w3.x, o[i][0]); o[i][1] = fmaf(av.w, w3.y, o[i][1]); o[i][2] = fmaf(av.w, w3.z, o[i][2]); o[i][3] = fmaf(av.w, w3.w, o[i][3]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    const int r = r0 + 16 * i;
+                    if (r < na) *reinterpret_cast<float4*>(Pmine + (long)r * (2 * Fp) + cg * 4) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
                 }
             }
         }
+        DEC_TICK(5)
         cluster_sync_all();
+        DEC_TICK(6)
 
-        // ---- P3: emission parameters, reparameterised sample, NLL ----
-        {
-            float acc[RT][4];
-            zero_acc(acc);
-            // noise and targets of this step's frames are fetched before the GEMM so their latency hides behind it
-            float ev[RT][2], gv[RT][2];
-            if (tm3.active && tm3.ks == 0) {
+        // ---- P3b: sum the partials of this CTA's x columns, reparameterised sample, NLL ----
+        for (int o = tid; o < na * XC; o += NTHREADS) {
+            const int r = o / XC, c = xc0 + o % XC;
+            if (c >= xc1) continue;
+            const long frame = off_t + tile + (long)n_tiles * r;
+            const float e = __ldg(p.eps + frame * p.ld_eps + c);
+            const float g = p.gt ? __ldg(p.gt + frame * p.ld_gt + c) : 0.f;
+            float pm[CL], pv[CL];
 #pragma unroll
-                for (int i = 0; i < RT; ++i) {
-                    int r = tm3.rg + i * RG;
-                    long frame = off_t + tile + (long)n_tiles * r;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        int c = xc0 + 2 * tm3.cg + j;
-                        bool ok = r < na && c < xc1;
-                        ev[i][j] = ok ? __ldg(p.eps + frame * p.ld_eps + c) : 0.f;
-                        gv[i][j] = (ok && p.gt) ? __ldg(p.gt + frame * p.ld_gt + c) : 0.f;
-                    }
-                }
+            for (int src = 0; src < CL; ++src) {
+                const float* q = Ptile + ((long)src * ROWS + r) * (2 * Fp) + c;
+                pm[src] = ld_cg(q);
+                pv[src] = ld_cg(q + Fp);
             }
-            auto rph = [=](int r) -> const float* { return Hid + (off_t + tile + (long)n_tiles * r) * (2 * ABCD_M); };
-            phase_gemm<NTHREADS, KC, DEC_NC3>(acc, st, 2 * M, rph, 0, NullRow(), na, W3, tm3, KS3, tid);
-            if (tm3.active && tm3.ks == 0) {
+            float mean = __ldg(p.em_b2[0] + c), lv = __ldg(p.em_b2[1] + c);
 #pragma unroll
-                for (int i = 0; i < RT; ++i) {
-                    int r = tm3.rg + i * RG;
-                    if (r >= na) continue;
-                    long frame = off_t + tile + (long)n_tiles * r;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        int c = xc0 + 2 * tm3.cg + j;
-                        if (c >= xc1) continue;
-                        float mean = acc[i][j] + bias3[j];
-                        float lv = acc[i][2 + j] + bias3[2 + j];
-                        float x = mean + expf(0.5f * lv) * ev[i][j];
-                        p.Mean[frame * Fp + c] = mean;
-                        p.Lv[frame * Fp + c] = lv;
-                        p.Xall[((long)B + frame) * Fp + c] = x;
-                        if (p.gt) {
-                            float d = gv[i][j] - mean;
-                            nll += 0.5f * (LOG_2PI + lv + d * expf(-lv) * d);
-                        }
-                    }
-                }
+            for (int src = 0; src < CL; ++src) { mean += pm[src]; lv += pv[src]; }
+            const float x = mean + expf(0.5f * lv) * e;
+            p.Mean[frame * Fp + c] = mean;
+            p.Lv[frame * Fp + c] = lv;
+            p.Xall[((long)B + frame) * Fp + c] = x;
+            if (p.gt) {
+                const float d = g - mean;
+                nll += 0.5f * (LOG_2PI + lv + d * expf(-lv) * d);
             }
         }
+        DEC_TICK(7)
+        DEC_TICK(8)
         cluster_sync_all();
+        DEC_TICK(9)
     }
+#undef DEC_TICK
+    if (timing) { tacc[15] = Tt; for (int i = 0; i < 16; ++i) g_dec_timing[i] = tacc[i]; }
     float tot = block_sum(nll, red);
     if (tid == 0) p.nll_partial[blockIdx.x] = tot;
 }
@@ -602,7 +629,7 @@ __global__ void unpad_copy_kernel(long rows, int F, int ld_src, const float* __r
 
 size_t dec_fwd_fixed_floats(int F) {   // resident weights + reduction scratch
     int Fp = pad4(F);
-    return (size_t)((Fp + ABCD_H) * U * 4 + ABCD_H * 2 * U + 2 * ABCD_M * DEC_NC3 + 64);
+    return (size_t)((Fp + ABCD_H) * U * 4 + ABCD_H * 2 * U + U * 2 * Fp + 64);
 }
 size_t dec_bwd_fixed_floats(int F) {   // resident weights + dh/dc carries
     int Fp = pad4(F);
@@ -637,7 +664,7 @@ int launch_cluster_dec(K kernel, int n_clusters, size_t smem, cudaStream_t strea
 }
 
 struct DecWs {
-    float *hc0, *Hall, *Call, *Xall, *Gs, *Hid, *Mean, *Lv, *HidOff, *OffLogit, *nll_partial, *bce_partial;
+    float *hc0, *Hall, *Call, *Xall, *Gs, *Hid, *Mean, *Lv, *HidOff, *OffLogit, *nll_partial, *bce_partial, *Pbuf;
     float *dML, *dHidPre, *dG, *dHoff, *dHidOffPre, *dLogit, *dHC0, *dbias, *partials;
     int* prev;
     size_t partial_floats;
@@ -664,6 +691,7 @@ DecWs dec_carve(void* base, size_t cap, int cell, int F, int fin, int B, int sum
     w.OffLogit = a.take<float>((size_t)sumT);
     w.nll_partial = a.take<float>((size_t)n_tiles * CL);
     w.bce_partial = a.take<float>(BCE_BLOCKS);
+    w.Pbuf = a.take<float>((size_t)n_tiles * CL * ROWS * 2 * Fp);
     w.dML = a.take<float>((size_t)sumT * 2 * Fp);
     w.dHidPre = a.take<float>((size_t)sumT * 2 * M);
     w.dG = a.take<float>((size_t)sumT * 4 * H);
@@ -697,7 +725,8 @@ DecK make_k(const DecParams& P, const PackedMeta& pk, const DecWs& w) {
     k.w_ih = P.w_ih; k.w_hh = P.w_hh; k.b_ih = P.b_ih; k.b_hh = P.b_hh;
     for (int i = 0; i < 2; ++i) { k.em_w1[i] = P.em_w1[i]; k.em_b1[i] = P.em_b1[i]; k.em_w2[i] = P.em_w2[i]; k.em_b2[i] = P.em_b2[i]; }
     k.Hall = w.Hall; k.Call = w.Call; k.Xall = w.Xall; k.Gs = w.Gs; k.Hid = w.Hid; k.Mean = w.Mean; k.Lv = w.Lv;
-    k.nll_partial = w.nll_partial;
+    k.nll_partial = w.nll_partial; k.Pbuf = w.Pbuf;
+    k.timing = getenv("ABCD_TIMING") != nullptr;
     k.dML = w.dML; k.dHidPre = w.dHidPre; k.dG = w.dG; k.dHoff = w.dHoff; k.dHC0 = w.dHC0; k.dbias = w.dbias;
     return k;
 }
@@ -713,6 +742,10 @@ int check_dec(const DecParams& P) {
 }  // namespace
 
 int rnn_max_active_clusters(const void* fn, size_t smem, int cluster, int threads, int* out);
+int dec_read_timing(unsigned long long* out16) {
+    CUDA_TRY(cudaMemcpyFromSymbol(out16, g_dec_timing, 16 * sizeof(unsigned long long)));
+    return ABCD_OK;
+}
 int dec_max_clusters(int which, int F, int* out) {
     const void* fn = which == 0 ? (dec_fwd_kc(F) == 64 ? (const void*)dec_fwd_kernel<0, 64> : (const void*)dec_fwd_kernel<0, 32>)
                                 : (dec_bwd_kc(F) == 64 ? (const void*)dec_bwd_kernel<0, 64> : (const void*)dec_bwd_kernel<0, 32>);

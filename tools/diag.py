@@ -66,5 +66,19 @@ def enc_timing():
 		print("   (tensor-core phase: prologue %.0f stage-wait %.0f split %.0f fence+sync %.0f issue %.0f)" % tuple(x / v[4] for x in v[5:10]))
 
 
+def dec_timing():
+	import ctypes as C
+	pkg = importlib.import_module('seq2seq_abcd-vae_b200')
+	out = (C.c_ulonglong * 16)()
+	pkg._lib.load().abcd_debug_dec_timing(out)
+	v = list(out)
+	if v[15]:
+		n = float(v[15])
+		names = ['P1 setup', 'P1 gemm', 'P1 cell', 'barrier', 'P2 gemm', 'P2 store', 'barrier', 'P3 setup+gemm', 'P3 sample', 'barrier']
+		print('dec_fwd CTA0 cycles/step: ' + ', '.join('%s %.0f' % (nm, x / n) for nm, x in zip(names, v[:10])) + ' (steps %d, total %.0f)' % (v[15], sum(v[:10]) / n))
+		print('   P1 gemm: stage-issue %.0f wait+sync %.0f mma %.0f chunks %.2f tail-sync %.0f' % tuple(x / n for x in v[10:15]))
+
+
 if os.environ.get('ABCD_TIMING'):
 	enc_timing()
+	dec_timing()
