@@ -18,7 +18,7 @@ using namespace rnn;
 namespace {
 
 constexpr int DEC_NC3 = 20;    // P3 weight-slice pitch: 2 mean + 2 log-var columns for up to 5 pairs of x columns per CTA
-constexpr int DEC_NCB1 = 28;   // B1 weight-slice pitch: 16 h columns + up to 12 x columns per CTA
+constexpr int DEC_N1P = 392;   // backward: pitch of the resident [W_hh | W_ih] rows (H + pad4(F) <= 388 for F <= 129)
 constexpr size_t SMEM_MAX = 232448;   // 227 KB of dynamic shared memory per CTA on sm_100
 constexpr float LOG_2PI = 1.8378770664093453f;
 
@@ -42,6 +42,8 @@ struct DecK {
     // backward only
     float* dML; float* dHidPre; float* dG; const float* dHoff; float* dHC0;
     float* dbias;   // [n_tiles][4H]: per-tile column sums of dG (recurrent bias gradients), interleaved layout
+    float* Pb2;     // [n_tiles][CL][ROWS][H]     partial dh from the MLP input layers, exchanged inside a cluster
+    float* Pb1;     // [n_tiles][CL][ROWS][H+Fp]  partial [dh_prev | dx] from the cell
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -289,19 +291,65 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
 // -------------------------------------------------------------------------------------------------
 // backward
 // -------------------------------------------------------------------------------------------------
+// out[rows, 4 ncg] = A[rows, 4*K4] * W[4*K4, LDW] on operands that are already in shared memory; work items are
+// (column group, row group) pairs with the usual 10-row x 4-column register tile (rows rg + 8 i) and the
+// register-double-buffered inner loop of rnn_common.cuh.  Results go to `out` (global, row pitch ldo).
+template <int K4, int LDA, int LDW>
+__device__ __forceinline__ void local_gemm_store(const float* A, const float* W, int ncg, int na, float* out, long ldo, int tid) {
+    const int nslots = (na + RG - 1) / RG;
+    for (int item = tid; item < ncg * NRG; item += NTHREADS) {
+        const int cg = item % ncg, rg = item / ncg;
+        if (rg >= na) continue;
+        const float* a = A + rg * LDA;
+        const float* w = W + cg * 4;
+        float acc[RT][4];
+        zero_acc(acc);
+        switch (nslots) {
+            case 1: mma_range<1, LDA, LDW>(acc, a, w, K4); break;
+            case 2: mma_range<2, LDA, LDW>(acc, a, w, K4); break;
+            case 3: mma_range<3, LDA, LDW>(acc, a, w, K4); break;
+            case 4: mma_range<4, LDA, LDW>(acc, a, w, K4); break;
+            case 5: mma_range<5, LDA, LDW>(acc, a, w, K4); break;
+            case 6: mma_range<6, LDA, LDW>(acc, a, w, K4); break;
+            case 7: mma_range<7, LDA, LDW>(acc, a, w, K4); break;
+            case 8: mma_range<8, LDA, LDW>(acc, a, w, K4); break;
+            case 9: mma_range<9, LDA, LDW>(acc, a, w, K4); break;
+            default: mma_range<RT, LDA, LDW>(acc, a, w, K4); break;
+        }
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            const int r = rg + i * RG;
+            if (r < na) *reinterpret_cast<float4*>(out + (long)r * ldo + cg * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+    }
+}
+
+// Backward.  Every contraction over a dimension that is partitioned over the cluster (the hidden units of the MLPs,
+// the gate columns of the cell) is computed as a partial product on the CTA's OWN slice -- which it has just produced
+// and still holds in shared memory -- followed by an in-cluster reduction of the partials through L2:
+//   B3  dHidPre[:, my 2U]   = (dML[:, 2Fp] W2^T) * (1 - Hid^2)        staged GEMM (K = 2Fp), slice kept in smem
+//   B2' partial dh[:, H]    = dHidPre[:, my 2U] W1[my 2U, H]          local GEMM -> Pb2        -- cluster barrier --
+//       dh[:, my U]         = sum of the CL partials + recurrent carry + offset-head gradient; gate gradients dG
+//   B1' partial [dh_prev|dx] = dG[:, my 4U] [W_hh | W_ih][my 4U, H+Fp] local GEMM -> Pb1        -- cluster barrier --
+//       dh carry[:, my U], dx[:, my x columns] = sums of the partials; dx is folded into dML of the previous frame
+//                                                                                              -- cluster barrier --
 template <int CELL, int KC>
 __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
     extern __shared__ __align__(16) float smem[];
     const int H = ABCD_H, M = ABCD_M;
     const int F = p.F, Fp = p.Fp;
     const int XC = xcols_per_cta(F);
-    constexpr int NCB1 = DEC_NCB1;
+    const int N1 = H + Fp;                    // columns of the B1' partial: [dh_prev (H) | dx (Fp)]
+    constexpr int DSP = 2 * U + 4;            // pitch of the dHidPre slice in shared memory
+    constexpr int GSP = 4 * U + 4;            // pitch of the dG slice in shared memory
     float* WB3 = smem;                        // [2Fp][2U]
-    float* WB2 = WB3 + 2 * Fp * (2 * U);      // [2M][U]
-    float* WB1 = WB2 + 2 * M * U;             // [4H][NCB1]
-    float* dh_sm = WB1 + 4 * H * NCB1;        // [ROWS][U]
+    float* W1s = WB3 + 2 * Fp * (2 * U);      // [2U][H]: rows of the MLP input layers of this CTA's hidden units
+    float* Wb1 = W1s + 2 * U * H;             // [4U][DEC_N1P]: rows of [W_hh | W_ih] of this CTA's gate columns
+    float* dh_sm = Wb1 + 4 * U * DEC_N1P;     // [ROWS][U]
     float* dc_sm = dh_sm + ROWS * U;          // [ROWS][U]
     const Stage st = make_stage(dc_sm + ROWS * U, KC);
+    float* Ds = st.buf0;                      // [ROWS][DSP]  (staging is idle outside B3)
+    float* Gsm = st.buf0;                     // [ROWS][GSP]  (Ds is dead by then; may run into buf1)
 
     const int tid = threadIdx.x;
     const int rank = (int)cluster_ctarank();
@@ -318,55 +366,96 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
         if (kk >= 0 && kk < F) v = p.em_w2[which][(long)kk * M + u0 + u];
         WB3[idx] = v;
     }
-    for (int idx = tid; idx < 2 * M * U; idx += NTHREADS) {
-        int j = idx % U, k = idx / U;
-        int which = k / M, kk = k % M;
-        WB2[idx] = p.em_w1[which][(long)kk * H + u0 + j];
+    for (int idx = tid; idx < 2 * U * H; idx += NTHREADS) {
+        int j = idx % H, k = idx / H;
+        W1s[idx] = p.em_w1[k / U][(long)(u0 + k % U) * H + j];
     }
-    for (int idx = tid; idx < 4 * H * NCB1; idx += NTHREADS) {
-        int col = idx % NCB1, kphys = idx / NCB1;
-        int uu = kphys >> 2, s = kphys & 3;
+    for (int idx = tid; idx < 4 * U * DEC_N1P; idx += NTHREADS) {
+        int j = idx % DEC_N1P, kphys = idx / DEC_N1P;
+        int uu = u0 + (kphys >> 2), s = kphys & 3;
         float v = 0.f;
-        if (col < U) {
+        if (j < H) {
             int gate = CELL == 0 ? s : (s == 0 ? 0 : s == 1 ? 1 : s == 3 ? 2 : -1);
-            if (gate >= 0) v = p.w_hh[(long)(gate * H + uu) * H + u0 + col];
+            if (gate >= 0) v = p.w_hh[(long)(gate * H + uu) * H + j];
         } else {
-            int c = xc0 + (col - U);
+            int c = j - H;
             int gate = CELL == 0 ? s : (s == 3 ? -1 : s);
-            if (gate >= 0 && (col - U) < XC && c < xc1) v = p.w_ih[(long)(gate * H + uu) * F + c];
+            if (gate >= 0 && c < F) v = p.w_ih[(long)(gate * H + uu) * F + c];
         }
-        WB1[idx] = v;
+        Wb1[idx] = v;
     }
     for (int idx = tid; idx < ROWS * U; idx += NTHREADS) { dh_sm[idx] = 0.f; dc_sm[idx] = 0.f; }
 
     const int KS3 = pick_ks_fit(2 * U / 4, 2 * U, KC);
     const ThreadMap tm3 = make_map(tid, 2 * U / 4, KS3);
-    const int KS2 = pick_ks_fit(U / 4, U, KC);
-    const ThreadMap tm2 = make_map(tid, U / 4, KS2);
-    const int ncg1 = NCB1 / 4;
-    const int KS1 = pick_ks_fit(ncg1, DEC_NCB1, KC);
-    const ThreadMap tm1 = make_map(tid, ncg1, KS1);
     constexpr int PRG = NTHREADS / U;   // pointwise mapping: 16 row groups x 16 units, rows prg + i*PRG
+    constexpr int PR = ROWS / PRG;      // rows per pointwise thread
     const int pu = tid % U, prg = tid / U;
     const int unit = u0 + pu;
 
     const int Tt = p.lengths[tile];
     const int n_tiles = p.n_tiles, B = p.B;
-    const float* dML = p.dML; const float* dHidPre = p.dHidPre; const float* dG = p.dG;
+    const float* dML = p.dML;
+    float* Pb2 = p.Pb2 + (long)blockIdx.x * ROWS * H;
+    const float* Pb2t = p.Pb2 + (long)tile * CL * ROWS * H;
+    float* Pb1 = p.Pb1 + (long)blockIdx.x * ROWS * N1;
+    const float* Pb1t = p.Pb1 + (long)tile * CL * ROWS * N1;
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);   // this thread's share of sum(dG) over rows and steps
     __syncthreads();
+    const bool timing = p.timing && blockIdx.x == 0 && tid == 0;
+    unsigned long long tacc[16];
+    for (int i = 0; i < 16; ++i) tacc[i] = 0;
+#define DEC_TICK(slot) if (timing) { long long now_ = clock64(); tacc[slot] += now_ - tick_; tick_ = now_; }
 
     for (int t = Tt - 1; t >= 0; --t) {
+        long long tick_ = timing ? clock64() : 0;
         const int na = active_rows(p.batch_sizes[t], tile, n_tiles);
         const long off_t = p.offsets[t];
         const long prev_base = t == 0 ? 0 : (long)B + p.offsets[t - 1];
 
-        // ---- B3: gradient w.r.t. the MLP hidden pre-activations ----
+        // saved forward activations for the gate-gradient step: fetched now, consumed after the first barrier
+        float4 g4v[PR];
+        float cv[PR], pv[PR], hov[PR];
+#pragma unroll
+        for (int i = 0; i < PR; ++i) {
+            int r = prg + i * PRG;
+            g4v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            cv[i] = pv[i] = hov[i] = 0.f;
+            if (r >= na) continue;
+            long b = tile + (long)n_tiles * r;
+            long frame = off_t + b;
+            long prow = prev_base + b;
+            g4v[i] = __ldg(reinterpret_cast<const float4*>(p.Gs + frame * (4 * H) + unit * 4));
+            hov[i] = __ldg(p.dHoff + frame * H + unit);
+            if (CELL == 0) {
+                cv[i] = __ldg(p.Call + ((long)B + frame) * H + unit);
+                pv[i] = __ldg(p.Call + prow * H + unit);
+            } else {
+                pv[i] = __ldg(p.Hall + prow * H + unit);
+            }
+        }
+
+        // ---- B3: gradient w.r.t. this CTA's MLP hidden pre-activations ----
         {
             float acc[RT][4];
             zero_acc(acc);
             auto rp = [=](int r) -> const float* { return dML + (off_t + tile + (long)n_tiles * r) * (2 * Fp); };
+            // tanh outputs of this thread's tile: fetched before the GEMM so the latency hides behind it
+            float4 hdv[RT];
+            if (tm3.active && tm3.ks == 0) {
+#pragma unroll
+                for (int i = 0; i < RT; ++i) {
+                    int r = tm3.rg + i * RG;
+                    hdv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r >= na) continue;
+                    long frame = off_t + tile + (long)n_tiles * r;
+                    int col = tm3.cg * 4;
+                    hdv[i] = __ldg(reinterpret_cast<const float4*>(p.Hid + frame * (2 * M) + (col / U) * M + u0 + col % U));
+                }
+            }
+            DEC_TICK(0)
             phase_gemm<NTHREADS, KC, 2 * U>(acc, st, 2 * Fp, rp, 0, NullRow(), na, WB3, tm3, KS3, tid);
+            DEC_TICK(1)
             if (tm3.active && tm3.ks == 0) {
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
@@ -376,136 +465,120 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
                     int col = tm3.cg * 4;
                     int which = col / U, uu = col % U;
                     long o = frame * (2 * M) + which * M + u0 + uu;
-                    float4 hd = __ldg(reinterpret_cast<const float4*>(p.Hid + o));
+                    float4 hd = hdv[i];
                     float4 v = make_float4(acc[i][0] * (1.f - hd.x * hd.x), acc[i][1] * (1.f - hd.y * hd.y),
                                            acc[i][2] * (1.f - hd.z * hd.z), acc[i][3] * (1.f - hd.w * hd.w));
                     *reinterpret_cast<float4*>(p.dHidPre + o) = v;
-                }
-            }
-        }
-        cluster_sync_all();
-
-        // ---- B2: dh from the emission MLPs, then gate gradients ----
-        {
-            float acc[RT][4];
-            zero_acc(acc);
-            // saved forward activations for the gate-gradient step: fetched now, consumed after the GEMM
-            float4 g4v[RT];
-            float cv[RT], pv[RT], hov[RT];
-#pragma unroll
-            for (int i = 0; i < RT; ++i) {
-                int r = prg + i * PRG;
-                g4v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                cv[i] = pv[i] = hov[i] = 0.f;
-                if (r >= na) continue;
-                long b = tile + (long)n_tiles * r;
-                long frame = off_t + b;
-                long prow = prev_base + b;
-                g4v[i] = __ldg(reinterpret_cast<const float4*>(p.Gs + frame * (4 * H) + unit * 4));
-                hov[i] = __ldg(p.dHoff + frame * H + unit);
-                if (CELL == 0) {
-                    cv[i] = __ldg(p.Call + ((long)B + frame) * H + unit);
-                    pv[i] = __ldg(p.Call + prow * H + unit);
-                } else {
-                    pv[i] = __ldg(p.Hall + prow * H + unit);
-                }
-            }
-            auto rp = [=](int r) -> const float* { return dHidPre + (off_t + tile + (long)n_tiles * r) * (2 * ABCD_M); };
-            phase_gemm<NTHREADS, KC, U>(acc, st, 2 * M, rp, 0, NullRow(), na, WB2, tm2, KS2, tid);
-            if (tm2.active && tm2.ks == 0) {
-#pragma unroll
-                for (int i = 0; i < RT; ++i) {
-                    int r = tm2.rg + i * RG;
-                    if (r >= na) continue;
-                    float4* d = reinterpret_cast<float4*>(dh_sm + r * U + tm2.cg * 4);
-                    float4 v = *d;
-                    v.x += acc[i][0]; v.y += acc[i][1]; v.z += acc[i][2]; v.w += acc[i][3];
-                    *d = v;
+                    *reinterpret_cast<float4*>(Ds + r * DSP + col) = v;
                 }
             }
             __syncthreads();
-#pragma unroll
-            for (int i = 0; i < RT; ++i) {
-                int r = prg + i * PRG;
-                if (r >= na) continue;
-                long frame = off_t + tile + (long)n_tiles * r;
-                float dh = dh_sm[r * U + pu] + hov[i];
-                float carry = dc_sm[r * U + pu];
-                const float4 g4 = g4v[i];
-                float4 dgv;
-                if (CELL == 0) {
-                    float c = cv[i];
-                    float c_prev = pv[i];
-                    float tc = tanhf(c);
-                    float ig = g4.x, fg = g4.y, gg = g4.z, og = g4.w;
-                    float dc = carry + dh * og * (1.f - tc * tc);
-                    dgv.x = dc * gg * ig * (1.f - ig);
-                    dgv.y = dc * c_prev * fg * (1.f - fg);
-                    dgv.z = dc * ig * (1.f - gg * gg);
-                    dgv.w = dh * tc * og * (1.f - og);
-                    dc_sm[r * U + pu] = dc * fg;
-                } else {
-                    dh += carry;
-                    float h_prev = pv[i];
-                    float rg_ = g4.x, zg = g4.y, ng = g4.z, hn = g4.w;
-                    float dn_pre = dh * (1.f - zg) * (1.f - ng * ng);
-                    dgv.x = dn_pre * hn * rg_ * (1.f - rg_);
-                    dgv.y = dh * (h_prev - ng) * zg * (1.f - zg);
-                    dgv.z = dn_pre;
-                    dgv.w = dn_pre * rg_;
-                    dc_sm[r * U + pu] = dh * zg;
-                }
-                *reinterpret_cast<float4*>(p.dG + frame * (4 * H) + unit * 4) = dgv;
-                bsum.x += dgv.x; bsum.y += dgv.y; bsum.z += dgv.z; bsum.w += dgv.w;
-            }
         }
+        // ---- B2': partial dh over all H units from this CTA's hidden slice ----
+        DEC_TICK(2)
+        local_gemm_store<2 * U / 4, DSP, ABCD_H>(Ds, W1s, H / 4, na, Pb2, H, tid);
+        DEC_TICK(3)
         cluster_sync_all();
+        DEC_TICK(4)
 
-        // ---- B1: [dh_{t-1} | dx_t] = dG * [W_hh | W_ih] ----
-        {
-            float acc[RT][4];
-            zero_acc(acc);
-            auto rp = [=](int r) -> const float* { return dG + (off_t + tile + (long)n_tiles * r) * (4 * ABCD_H); };
-            phase_gemm<NTHREADS, KC, DEC_NCB1>(acc, st, 4 * H, rp, 0, NullRow(), na, WB1, tm1, KS1, tid);
-            if (tm1.active && tm1.ks == 0) {
+        // ---- dh of this CTA's units = sum of the partials (+ carry), then the gate gradients ----
+        for (int idx = tid; idx < na * (U / 4); idx += NTHREADS) {
+            const int r = idx / (U / 4), q = idx % (U / 4);
+            float4 v[CL];
 #pragma unroll
-                for (int i = 0; i < RT; ++i) {
-                    int r = tm1.rg + i * RG;
-                    if (r >= na) continue;
-                    if (tm1.cg < U / 4) {
-                        *reinterpret_cast<float4*>(dh_sm + r * U + tm1.cg * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-                    } else if (t > 0) {
-                        long pf = p.offsets[t - 1] + tile + (long)n_tiles * r;   // frame that produced x_t
-                        // loads of the 4 columns first, then the read-modify-writes (one round trip per row slot)
-                        float lvv[4], evv[4], m0[4], m1[4];
+            for (int src = 0; src < CL; ++src) v[src] = ld_cg4(Pb2t + ((long)src * ROWS + r) * H + u0 + q * 4);
+            float4 a = *reinterpret_cast<float4*>(dh_sm + r * U + q * 4);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            int q = (tm1.cg - U / 4) * 4 + j;
-                            int c = xc0 + q;
-                            bool ok = q < XC && c < xc1;
-                            lvv[j] = ok ? __ldg(p.Lv + pf * Fp + c) : 0.f;
-                            evv[j] = ok ? __ldg(p.eps + pf * p.ld_eps + c) : 0.f;
-                            m0[j] = ok ? p.dML[pf * (2 * Fp) + c] : 0.f;
-                            m1[j] = ok ? p.dML[pf * (2 * Fp) + Fp + c] : 0.f;
-                        }
+            for (int src = 0; src < CL; ++src) { a.x += v[src].x; a.y += v[src].y; a.z += v[src].z; a.w += v[src].w; }
+            *reinterpret_cast<float4*>(dh_sm + r * U + q * 4) = a;
+        }
+        __syncthreads();
+        DEC_TICK(5)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            int q = (tm1.cg - U / 4) * 4 + j;
-                            int c = xc0 + q;
-                            if (q < XC && c < xc1) {
-                                float dx = acc[i][j];
-                                p.dML[pf * (2 * Fp) + c] = m0[j] + dx;
-                                p.dML[pf * (2 * Fp) + Fp + c] = m1[j] + dx * 0.5f * expf(0.5f * lvv[j]) * evv[j];
-                            }
-                        }
-                    }
-                }
+        for (int i = 0; i < PR; ++i) {
+            int r = prg + i * PRG;
+            if (r >= na) continue;
+            long frame = off_t + tile + (long)n_tiles * r;
+            float dh = dh_sm[r * U + pu] + hov[i];
+            float carry = dc_sm[r * U + pu];
+            const float4 g4 = g4v[i];
+            float4 dgv;
+            if (CELL == 0) {
+                float c = cv[i];
+                float c_prev = pv[i];
+                float tc = tanhf(c);
+                float ig = g4.x, fg = g4.y, gg = g4.z, og = g4.w;
+                float dc = carry + dh * og * (1.f - tc * tc);
+                dgv.x = dc * gg * ig * (1.f - ig);
+                dgv.y = dc * c_prev * fg * (1.f - fg);
+                dgv.z = dc * ig * (1.f - gg * gg);
+                dgv.w = dh * tc * og * (1.f - og);
+                dc_sm[r * U + pu] = dc * fg;
+            } else {
+                dh += carry;
+                float h_prev = pv[i];
+                float rg_ = g4.x, zg = g4.y, ng = g4.z, hn = g4.w;
+                float dn_pre = dh * (1.f - zg) * (1.f - ng * ng);
+                dgv.x = dn_pre * hn * rg_ * (1.f - rg_);
+                dgv.y = dh * (h_prev - ng) * zg * (1.f - zg);
+                dgv.z = dn_pre;
+                dgv.w = dn_pre * rg_;
+                dc_sm[r * U + pu] = dh * zg;
+            }
+            *reinterpret_cast<float4*>(p.dG + frame * (4 * H) + unit * 4) = dgv;
+            *reinterpret_cast<float4*>(Gsm + r * GSP + pu * 4) = dgv;
+            bsum.x += dgv.x; bsum.y += dgv.y; bsum.z += dgv.z; bsum.w += dgv.w;
+        }
+        __syncthreads();
+
+        // ---- B1': partial [dh_{t-1} | dx_t] from this CTA's gate columns ----
+        DEC_TICK(6)
+        local_gemm_store<U, GSP, DEC_N1P>(Gsm, Wb1, N1 / 4, na, Pb1, N1, tid);
+        DEC_TICK(7)
+        cluster_sync_all();
+        DEC_TICK(8)
+
+        // ---- recurrent carry for this CTA's units, dx for its x columns (folded into dML of the previous frame) ----
+        // x columns first (longest dependency chain: partials + saved activations + read-modify-write), one column per
+        // thread; then the dh quads.  All loads of an item are issued before its first use.
+        if (t > 0) {
+            const long pbase = p.offsets[t - 1] + tile;
+            for (int idx = tid; idx < na * XC; idx += NTHREADS) {
+                const int r = idx / XC, c = xc0 + idx % XC;
+                if (c >= xc1) continue;
+                const long pf = pbase + (long)n_tiles * r;   // frame that produced x_t
+                float v[CL];
+#pragma unroll
+                for (int src = 0; src < CL; ++src) v[src] = ld_cg(Pb1t + ((long)src * ROWS + r) * N1 + H + c);
+                const float lv = __ldg(p.Lv + pf * Fp + c);
+                const float e = __ldg(p.eps + pf * p.ld_eps + c);
+                float* dm = p.dML + pf * (2 * Fp) + c;
+                const float m0 = dm[0], m1 = dm[Fp];
+                float dx = v[0];
+#pragma unroll
+                for (int src = 1; src < CL; ++src) dx += v[src];
+                dm[0] = m0 + dx;
+                dm[Fp] = m1 + dx * 0.5f * expf(0.5f * lv) * e;
             }
         }
+        for (int idx = tid; idx < na * (U / 4); idx += NTHREADS) {
+            const int r = idx / (U / 4), q = idx % (U / 4);
+            float4 v[CL];
+#pragma unroll
+            for (int src = 0; src < CL; ++src) v[src] = ld_cg4(Pb1t + ((long)src * ROWS + r) * N1 + u0 + q * 4);
+            float4 a = v[0];
+#pragma unroll
+            for (int src = 1; src < CL; ++src) { a.x += v[src].x; a.y += v[src].y; a.z += v[src].z; a.w += v[src].w; }
+            *reinterpret_cast<float4*>(dh_sm + r * U + q * 4) = a;
+        }
+        DEC_TICK(9)
         cluster_sync_all();
+        DEC_TICK(10)
     }
+#undef DEC_TICK
+    if (timing) { tacc[15] = Tt; for (int i = 0; i < 16; ++i) g_dec_timing[i] = tacc[i]; }
     // gradient w.r.t. the initial state produced by feature2hidden (h0 = even, c0 = odd columns; model.py:100)
-    for (int i = 0; i < RT; ++i) {
+    for (int i = 0; i < PR; ++i) {
         int r = prg + i * PRG;
         long b = tile + (long)n_tiles * r;
         if (b >= B || r >= ROWS) continue;
@@ -518,6 +591,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
     }
     // recurrent bias gradients: fixed-order reduction over the row groups, one row of partial sums per tile
     {
+        __syncthreads();
         float4* red = reinterpret_cast<float4*>(st.buf0);
         red[prg * U + pu] = bsum;
         __syncthreads();
@@ -633,7 +707,7 @@ size_t dec_fwd_fixed_floats(int F) {   // resident weights + reduction scratch
 }
 size_t dec_bwd_fixed_floats(int F) {   // resident weights + dh/dc carries
     int Fp = pad4(F);
-    return (size_t)(2 * Fp * 2 * U + 2 * ABCD_M * U + 4 * ABCD_H * DEC_NCB1 + 2 * ROWS * U);
+    return (size_t)(2 * Fp * 2 * U + 2 * U * ABCD_H + 4 * U * DEC_N1P + 2 * ROWS * U);
 }
 int pick_kc(size_t fixed_floats) {
     for (int kc : {64, 32})
@@ -665,7 +739,7 @@ int launch_cluster_dec(K kernel, int n_clusters, size_t smem, cudaStream_t strea
 
 struct DecWs {
     float *hc0, *Hall, *Call, *Xall, *Gs, *Hid, *Mean, *Lv, *HidOff, *OffLogit, *nll_partial, *bce_partial, *Pbuf;
-    float *dML, *dHidPre, *dG, *dHoff, *dHidOffPre, *dLogit, *dHC0, *dbias, *partials;
+    float *dML, *dHidPre, *dG, *dHoff, *dHidOffPre, *dLogit, *dHC0, *dbias, *Pb2, *Pb1, *partials;
     int* prev;
     size_t partial_floats;
     size_t bytes;
@@ -700,6 +774,8 @@ DecWs dec_carve(void* base, size_t cap, int cell, int F, int fin, int B, int sum
     w.dLogit = a.take<float>((size_t)sumT);
     w.dHC0 = a.take<float>((size_t)B * hc);
     w.dbias = a.take<float>((size_t)n_tiles * 4 * H);
+    w.Pb2 = a.take<float>((size_t)n_tiles * CL * ROWS * H);
+    w.Pb1 = a.take<float>((size_t)n_tiles * CL * ROWS * (H + Fp));
     w.prev = a.take<int>((size_t)sumT);
     // largest split-K partial: dW_hh / dW_ih ([4H] x [H|F]) or MLP weights ([M] x [H])
     size_t mx = 0;
@@ -727,7 +803,7 @@ DecK make_k(const DecParams& P, const PackedMeta& pk, const DecWs& w) {
     k.Hall = w.Hall; k.Call = w.Call; k.Xall = w.Xall; k.Gs = w.Gs; k.Hid = w.Hid; k.Mean = w.Mean; k.Lv = w.Lv;
     k.nll_partial = w.nll_partial; k.Pbuf = w.Pbuf;
     k.timing = getenv("ABCD_TIMING") != nullptr;
-    k.dML = w.dML; k.dHidPre = w.dHidPre; k.dG = w.dG; k.dHoff = w.dHoff; k.dHC0 = w.dHC0; k.dbias = w.dbias;
+    k.dML = w.dML; k.dHidPre = w.dHidPre; k.dG = w.dG; k.dHoff = w.dHoff; k.dHC0 = w.dHC0; k.dbias = w.dbias; k.Pb2 = w.Pb2; k.Pb1 = w.Pb1;
     return k;
 }
 

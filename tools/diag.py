@@ -79,6 +79,15 @@ def dec_timing():
 		print('   P1 gemm: stage-issue %.0f wait+sync %.0f mma %.0f chunks %.2f tail-sync %.0f' % tuple(x / n for x in v[10:15]))
 
 
-if os.environ.get('ABCD_TIMING'):
+if os.environ.get('ABCD_TIMING') == '3':
+	# the last dec launch was the backward kernel
+	import ctypes as C
+	pkg = importlib.import_module('seq2seq_abcd-vae_b200')
+	out = (C.c_ulonglong * 16)()
+	pkg._lib.load().abcd_debug_dec_timing(out)
+	v = list(out); n = float(max(v[15], 1))
+	names = ['prefetch', 'B3 gemm', 'B3 store', 'B2 local gemm', 'barrier', 'B2 reduce', 'pointwise', 'B1 local gemm', 'barrier', 'B1 reduce', 'barrier']
+	print('dec_bwd CTA0 cycles/step: ' + ', '.join('%s %.0f' % (nm, x / n) for nm, x in zip(names, v[:11])) + ' (steps %d, total %.0f)' % (v[15], sum(v[:11]) / n))
+elif os.environ.get('ABCD_TIMING'):
 	enc_timing()
 	dec_timing()
