@@ -291,39 +291,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
 // -------------------------------------------------------------------------------------------------
 // backward
 // -------------------------------------------------------------------------------------------------
-// out[rows, 4 ncg] = A[rows, 4*K4] * W[4*K4, LDW] on operands that are already in shared memory; work items are
-// (column group, row group) pairs with the usual 10-row x 4-column register tile (rows rg + 8 i) and the
-// register-double-buffered inner loop of rnn_common.cuh.  Results go to `out` (global, row pitch ldo).
-template <int K4, int LDA, int LDW>
-__device__ __forceinline__ void local_gemm_store(const float* A, const float* W, int ncg, int na, float* out, long ldo, int tid) {
-    const int nslots = (na + RG - 1) / RG;
-    for (int item = tid; item < ncg * NRG; item += NTHREADS) {
-        const int cg = item % ncg, rg = item / ncg;
-        if (rg >= na) continue;
-        const float* a = A + rg * LDA;
-        const float* w = W + cg * 4;
-        float acc[RT][4];
-        zero_acc(acc);
-        switch (nslots) {
-            case 1: mma_range<1, LDA, LDW>(acc, a, w, K4); break;
-            case 2: mma_range<2, LDA, LDW>(acc, a, w, K4); break;
-            case 3: mma_range<3, LDA, LDW>(acc, a, w, K4); break;
-            case 4: mma_range<4, LDA, LDW>(acc, a, w, K4); break;
-            case 5: mma_range<5, LDA, LDW>(acc, a, w, K4); break;
-            case 6: mma_range<6, LDA, LDW>(acc, a, w, K4); break;
-            case 7: mma_range<7, LDA, LDW>(acc, a, w, K4); break;
-            case 8: mma_range<8, LDA, LDW>(acc, a, w, K4); break;
-            case 9: mma_range<9, LDA, LDW>(acc, a, w, K4); break;
-            default: mma_range<RT, LDA, LDW>(acc, a, w, K4); break;
-        }
-#pragma unroll
-        for (int i = 0; i < RT; ++i) {
-            const int r = rg + i * RG;
-            if (r < na) *reinterpret_cast<float4*>(out + (long)r * ldo + cg * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        }
-    }
-}
-
 // Backward.  Every contraction over a dimension that is partitioned over the cluster (the hidden units of the MLPs,
 // the gate columns of the cell) is computed as a partial product on the CTA's OWN slice -- which it has just produced
 // and still holds in shared memory -- followed by an in-cluster reduction of the partials through L2:

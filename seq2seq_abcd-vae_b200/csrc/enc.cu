@@ -233,17 +233,24 @@ struct EncBwdK {
     const float* d_out;   // [B][out_ld]
     float* dg[2];         // [sumT][4H]
     float* dbias[2];      // [n_tiles][4H]: per-tile column sums of dg (bias gradients), interleaved layout
+    float* pbuf;          // [2 parities][gridDim.x][ROWS][H]: partial dh exchanged inside a cluster
 };
 
+// The gate gradients dG_t of a step are produced unit by unit (thread-local cell backward), so the contraction
+// dh_{t-1} = dG_t W_hh runs over a dimension that is partitioned over the cluster: every CTA multiplies ITS dG slice
+// (still in shared memory) by the matching rows of W_hh into a partial dh over all H units, publishes it through L2,
+// and after the cluster barrier the owner of each unit adds the CL partials in a fixed order.  The partial buffers
+// alternate between steps, so one cluster barrier per step is enough.
 template <int CELL>
 __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
     constexpr int CL = ENC_CL, U = ENC_U, NTHREADS = ENC_NT;
+    constexpr int GSP = 4 * U + 4;           // pitch of the dG slice in shared memory
     extern __shared__ __align__(16) float smem[];
     const int H = ABCD_H;
-    float* Wsm = smem;                       // [4H][U]: Wsm[uu*4+slot][j] = W_hh[gate(slot)*H+uu][u0+j]
-    float* dh_sm = Wsm + 4 * H * U;          // [ROWS][U] recurrent dh carried to the next (earlier) step
+    float* Wr = smem;                        // [4U][H]: Wr[u*4+slot][j] = W_hh[gate(slot)*H + u0+u][j]
+    float* dh_sm = Wr + 4 * U * H;           // [ROWS][U] recurrent dh carried to the next (earlier) step
     float* dc_sm = dh_sm + ROWS * U;         // [ROWS][U] LSTM: dc carry; GRU: direct dh*z carry
-    const Stage st = make_stage(dc_sm + ROWS * U, ENC_KC_BWD);
+    float* Gsm = dc_sm + ROWS * U;           // [ROWS][GSP] this step's dG slice
 
     const int tid = threadIdx.x;
     const int rank = (int)cluster_ctarank();
@@ -252,13 +259,13 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
     const int u0 = rank * U;
     {
         const float* W = p.w_hh[dir];
-        for (int idx = tid; idx < 4 * H * (U / 4); idx += NTHREADS) {
-            int jq = idx % (U / 4), kphys = idx / (U / 4);
-            int uu = kphys >> 2, s = kphys & 3;
+        for (int idx = tid; idx < 4 * U * (H / 4); idx += NTHREADS) {
+            int jq = idx % (H / 4), kphys = idx / (H / 4);
+            int uu = u0 + (kphys >> 2), s = kphys & 3;
             int gate = CELL == 0 ? s : (s == 0 ? 0 : s == 1 ? 1 : s == 3 ? 2 : -1);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gate >= 0) v = *reinterpret_cast<const float4*>(W + (long)(gate * H + uu) * H + u0 + jq * 4);
-            *reinterpret_cast<float4*>(Wsm + kphys * U + jq * 4) = v;
+            if (gate >= 0) v = *reinterpret_cast<const float4*>(W + (long)(gate * H + uu) * H + jq * 4);
+            *reinterpret_cast<float4*>(Wr + kphys * H + jq * 4) = v;
         }
         for (int idx = tid; idx < ROWS * U; idx += NTHREADS) { dh_sm[idx] = 0.f; dc_sm[idx] = 0.f; }
     }
@@ -271,13 +278,14 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
         int b = tile + p.n_tiles * (prg + i * RG);
         len[i] = b < p.B ? p.lengths[b] : 0;
     }
-    const int KS = pick_ks_fit(U / 4, U, ENC_KC_BWD, NTHREADS);
-    const ThreadMap tm = make_map(tid, U / 4, KS);
     const int Tt = p.lengths[tile];
     const float* gs = p.gs[dir];
     const float* cs = p.cs[dir];
     const float* hs = p.hs[dir];
     float* dg = p.dg[dir];
+    const long pb_stride = (long)gridDim.x * ROWS * H;             // one parity buffer
+    float* Pmine = p.pbuf + (long)blockIdx.x * ROWS * H;
+    const float* Pclu = p.pbuf + (long)cid * CL * ROWS * H;
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);   // this thread's share of the bias gradient (sum of dG over rows and steps)
     __syncthreads();
 
@@ -350,30 +358,29 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
                 dc_sm[r * U + pu] = dh * zg;
             }
             *reinterpret_cast<float4*>(dg + frame * (4 * H) + unit * 4) = dgv;
+            *reinterpret_cast<float4*>(Gsm + r * GSP + pu * 4) = dgv;
             bsum.x += dgv.x; bsum.y += dgv.y; bsum.z += dgv.z; bsum.w += dgv.w;
         }
+        __syncthreads();
+        // partial dh_prev[rows, H] = dG[rows, my 4U] * W_hh[my 4U, H]; only rows that have a previous frame
+        const long par = (long)(s & 1) * pb_stride;
+        if (na_src > 0) local_gemm_store<U, GSP, ABCD_H>(Gsm, Wr, H / 4, na_src, Pmine + par, H, tid);
         cluster_sync_all();
-        // dh_prev[rows, my units] = dG[rows, 4H] * W_hh[4H, my units]; only rows that have a previous frame
-        if (na_src > 0) {
-            float acc[RT][4];
-            zero_acc(acc);
-            const int n_tiles = p.n_tiles;
-            auto rp = [=](int r) -> const float* { return dg + ((long)off_t + tile + (long)n_tiles * r) * (4 * ABCD_H); };
-            phase_gemm<ENC_NT, ENC_KC_BWD, ENC_U>(acc, st, 4 * H, rp, 0, NullRow(), na_src, Wsm, tm, KS, tid);
-            if (tm.active && tm.ks == 0) {
+        for (int idx = tid; idx < na_src * (U / 4); idx += NTHREADS) {
+            const int r = idx / (U / 4), q = idx % (U / 4);
+            float4 v[CL];
 #pragma unroll
-                for (int i = 0; i < RT; ++i) {
-                    int r = tm.rg + i * RG;
-                    if (r < na_src)
-                        *reinterpret_cast<float4*>(dh_sm + r * U + tm.cg * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-                }
-            }
+            for (int src = 0; src < CL; ++src) v[src] = ld_cg4(Pclu + par + ((long)src * ROWS + r) * H + u0 + q * 4);
+            float4 a = v[0];
+#pragma unroll
+            for (int src = 1; src < CL; ++src) { a.x += v[src].x; a.y += v[src].y; a.z += v[src].z; a.w += v[src].w; }
+            *reinterpret_cast<float4*>(dh_sm + r * U + q * 4) = a;
         }
         __syncthreads();
     }
     // bias gradients: fixed-order reduction over the row groups, one row of partial sums per tile
     {
-        float4* red = reinterpret_cast<float4*>(st.buf0);
+        float4* red = reinterpret_cast<float4*>(Gsm);
         red[prg * U + pu] = bsum;
         __syncthreads();
         if (tid < U) {
@@ -397,7 +404,7 @@ bool rnn_use_tc() {
     if (g_rnn_tc < 0) { const char* e = getenv("ABCD_RNN_TC"); g_rnn_tc = (e && e[0] == '1') ? 1 : 0; }
     return g_rnn_tc == 1;
 }
-size_t enc_bwd_smem() { return (size_t)(4 * ABCD_H * ENC_U + 2 * ROWS * ENC_U + stage_floats(ENC_KC_BWD)) * sizeof(float); }
+size_t enc_bwd_smem() { return (size_t)(4 * ENC_U * ABCD_H + 2 * ROWS * ENC_U + ROWS * (4 * ENC_U + 4)) * sizeof(float); }
 
 template <class K, class P>
 int launch_cluster(K kernel, int n_clusters, size_t smem, cudaStream_t stream, const P& params) {
@@ -474,6 +481,7 @@ struct EncWs {
     float* cs[2];
     float* dg[2];
     float* dbias[2];
+    float* pbuf;
     int* prev_fwd;
     int* prev_bwd;
     float* xpad;      // [sumT][pad4(F)] copy of the input with 16-byte aligned rows (bulk-copy friendly)
@@ -500,6 +508,7 @@ static EncWs enc_carve(void* base, size_t cap, int cell, int F, int B, int sumT,
         // dG aliases xproj (dead after the forward recurrence) -- both [sumT][4H] per direction
         for (int d = 0; d < ndirs; ++d) w.dg[d] = w.xproj[d];
         for (int d = 0; d < ndirs; ++d) w.dbias[d] = a.take<float>((size_t)((B + ROWS - 1) / ROWS) * 4 * H);
+        w.pbuf = a.take<float>((size_t)2 * ndirs * ((B + ROWS - 1) / ROWS) * ENC_CL * ROWS * H);
         w.prev_fwd = a.take<int>(sumT);
         w.prev_bwd = a.take<int>(sumT);
         w.xpad = a.take<float>((size_t)sumT * ((F + 3) & ~3));
@@ -579,6 +588,7 @@ int enc_backward(const EncParams& P, const EncGrads& G, const PackedMeta& pk, co
     k.out_ld = ndirs * H * (P.cell == 0 ? 2 : 1);
     k.batch_sizes = pk.batch_sizes; k.offsets = pk.offsets; k.lengths = pk.lengths;
     k.d_out = d_last_hidden;
+    k.pbuf = w.pbuf;
     for (int d = 0; d < ndirs; ++d) {
         k.w_hh[d] = P.w_hh[d]; k.hs[d] = w.hs[d]; k.gs[d] = w.gs[d]; k.cs[d] = w.cs[d]; k.dg[d] = w.dg[d]; k.dbias[d] = w.dbias[d];
     }
