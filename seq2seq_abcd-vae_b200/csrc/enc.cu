@@ -39,6 +39,27 @@ __global__ void combine_bias_kernel(int cell, const float* __restrict__ b_ih, co
     out[i] = v;
 }
 
+// Input-projection operands for the tensor-core GEMM: weight_ih re-homed as [4H physical columns (u*4+slot)][Fpad]
+// (16-byte aligned rows, zero padded) and the combined bias in the same interleaved order.
+__global__ void prep_ih_kernel(int cell, int F, int Fpad, const float* __restrict__ w_ih, const float* __restrict__ b_ih,
+                               const float* __restrict__ b_hh, float* __restrict__ w_out, float* __restrict__ b_out) {
+    const int H = ABCD_H;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 4 * H * Fpad; idx += gridDim.x * blockDim.x) {
+        const int phys = idx / Fpad, k = idx % Fpad;
+        const int u = phys >> 2, s = phys & 3;
+        const int gate = cell == 0 ? s : (s == 3 ? -1 : s);
+        w_out[idx] = (gate >= 0 && k < F) ? w_ih[(long)(gate * H + u) * F + k] : 0.f;
+        if (k == 0) {
+            float b = 0.f;
+            if (gate >= 0) {
+                b = b_ih[gate * H + u];
+                if (cell == 0 || gate < 2) b += b_hh[gate * H + u];
+            }
+            b_out[phys] = b;
+        }
+    }
+}
+
 __global__ void pad_rows_kernel(long rows, int F, int Fpad, const float* __restrict__ src, int ld_src, float* __restrict__ dst) {
     long total = rows * Fpad;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -475,6 +496,7 @@ int enc_init() {
 // ---- workspace layout --------------------------------------------------------------------------
 struct EncWs {
     float* bias_comb[2];
+    float* wih_pad[2];  // [4H][pad4(F)] interleaved, zero-padded copy of weight_ih
     float* xproj[2];
     float* hs[2];
     float* gs[2];
@@ -497,6 +519,7 @@ static EncWs enc_carve(void* base, size_t cap, int cell, int F, int B, int sumT,
     const int H = ABCD_H;
     for (int d = 0; d < ndirs; ++d) {
         w.bias_comb[d] = a.take<float>(4 * H);
+        w.wih_pad[d] = a.take<float>((size_t)4 * H * ((F + 3) & ~3));
         w.xproj[d] = a.take<float>((size_t)sumT * 4 * H);
         w.hs[d] = a.take<float>(save ? (size_t)sumT * H : (size_t)2 * B * H);
         if (save) {
@@ -504,6 +527,7 @@ static EncWs enc_carve(void* base, size_t cap, int cell, int F, int B, int sumT,
             if (cell == 0) w.cs[d] = a.take<float>((size_t)sumT * H);
         }
     }
+    w.xpad = a.take<float>((size_t)sumT * ((F + 3) & ~3));
     if (save) {
         // dG aliases xproj (dead after the forward recurrence) -- both [sumT][4H] per direction
         for (int d = 0; d < ndirs; ++d) w.dg[d] = w.xproj[d];
@@ -511,7 +535,6 @@ static EncWs enc_carve(void* base, size_t cap, int cell, int F, int B, int sumT,
         w.pbuf = a.take<float>((size_t)2 * ndirs * ((B + ROWS - 1) / ROWS) * ENC_CL * ROWS * H);
         w.prev_fwd = a.take<int>(sumT);
         w.prev_bwd = a.take<int>(sumT);
-        w.xpad = a.take<float>((size_t)sumT * ((F + 3) & ~3));
         int s1 = sgemm_pick_splits(4 * H, H, sumT), s2 = sgemm_pick_splits(4 * H, F, sumT);
         w.partial_floats = (size_t)4 * H * ((size_t)s1 * H > (size_t)s2 * F ? (size_t)s1 * H : (size_t)s2 * F);
         w.partials = a.take<float>(w.partial_floats);
@@ -543,14 +566,21 @@ int enc_forward(const EncParams& P, const PackedMeta& pk, const float* x, int ld
     k.out_ld = ndirs * H * (P.cell == 0 ? 2 : 1);
     k.batch_sizes = pk.batch_sizes; k.offsets = pk.offsets; k.lengths = pk.lengths;
     k.out = last_hidden;
-    for (int d = 0; d < ndirs; ++d) {
-        combine_bias_kernel<<<(4 * H + 255) / 256, 256, 0, stream>>>(P.cell, P.b_ih[d], P.b_hh[d], w.bias_comb[d]);
+    // the input rows are re-homed with a 16-byte aligned pitch so the tensor-core GEMMs can stream them
+    const int Fpad = (P.F + 3) & ~3;
+    const bool use_pad = (ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0);
+    if (use_pad) {
+        pad_rows_kernel<<<592, 256, 0, stream>>>(pk.sumT, P.F, Fpad, x, ldx, w.xpad);
         KERNEL_CHECK();
+    }
+    for (int d = 0; d < ndirs; ++d) {
+        prep_ih_kernel<<<148, 256, 0, stream>>>(P.cell, P.F, Fpad, P.w_ih[d], P.b_ih[d], P.b_hh[d], w.wih_pad[d], w.bias_comb[d]);
+        KERNEL_CHECK();
+        // xproj[frame][u*4+slot] = x W_ih^T + bias (gate-interleaved by construction of the operands)
         GemmArgs g = gemm_args_zero();
-        g.M = pk.sumT; g.N = 4 * H; g.K = P.F;
-        g.A = x; g.lda = ldx; g.a_kmajor = 1;
-        g.B = P.w_ih[d]; g.ldb = P.F; g.b_kmajor = 1;
-        g.b_nsrc = P.cell == 0 ? gate_map(H, 0, 1, 2, 3) : gate_map(H, 0, 1, 2, -1);
+        g.M = pk.sumT; g.N = 4 * H; g.K = (use_pad || ldx >= Fpad) ? Fpad : P.F;
+        g.A = use_pad ? w.xpad : x; g.lda = use_pad ? Fpad : ldx; g.a_kmajor = 1;
+        g.B = w.wih_pad[d]; g.ldb = Fpad; g.b_kmajor = 1;
         g.C = w.xproj[d]; g.ldc = 4 * H;
         g.bias = w.bias_comb[d];
         TRY(sgemm_launch(g, stream));
@@ -615,10 +645,7 @@ int enc_backward(const EncParams& P, const EncGrads& G, const PackedMeta& pk, co
         // dW_ih += dG^T * X
         // the input rows are re-homed with a 16-byte aligned pitch so the tensor-core path can bulk-copy them
         const int Fpad = (P.F + 3) & ~3;
-        if (d == 0 && (ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0)) {
-            pad_rows_kernel<<<592, 256, 0, stream>>>(pk.sumT, P.F, Fpad, x, ldx, w.xpad);
-            KERNEL_CHECK();
-        }
+        // (the padded copy of x was made by the forward pass and lives in the same workspace)
         const bool use_pad = (ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0);
         g.N = P.F; g.B = use_pad ? w.xpad : x; g.ldb = use_pad ? Fpad : ldx; g.b_kgather = nullptr;
         g.m_dst = map_ih; g.C = G.w_ih[d]; g.ldc = P.F;

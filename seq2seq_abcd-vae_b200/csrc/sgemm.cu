@@ -334,6 +334,8 @@ static bool use_small_tiles(int M, int N, int splits) {
 bool umma_tn_eligible(const GemmArgs& g);
 int umma_tn_pick_splits(int M, int K);
 int umma_tn_launch(const GemmArgs& g, int splits, cudaStream_t stream);
+bool umma_rm_eligible(const GemmArgs& g);
+int umma_rm_launch(const GemmArgs& g, cudaStream_t stream);
 
 // ABCD_UMMA=0 forces the FFMA path for every GEMM (A/B comparisons, debugging)
 static bool umma_enabled() {
@@ -366,6 +368,7 @@ int sgemm_launch(const GemmArgs& gin, cudaStream_t stream) {
     ARG_CHECK(!(g.b_kgather && g.b_kmajor), "sgemm: k-gather needs n-major B");
     ARG_CHECK(!(g.b_nsrc.enabled && !g.b_kmajor), "sgemm: n source map needs k-major B");
     ProfScope ps(PROF_GEMM, stream);
+    if (umma_enabled() && umma_rm_eligible(g)) return umma_rm_launch(g, stream);   // tall row-major products on tcgen05
     if (umma_enabled() && umma_tn_eligible(g)) {
         // tensor-core path (tcgen05 3xTF32): partial tiles per split, then the common reduce/epilogue kernel
         TRY(umma_tn_launch(g, g.splits, stream));

@@ -221,6 +221,29 @@ def test_sgemm_layouts(abcd):
 				assert rel_to_max(Cout, want) < 2e-6 * max(1, K ** 0.5), (M, N, K, a_km, b_km, splits)
 
 
+def test_umma_rowmajor_gemm_3xtf32(abcd):
+	"""tcgen05 3xTF32 GEMM for tall row-major activations (NT: input projection / MLP layers, NN: data gradients), fused
+	bias + scale + tanh epilogue, ragged last row tile and column block."""
+	L = abcd._lib
+	L.ensure_device(torch.device('cuda'))
+	torch.manual_seed(2)
+	for (M, N, K, act) in ((14755, 1024, 68, 0), (4100, 256, 256, 1), (2048, 324, 1024, 0), (3000, 64, 32, 1)):
+		A = torch.randn(M, K, device='cuda'); Bm = torch.randn(K, N, device='cuda') * 0.2
+		bias = torch.randn(N, device='cuda')
+		want = 0.5 * (A.double() @ Bm.double()) + bias.double()
+		scale = float(want.abs().max())   # error budget is relative to the largest pre-activation
+		if act:
+			want = torch.tanh(want)
+		for b_km in (1, 0):
+			Bin = Bm.t().contiguous() if b_km else Bm.contiguous()
+			Cout = torch.full((M, N), 7.0, device='cuda')
+			L.call('abcd_sgemm', M, N, K, L.ptr(A), K, 1, L.ptr(Bin), Bin.shape[1], b_km, L.ptr(Cout), N,
+				0.5, L.ptr(bias), act, 0, 1, None, L.stream_ptr())
+			torch.cuda.synchronize()
+			err = float((Cout.double() - want).abs().max()) / scale
+			assert err < 3e-6 + 1.5e-8 * K, (M, N, K, act, b_km, err)
+
+
 def test_clip_sgd_matches_golden(abcd, golden_dir):
 	L = abcd._lib
 	L.ensure_device(torch.device('cuda'))
