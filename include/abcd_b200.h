@@ -11,7 +11,9 @@
  *  - functions only enqueue work on `stream` (a cudaStream_t passed as void*); they never synchronise;
  *  - return 0 on success, a negative code otherwise; abcd_last_error() returns a thread-local message;
  *  - nothing throws across the ABI; re-entrant across streams/threads after abcd_init();
- *  - all arithmetic is IEEE fp32 (FFMA), special functions of the Dirichlet KL in fp64;
+ *  - fp32 throughout: the recurrent kernels are IEEE fp32 FFMA, the GEMMs outside the time loops run on the tensor
+ *    cores as 3xTF32 (hi/lo split, fp32 accumulation; <= 3e-6 + 1.5e-8*K relative to the largest output), special
+ *    functions of the Dirichlet KL in fp64;
  *  - recurrent kernels are specialised for rnn_hidden_size = mlp_hidden_size = 256 and output_size <= 129;
  *    anything else is rejected with ABCD_ERR_UNSUPPORTED/ABCD_ERR_ARG -- there is no fallback path.
  *

@@ -101,7 +101,7 @@ static DecGrads to_dg(const abcd_dec_grads_t* p) {
 extern "C" {
 
 const char* abcd_last_error(void) { return g_err; }
-const char* abcd_version(void) { return "abcd_b200 0.1 (sm_100a, fp32 FFMA cluster-persistent recurrences)"; }
+const char* abcd_version(void) { return "abcd_b200 0.2 (sm_100a: cluster-persistent fp32 recurrences, tcgen05 3xTF32 GEMMs)"; }
 
 // which: 0 enc_fwd, 1 enc_bwd, 2 dec_fwd, 3 dec_bwd -> number of co-resident clusters (or negative error)
 int abcd_max_active_clusters(int which, int F) {
