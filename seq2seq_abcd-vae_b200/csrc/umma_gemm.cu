@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_tn_kernel(UmmaArgs g) {
     char* stage = b_lo + B_TILE;                               // UM_STAGES x STAGE_BYTES
     __shared__ uint64_t mma_bar;
     __shared__ uint32_t tmem_base_sh;
+    __shared__ int brow_sm[4][UM_SLAB];   // source row of B per reduction index (gather resolved one slab ahead), -1: none
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * UM_BM;
@@ -102,18 +103,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_tn_kernel(UmmaArgs g) {
                 const int n4 = (g.N + 3) >> 2;   // 16-byte pieces per row (rows are padded to 4 columns)
                 for (int idx = tid; idx < UM_SLAB * (NB / 4); idx += UM_THREADS) {
                     const int k = idx / (NB / 4), mn4 = idx % (NB / 4);
-                    const int gk = k0s + k;
-                    if (gk < kend && mn4 < n4) {
-                        const long brow = g.b_kgather ? (long)__ldg(g.b_kgather + gk) : (long)gk;
+                    if (mn4 < n4) {
+                        const long brow = brow_sm[s & 3][k];
                         if (brow >= 0) cp_async16(stb + k * (NB * 4) + mn4 * 16, g.B + brow * g.ldb + mn4 * 4);
                     }
                 }
             } else {
                 for (int idx = tid; idx < UM_SLAB * NB; idx += UM_THREADS) {
                     const int k = idx / NB, n = idx % NB;
-                    const int gk = k0s + k;
-                    if (gk < kend && n < g.N) {
-                        const long brow = g.b_kgather ? (long)__ldg(g.b_kgather + gk) : (long)gk;
+                    if (n < g.N) {
+                        const long brow = brow_sm[s & 3][k];
                         if (brow >= 0) {
                             unsigned sa = smem_u32(stb + k * (NB * 4) + n * 4);
                             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(g.B + brow * g.ldb + n) : "memory");
@@ -125,6 +124,17 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_tn_kernel(UmmaArgs g) {
         cp_async_commit();
     };
 
+    // gather indices are resolved a slab before the copies that need them, so no copy waits on an index load
+    auto load_rows = [&](int s) {
+        if (tid < UM_SLAB) {
+            const int gk = kbeg + s * UM_SLAB + tid;
+            int r = -1;
+            if (s < nslab && gk < kend) r = g.b_kgather ? __ldg(g.b_kgather + gk) : gk;
+            brow_sm[s & 3][tid] = r;
+        }
+    };
+    load_rows(0); load_rows(1); load_rows(2);
+    __syncthreads();
     for (int s = 0; s < UM_STAGES; ++s) issue_slab(s, s);
 
     for (int s = 0; s < nslab; ++s) {
@@ -132,6 +142,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_tn_kernel(UmmaArgs g) {
         const int k0 = kbeg + s * UM_SLAB;
         cp_async_wait<UM_STAGES - 1>();                                     // this thread's copies of slab s landed
         __syncthreads();                                                    // ... and everyone else's
+        load_rows(s + 3);
         if (s > 0) mbar_wait(&mma_bar, (uint32_t)((s - 1) & 1));            // tiles are free again
         const char* st = stage + (size_t)slot * STAGE_BYTES;
         // ---- split staged fp32 rows into swizzled hi / lo tiles ----
@@ -144,9 +155,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_tn_kernel(UmmaArgs g) {
         for (int idx = tid; idx < UM_SLAB * (NB / 4); idx += UM_THREADS) {
             const int k = idx / (NB / 4), mn4 = idx % (NB / 4);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int gk = k0 + k;
-            if (gk < kend && mn4 * 4 < g.N) {
-                const bool present = g.b_kgather ? (__ldg(g.b_kgather + gk) >= 0) : true;
+            if (mn4 * 4 < g.N) {
+                const bool present = brow_sm[s & 3][k] >= 0;
                 if (present) {
                     v = *reinterpret_cast<const float4*>(st + UM_SLAB * UM_BM * 4 + k * (NB * 4) + mn4 * 16);
                     const int n = mn4 * 4;   // columns past N hold stale staging bytes: clear them
