@@ -64,6 +64,9 @@ __device__ __forceinline__ uint32_t tile_off(int k, int mn4 /* float4 index alon
     return (uint32_t)(chunk * CHUNK_BYTES + k * 128 + (((c32 ^ (k & 3)) << 5) | (half << 4)));
 }
 // 3xTF32 split: hi = x with the low 13 mantissa bits cleared (exact in TF32), lo = x - hi (exact in fp32)
+// (kind::tf32 itself ignores the low 13 mantissa bits of its 32-bit operands -- measured: feeding the raw fp32 value as
+// `hi` gives bit-identical results -- so a kernel that can place raw data directly in the tile layout only has to
+// produce the `lo` tile; see lo_of().)
 __device__ __forceinline__ void split_store(char* hi_base, char* lo_base, uint32_t off, float4 v) {
     float4 h, l;
     h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
@@ -72,6 +75,14 @@ __device__ __forceinline__ void split_store(char* hi_base, char* lo_base, uint32
     h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
     *reinterpret_cast<float4*>(hi_base + off) = h;
     *reinterpret_cast<float4*>(lo_base + off) = l;
+}
+__device__ __forceinline__ float4 lo_of(float4 v) {
+    float4 l;
+    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    return l;
 }
 // 16 accumulator columns of this warp's 32 TMEM lanes
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
