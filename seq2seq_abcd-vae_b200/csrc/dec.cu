@@ -677,7 +677,7 @@ size_t dec_bwd_fixed_floats(int F) {   // resident weights + dh/dc carries
     return (size_t)(2 * Fp * 2 * U + 2 * U * ABCD_H + 4 * U * DEC_N1P + 2 * ROWS * U);
 }
 int pick_kc(size_t fixed_floats) {
-    for (int kc : {64, 32})
+    for (int kc : {128, 64, 32})
         if ((fixed_floats + stage_floats(kc)) * sizeof(float) <= SMEM_MAX) return kc;
     return 0;
 }
@@ -790,12 +790,17 @@ int dec_read_timing(unsigned long long* out16) {
     return ABCD_OK;
 }
 int dec_max_clusters(int which, int F, int* out) {
-    const void* fn = which == 0 ? (dec_fwd_kc(F) == 64 ? (const void*)dec_fwd_kernel<0, 64> : (const void*)dec_fwd_kernel<0, 32>)
-                                : (dec_bwd_kc(F) == 64 ? (const void*)dec_bwd_kernel<0, 64> : (const void*)dec_bwd_kernel<0, 32>);
+    const int kc = which == 0 ? dec_fwd_kc(F) : dec_bwd_kc(F);
+    const void* fn = which == 0 ? (kc == 128 ? (const void*)dec_fwd_kernel<0, 128> : kc == 64 ? (const void*)dec_fwd_kernel<0, 64> : (const void*)dec_fwd_kernel<0, 32>)
+                                : (kc == 128 ? (const void*)dec_bwd_kernel<0, 128> : kc == 64 ? (const void*)dec_bwd_kernel<0, 64> : (const void*)dec_bwd_kernel<0, 32>);
     return rnn_max_active_clusters(fn, which == 0 ? dec_fwd_smem(F) : dec_bwd_smem(F), CL, NTHREADS, out);
 }
 
 int dec_init() {
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0, 128>, SMEM_MAX));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1, 128>, SMEM_MAX));
+    TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<0, 128>, SMEM_MAX));
+    TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<1, 128>, SMEM_MAX));
     TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0, 64>, SMEM_MAX));
     TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1, 64>, SMEM_MAX));
     TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0, 32>, SMEM_MAX));
@@ -841,7 +846,10 @@ int dec_forward(const DecParams& P, const PackedMeta& pk, const float* feat_in, 
     {
         ProfScope ps(PROF_DEC_FWD, stream);
         const size_t sm = dec_fwd_smem(P.F);
-        if (k.kc == 64) {
+        if (k.kc == 128) {
+            if (P.cell == 0) TRY(launch_cluster_dec(dec_fwd_kernel<0, 128>, n_tiles, sm, stream, k));
+            else TRY(launch_cluster_dec(dec_fwd_kernel<1, 128>, n_tiles, sm, stream, k));
+        } else if (k.kc == 64) {
             if (P.cell == 0) TRY(launch_cluster_dec(dec_fwd_kernel<0, 64>, n_tiles, sm, stream, k));
             else TRY(launch_cluster_dec(dec_fwd_kernel<1, 64>, n_tiles, sm, stream, k));
         } else {
@@ -909,7 +917,10 @@ int dec_backward(const DecParams& P, const DecGrads& G, const PackedMeta& pk, co
     {
         ProfScope ps(PROF_DEC_BWD, stream);
         const size_t sm = dec_bwd_smem(P.F);
-        if (k.kc == 64) {
+        if (k.kc == 128) {
+            if (P.cell == 0) TRY(launch_cluster_dec(dec_bwd_kernel<0, 128>, n_tiles, sm, stream, k));
+            else TRY(launch_cluster_dec(dec_bwd_kernel<1, 128>, n_tiles, sm, stream, k));
+        } else if (k.kc == 64) {
             if (P.cell == 0) TRY(launch_cluster_dec(dec_bwd_kernel<0, 64>, n_tiles, sm, stream, k));
             else TRY(launch_cluster_dec(dec_bwd_kernel<1, 64>, n_tiles, sm, stream, k));
         } else {
