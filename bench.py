@@ -50,10 +50,19 @@ def parse():
 # ---------------------------------------------------------------------------------------------------------
 # synthetic workload (deterministic; identical for both arms)
 # ---------------------------------------------------------------------------------------------------------
-def make_batch(B, F, seed):
+def make_batch(B, F, seed, rank=0, world=1):
+	"""Synthetic batch of B segments for one rank.  With world > 1 the GLOBAL length-sorted batch of B*world segments is
+	sharded the way training shards it (dist.shard_sorted_batch: rank r takes positions r, r+world, ...), so every rank
+	sees the same length distribution; values are drawn per rank."""
 	from oracle import cases as CS
 	from oracle import abcd_oracle as O
-	lengths = CS.synthetic_lengths(B, 1000 + seed)
+	if world == 1:
+		lengths = CS.synthetic_lengths(B, 1000 + seed)
+	else:
+		dist = importlib.import_module('seq2seq_abcd-vae_b200.dist')
+		_, lengths = dist.shard_sorted_batch(CS.synthetic_lengths(B * world, 1000), rank, world)
+		lengths = np.ascontiguousarray(lengths)
+		seed = seed + rank
 	rng = np.random.RandomState(seed)
 	sumT = int(lengths.sum())
 	x = np.clip(rng.normal(0.45, 0.25, size=(sumT, F)), -0.945, 1.05).astype(np.float32)
@@ -214,7 +223,7 @@ def main():
 	L = pkg._lib
 	from oracle import cases as CS
 
-	lengths, bs, x_host, off_host = make_batch(args.batch, args.bins, rank)
+	lengths, bs, x_host, off_host = make_batch(args.batch, args.bins, 0, rank, world)
 	learner = learning.Learner(args.bins, 256, 256, 256, CFG['K'], CFG['f'], None, encoder_rnn_type=args.rnn,
 								decoder_rnn_type=args.rnn, device=str(dev), seed=1111)
 	# identical deterministic weights on every rank (and in the CPU arm)

@@ -22,13 +22,27 @@ __device__ __forceinline__ int gate_src_row(const GateMap& gm, int phys) {
     return g < 0 ? -1 : g * gm.H + u;
 }
 
-template <int BM, int BN, int TM, int TN, bool A_KM, bool B_KM>
+constexpr int CLK_SIZE = 8;   // cluster split-K factor of the small-problem path
+
+__device__ __forceinline__ float4 ld_dsmem4(const float* local, unsigned rank) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(local), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(a), "r"(rank));
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(r) : "memory");
+    return v;
+}
+
+// CLK: the CTAs of a (1,1,CLK_SIZE) cluster split K; their partial tiles meet in distributed shared memory, every CTA
+// reduces BM/CLK_SIZE rows of the tile in a fixed order and applies the epilogue (small problems that cannot fill the GPU
+// with output tiles alone: the 512-row sampler / MLP GEMMs; deterministic, no partials workspace).
+template <int BM, int BN, int TM, int TN, bool A_KM, bool B_KM, bool CLK = false>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 sgemm_kernel(GemmArgs g, int a_vec, int b_vec) {
     constexpr int NT = (BM / TM) * (BN / TN);
     constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
     __shared__ __align__(16) float As[2][BK][LDA_S];
     __shared__ __align__(16) float Bs[2][BK][LDB_S];
+    __shared__ __align__(16) float Cs[CLK ? BM : 1][CLK ? BN + 4 : 4];
 
     const int tid = threadIdx.x;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -197,6 +211,46 @@ sgemm_kernel(GemmArgs g, int a_vec, int b_vec) {
         }
     }
 
+    if (CLK) {
+        // partial tile -> own shared memory; reduce a slice of the tile across the cluster; epilogue
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int gq = 0; gq < NG; ++gq)
+                *reinterpret_cast<float4*>(&Cs[(i / 4) * (TYN * 4) + ty * 4 + (i % 4)][gq * (TXN * 4) + tx * 4]) =
+                    make_float4(acc[i][gq * 4], acc[i][gq * 4 + 1], acc[i][gq * 4 + 2], acc[i][gq * 4 + 3]);
+        cluster_sync_all();
+        const unsigned rank = cluster_ctarank();
+        constexpr int RPC = BM / CLK_SIZE;
+        for (int idx = tid; idx < RPC * (BN / 4); idx += NT) {
+            const int r = rank * RPC + idx / (BN / 4), c4 = idx % (BN / 4);
+            float4 sum = ld_dsmem4(&Cs[r][c4 * 4], 0);
+#pragma unroll
+            for (unsigned pr = 1; pr < CLK_SIZE; ++pr) {
+                const float4 v = ld_dsmem4(&Cs[r][c4 * 4], pr);
+                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            }
+            const int m = m0 + r, nb = n0 + c4 * 4;
+            if (m >= g.M || nb >= g.N) continue;
+            const int mrow = gate_src_row(g.m_dst, m);
+            if (mrow < 0) continue;
+            float v[4] = {sum.x, sum.y, sum.z, sum.w};
+            float* dst = g.C + (long)mrow * g.ldc + nb;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (nb + q >= g.N) continue;
+                float t = g.alpha * v[q];
+                if (g.bias) {
+                    int bi = g.bias_on_m ? mrow : gate_src_row(g.b_nsrc, nb + q);
+                    t += g.bias[bi < 0 ? 0 : bi];
+                }
+                if (g.act == 1) t = tanhf(t);
+                dst[q] = g.accumulate ? dst[q] + t : t;
+            }
+        }
+        cluster_sync_all();   // peers may still be reading this CTA's tile
+        return;
+    }
     // epilogue
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
@@ -322,6 +376,22 @@ int launch_cfg(const GemmArgs& g, int a_vec, int b_vec, cudaStream_t stream) {
     return ABCD_OK;
 }
 
+template <bool A_KM, bool B_KM>
+int launch_clk(const GemmArgs& g, int a_vec, int b_vec, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((g.N + 63) / 64, (g.M + 63) / 64, CLK_SIZE);
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = CLK_SIZE;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    abcd_note_launch(1);
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, sgemm_kernel<64, 64, 4, 4, A_KM, B_KM, true>, g, a_vec, b_vec));
+    return ABCD_OK;
+}
+
 }  // namespace
 
 // 128x128 tiles only when they alone fill the GPU; otherwise 64x64 tiles (4x the CTAs, shorter K loops per CTA)
@@ -382,6 +452,13 @@ int sgemm_launch(const GemmArgs& gin, cudaStream_t stream) {
     const int a_vec = ((uintptr_t)g.A % 16 == 0) && (g.lda % 4 == 0);
     const int b_vec = ((uintptr_t)g.B % 16 == 0) && (g.ldb % 4 == 0);
     int r;
+    // small problems (few output tiles, long K): split K over an 8-CTA cluster, reduce through distributed shared memory
+    const long tiles64 = (long)((g.M + 63) / 64) * ((g.N + 63) / 64);
+    if (g.splits == 1 && !g.b_kgather && tiles64 <= 64 && g.K >= 256 && !(!g.a_kmajor && g.b_kmajor)) {
+        if (g.a_kmajor && g.b_kmajor) return launch_clk<true, true>(g, a_vec, b_vec, stream);
+        if (g.a_kmajor && !g.b_kmajor) return launch_clk<true, false>(g, a_vec, b_vec, stream);
+        return launch_clk<false, false>(g, a_vec, b_vec, stream);
+    }
     if (use_small_tiles(g.M, g.N, g.splits)) r = launch_cfg<64, 64, 4, 4>(g, a_vec, b_vec, stream);
     else r = launch_cfg<128, 128, 8, 8>(g, a_vec, b_vec, stream);
     if (r != ABCD_OK) return r;
