@@ -14,6 +14,17 @@ TRAIN_CASES = {
 								num_speakers=3, E=256),
 	'train_lstm_f129': dict(rnn='LSTM', F=129, K=128, f=256, lengths=[9, 6, 6, 2], pretrain=True, tau=1.0, N_data=4, seed=4),
 }
+# Additional GPU-vs-oracle cases (no golden file: the oracle itself is pinned to the reference by the cases above):
+# several row tiles, ragged tiles, narrow / odd feature sizes.
+EXTRA_CASES = {
+	'train_lstm_3tiles': dict(rnn='LSTM', F=65, K=128, f=256, lengths=sorted([(i * 7) % 23 + 1 for i in range(170)], reverse=True),
+								pretrain=False, tau=0.9, N_data=5000, seed=5),
+	'train_gru_f33_2tiles': dict(rnn='GRU', F=33, K=64, f=128, lengths=sorted([(i * 5) % 17 + 1 for i in range(85)], reverse=True),
+								pretrain=True, tau=1.0, N_data=85, seed=6),
+	'train_lstm_f5': dict(rnn='LSTM', F=5, K=16, f=32, lengths=[7, 5, 5, 3, 1], pretrain=False, tau=1.0, N_data=50, seed=7),
+	'train_gru_f129_speaker': dict(rnn='GRU', F=129, K=32, f=64, lengths=[12, 12, 9, 4, 4, 4, 2, 1, 1], pretrain=False, tau=0.7, N_data=9, seed=8,
+								num_speakers=4, E=256),
+}
 SAMPLE_STRIDE = 101
 
 
