@@ -106,6 +106,50 @@ def test_train_step_matches_oracle_and_golden(abcd, golden_dir, name):
 			np.testing.assert_allclose(CS.sample_vec(gr), g['gradsample/{}/{}'.format(m, k)], rtol=0, atol=TOL * ref_norm + 1e-12)
 
 
+def test_learner_train_steps_match_oracle(abcd):
+	"""learning.Learner.train_step: backward kernels accumulating straight into the flat gradient arena, fused global-norm
+	clip + SGD (+ zeroing) -- two consecutive steps against the fp64 oracle (reference: learning.py:147-163)."""
+	import importlib
+	learning = importlib.import_module('seq2seq_abcd-vae_b200.learning')
+	cfg = CS.TRAIN_CASES['train_lstm_gumbel']
+	F = cfg['F']
+	learner = learning.Learner(F, 256, 256, 256, cfg['K'], cfg['f'], None, device='cuda', seed=3)
+	mods = learner._modules()
+	enc_sd, smp_sd, dec_sd, seqs, eps, gumbel, speaker = CS.build_case(cfg, mods)
+	for m, sd in zip(mods, (enc_sd, smp_sd, dec_sd)):
+		m.load_state_dict({k: v.cuda() for k, v in sd.items()})
+	learner.setup_optimizer(0.5, 0.0, gradient_clip=1.0, patience=0)
+	learner.feature_sampler.train()
+	learner.feature_sampler.temperature = cfg['tau']
+	packed = torch.nn.utils.rnn.pack_sequence(seqs)
+	is_off = O.is_offset_packed(packed.batch_sizes.tolist())
+	p_in = torch.nn.utils.rnn.PackedSequence(packed.data.cuda(), packed.batch_sizes)
+	p_off = torch.nn.utils.rnn.PackedSequence(is_off.cuda(), packed.batch_sizes)
+	dt = torch.float64
+	state = [{k: (v.to(dt) if v.dtype.is_floating_point else v) for k, v in sd.items()} for sd in (enc_sd, smp_sd, dec_sd)]
+	names = ('encoder', 'feature_sampler', 'decoder')
+	for step in range(2):
+		learner.feature_sampler.injected_gumbel_noise = gumbel.cuda()
+		learner.decoder.injected_emission_noise = eps.cuda()
+		loss = learner.train_step(p_in, p_off, None, cfg['N_data'], False)[0]
+		o = O.train_step(state[0], state[1], state[2], [x.to(dt) for x in seqs], eps.to(dt), gumbel.to(dt), cfg['N_data'], False,
+						cfg['tau'], cfg['rnn'], 1.0, None)
+		assert abs(loss.item() - o['loss'].item()) < 2e-5 * abs(o['loss'].item()), step
+		keys, params, grads = [], [], []
+		for i, n in enumerate(names):
+			for k, g in o['grads'][n].items():
+				keys.append((i, k)); params.append(state[i][k]); grads.append(g)
+		new, total, _ = O.clip_and_sgd(params, grads, 0.5, 1.0)
+		for (i, k), p in zip(keys, new):
+			state[i][k] = p.detach()
+		assert abs(learner.arena.norm.item() - total) < 1e-4 * total
+		assert float(learner.arena.grad.abs().max()) == 0.0          # the fused step leaves the gradient arena zeroed
+		for i, m in enumerate(mods):
+			for k, v in m.state_dict().items():
+				if v.dtype.is_floating_point and k != 'prior_concentration':
+					assert rel_to_max(v, state[i][k]) < TOL, (step, names[i], k)
+
+
 def test_encoder_large_ragged_batch_matches_oracle(abcd):
 	"""More than one row tile (B > 64), ties, length-1 segments; inference (no-save) path; LSTM and GRU."""
 	for rnn, seed in (('LSTM', 11), ('GRU', 12)):
