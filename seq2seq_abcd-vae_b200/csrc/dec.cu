@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
     const int F = p.F, Fp = p.Fp;
     const int XC = xcols_per_cta(F);
     constexpr int HSP = 2 * U + 4;            // pitch of the CTA's own hidden-layer slice kept in shared memory
-    float* Wg = smem;                         // [Fp+H][U*4]
+    float* Wg = smem;                         // [H+Fp][U*4]: recurrent rows first, then the input rows
     float* W1 = Wg + (Fp + H) * (U * 4);      // [H][2U]
     float* W2s = W1 + H * (2 * U);            // [U][2Fp]: rows of the output layers that multiply this CTA's hidden units
     const Stage st = make_stage(W2s + U * 2 * Fp, KC);
@@ -77,12 +77,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
         int col = idx % (U * 4), k = idx / (U * 4);
         int u = col >> 2, s = col & 3;
         float v = 0.f;
-        if (k < Fp) {
+        if (k >= H) {
             int gate = CELL == 0 ? s : (s == 3 ? -1 : s);
-            if (k < F && gate >= 0) v = p.w_ih[(long)(gate * H + u0 + u) * F + k];
+            if (k - H < F && gate >= 0) v = p.w_ih[(long)(gate * H + u0 + u) * F + (k - H)];
         } else {
             int gate = CELL == 0 ? s : (s == 0 ? 0 : s == 1 ? 1 : s == 3 ? 2 : -1);
-            if (gate >= 0) v = p.w_hh[(long)(gate * H + u0 + u) * H + (k - Fp)];
+            if (gate >= 0) v = p.w_hh[(long)(gate * H + u0 + u) * H + k];
         }
         Wg[idx] = v;
     }
@@ -157,7 +157,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
             auto rpx = [=](int r) -> const float* { return Xall + (prev_base + tile + (long)n_tiles * r) * Fp; };
             auto rph = [=](int r) -> const float* { return Hall + (prev_base + tile + (long)n_tiles * r) * ABCD_H; };
             DEC_TICK(0)
-            phase_gemm<NTHREADS, KC, U * 4>(acc, st, Fp, rpx, H, rph, na, Wg, tm1, KS1, tid, timing ? tacc + 10 : nullptr);
+            // h_{t-1} has been visible since the first barrier of the previous step; x_t only after the barrier whose
+            // arrive ended that step: the h part of the contraction overlaps that barrier
+            phase_gemm<NTHREADS, KC, U * 4>(acc, st, H, rph, Fp, rpx, na, Wg, tm1, KS1, tid, timing ? tacc + 10 : nullptr, t > 0 ? H / KC : -1);
             DEC_TICK(1)
 #pragma unroll
             for (int i = 0; i < RT; ++i) {
@@ -279,10 +281,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
         }
         DEC_TICK(7)
         DEC_TICK(8)
-        cluster_sync_all();
+        cluster_arrive_release();   // matched by the wait inside the next step's P1 (or the one after the loop)
         DEC_TICK(9)
     }
 #undef DEC_TICK
+    if (Tt > 0) cluster_wait_acquire();
     if (timing) { tacc[15] = Tt; for (int i = 0; i < 16; ++i) g_dec_timing[i] = tacc[i]; }
     float tot = block_sum(nll, red);
     if (tid == 0) p.nll_partial[blockIdx.x] = tot;

@@ -310,20 +310,22 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);   // this thread's share of the bias gradient (sum of dG over rows and steps)
     __syncthreads();
 
-    for (int s = 0; s < Tt; ++s) {
+    // Saved activations of a step are fetched one step ahead (issued before the previous step's local GEMM), so their
+    // L2 latency hides behind that GEMM instead of sitting in front of the cell backward.
+    float4 g4v[RT];
+    float cv[RT], pv[RT], doh[RT], doc[RT];
+    auto step_geometry = [&](int s, int& t, int& na, int& off_t, int& na_src, int& off_src) {
         // walk the forward recurrence of this direction backwards
-        const int t = dir == 0 ? Tt - 1 - s : s;
-        const int na = active_rows(p.batch_sizes[t], tile, p.n_tiles);
-        const int off_t = p.offsets[t];
+        t = dir == 0 ? Tt - 1 - s : s;
+        na = active_rows(p.batch_sizes[t], tile, p.n_tiles);
+        off_t = p.offsets[t];
         // "previous" frame in the forward recurrence of this direction (source of h_prev / c_prev)
-        int na_src, off_src;
         if (dir == 0) { na_src = t > 0 ? na : 0; off_src = t > 0 ? p.offsets[t - 1] : 0; }
         else { na_src = (t + 1 < Tt) ? active_rows(p.batch_sizes[t + 1], tile, p.n_tiles) : 0; off_src = (t + 1 < Tt) ? p.offsets[t + 1] : 0; }
-
-        // gather every saved activation this thread needs first (independent loads in flight together), then
-        // compute and store: interleaving them row by row would serialise one memory round trip per row
-        float4 g4v[RT];
-        float cv[RT], pv[RT], doh[RT], doc[RT];
+    };
+    auto prefetch = [&](int s) {
+        int t, na, off_t, na_src, off_src;
+        step_geometry(s, t, na, off_t, na_src, off_src);
 #pragma unroll
         for (int i = 0; i < RT; ++i) {
             int r = prg + i * RG;
@@ -344,6 +346,13 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
                 if (is_final) doh[i] = __ldg(dout + dir * H + unit);
             }
         }
+    };
+    if (Tt > 0) prefetch(0);
+
+    for (int s = 0; s < Tt; ++s) {
+        int t, na, off_t, na_src, off_src;
+        step_geometry(s, t, na, off_t, na_src, off_src);
+        (void)off_src;
 #pragma unroll
         for (int i = 0; i < RT; ++i) {
             int r = prg + i * RG;
@@ -383,6 +392,7 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
             bsum.x += dgv.x; bsum.y += dgv.y; bsum.z += dgv.z; bsum.w += dgv.w;
         }
         __syncthreads();
+        if (s + 1 < Tt) prefetch(s + 1);
         // partial dh_prev[rows, H] = dG[rows, my 4U] * W_hh[my 4U, H]; only rows that have a previous frame
         const long par = (long)(s & 1) * pb_stride;
         if (na_src > 0) local_gemm_store<U, GSP, ABCD_H>(Gsm, Wr, H / 4, na_src, Pmine + par, H, tid);

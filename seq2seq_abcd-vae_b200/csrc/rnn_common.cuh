@@ -180,12 +180,13 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[RT][4], const float* As, 
 
 // acc += A[rows, K0+K1] * Wsm[K0+K1, LDW] for this thread's tile.  On return the threads with ks == 0
 // hold the full sums for rows rg + i*RG (i < RT) and columns cg*4 .. cg*4+3.  Ends with a CTA barrier, so the
-// staging buffers may be reused immediately.  `dbg` (optional) accumulates clock cycles of the calling thread:
+// staging buffers may be reused immediately.  `wait_chunk` >= 1: the caller has issued a cluster arrive; the matching
+// wait is executed just before chunk `wait_chunk` is staged.  `dbg` (optional) accumulates clock cycles of the calling thread:
 // [0] staging issue, [1] wait + barrier, [2] multiply, [3] chunks, [4] tail barrier.
 template <int NT, int KC, int LDW, class RP0, class RP1>
 __device__ __forceinline__ void phase_gemm(float (&acc)[RT][4], const Stage& st, int K0, RP0 rp0, int K1,
                                            RP1 rp1, int nrows, const float* Wsm, const ThreadMap& tm,
-                                           int KS, int tid, unsigned long long* dbg = nullptr) {
+                                           int KS, int tid, unsigned long long* dbg = nullptr, int wait_chunk = -1) {
     const int K = K0 + K1;
     const int nslots = (nrows + RG - 1) / RG;   // active 16-row slots (uniform over the CTA)
     const int nch = (K + KC - 1) / KC;
@@ -200,6 +201,9 @@ __device__ __forceinline__ void phase_gemm(float (&acc)[RT][4], const Stage& st,
         __syncthreads();   // chunk c visible to all; everyone is done with chunk c-1's buffer
         long long e1 = dbg ? clock64() : 0;
         if (c + 1 < nch) {
+            // split-phase cluster barrier: rows of chunks >= wait_chunk are produced by other CTAs in the phase that ended
+            // with a cluster arrive; everything before them overlaps the barrier latency
+            if (c + 1 == wait_chunk) cluster_wait_acquire();
             const int kb = (c + 1) * KC;
             stage_chunk<NT, KC>((c & 1) ? st.buf0 : st.buf1, kb, min(KC, K - kb), nrows, K0, rp0, rp1, tid);
             cp_async_commit();
@@ -211,6 +215,7 @@ __device__ __forceinline__ void phase_gemm(float (&acc)[RT][4], const Stage& st,
         }
         if (dbg) { long long e3 = clock64(); dbg[1] += e1 - e0; dbg[0] += e2 - e1; dbg[2] += e3 - e2; dbg[3] += 1; }
     }
+    if (wait_chunk >= nch) cluster_wait_acquire();   // (never with the callers' shapes; keeps arrive/wait paired)
     long long f0 = dbg ? clock64() : 0;
     __syncthreads();
     if (dbg) dbg[4] += clock64() - f0;
