@@ -423,6 +423,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
                     hdv[i] = __ldg(reinterpret_cast<const float4*>(p.Hid + frame * (2 * M) + (col / U) * M + u0 + col % U));
                 }
             }
+            // the saved-activation loads above do not depend on other CTAs: they overlap the barrier that ended the
+            // previous step (whose dML updates feed the contraction below)
+            if (t < Tt - 1) cluster_wait_acquire();
             DEC_TICK(0)
             phase_gemm<NTHREADS, KC, 2 * U>(acc, st, 2 * Fp, rp, 0, NullRow(), na, WB3, tm3, KS3, tid);
             DEC_TICK(1)
@@ -542,10 +545,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
             *reinterpret_cast<float4*>(dh_sm + r * U + q * 4) = a;
         }
         DEC_TICK(9)
-        cluster_sync_all();
+        cluster_arrive_release();   // matched by the wait after the next step's prefetch (or the one after the loop)
         DEC_TICK(10)
     }
 #undef DEC_TICK
+    if (Tt > 0) cluster_wait_acquire();
     if (timing) { tacc[15] = Tt; for (int i = 0; i < 16; ++i) g_dec_timing[i] = tacc[i]; }
     // gradient w.r.t. the initial state produced by feature2hidden (h0 = even, c0 = odd columns; model.py:100)
     for (int i = 0; i < PR; ++i) {

@@ -179,6 +179,8 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
                 xp[i] = __ldg(reinterpret_cast<const float4*>(xp_base + frame * (4 * H) + unit * 4));
             }
         }
+        // the loads above are independent of other CTAs: they overlap the barrier that ended the previous step
+        if (s > 0) cluster_wait_acquire();
         float acc[RT][4];
         zero_acc(acc);
         long long c1 = timing ? clock64() : 0;
@@ -233,12 +235,13 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
             }
         }
         long long c3 = timing ? clock64() : 0;
-        cluster_sync_all();
+        cluster_arrive_release();   // matched by the wait after the next step's input loads (or the one after the loop)
         if (timing) {
             long long c4 = clock64();
             tacc[0] += c1 - c0; tacc[1] += c2 - c1; tacc[2] += c3 - c2; tacc[3] += c4 - c3; tacc[4] += 1;
         }
     }
+    if (Tt > 0) cluster_wait_acquire();
     if (timing) for (int i = 0; i < 5; ++i) { g_enc_timing[i] = tacc[i]; g_enc_timing[5 + i] = pg[i]; }
     if (TC) tc_fini<TS::TMEM_COLS>(tc, tid);
 }
