@@ -29,6 +29,12 @@ if ROOT not in sys.path:
 	sys.path.insert(0, ROOT)
 
 METRIC = 'train segments/sec (fwd+bwd+step)'
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the persistent kernels on this workload, from the
+# `ncu --set full` capture summarised in profiles/r01_d_split_barriers_cluster_splitk_B512.txt (B=512, F=65, LSTM)
+NCU_TRAFFIC_BYTES = {
+	'enc_fwd_kernel': 123.13e6 + 132.33e6, 'enc_bwd_kernel': 155.37e6 + 96.92e6,
+	'dec_fwd_kernel': 12.01e6 + 81.92e6, 'dec_bwd_kernel': 139.44e6 + 73.62e6,
+}
 CFG = dict(rnn='LSTM', F=65, K=128, f=256, H=256, M=256, B=512, N_data=100000)
 
 
@@ -321,8 +327,10 @@ def main():
 		dur = groups[dom]['ms_per_step'] / max(groups[dom]['launches_per_step'], 1) * 1e-3
 		achieved = kernel_flops[dom] / dur / 1e12
 		peak = peaks.get('bf16_tflops_sustained', 1400.0)
+		publication = args.batch == CFG['B'] and args.bins == CFG['F'] and args.rnn == 'LSTM'
 		roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-					'traffic': None, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1400 (B200_PROFILING.md)',
+					'traffic': NCU_TRAFFIC_BYTES.get(dom) if publication else None, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1400 (B200_PROFILING.md)',
+					'traffic_source': 'profiles/r01_d_split_barriers_cluster_splitk_B512.txt (ncu --set full, bytes per launch)' if publication else None,
 					'note': 'fp32 FFMA kernel (fp32-exact mode); fraction is of the measured bf16 tensor peak; fp32 FFMA peak is ~72 TFLOP/s',
 					'frac_of_fp32_ffma_peak': achieved / 72.0, 'avg_launch_ms': dur * 1e3}
 

@@ -5,8 +5,8 @@
 //
 // One persistent cluster kernel per direction of time (forward / BPTT).  Per step, three phases separated by
 // hardware cluster barriers; every weight slice stays resident in shared memory (see rnn_common.cuh):
-//   fwd  P1 gates+cell (K = Fp+H)      P2 MLP hidden layers (K = H)        P3 mean/log-var/sample/NLL (K = 2M)
-//   bwd  B3 d(hidden pre-act) (K=2Fp)  B2 dh + gate gradients (K = 2M)     B1 [dh_prev | dx] (K = 4H)
+//   fwd  P1 gates+cell (K = H+Fp)      P2 MLP hidden layers (K = H)        P3 mean/log-var/sample/NLL (K-split over the hidden units)
+//   bwd  B3 d(hidden pre-act) (K=2Fp)  B2' dh + gate gradients             B1' [dh_prev | dx]   (both K-split over the CTA's own slice)
 // The offset predictor (model.py:191-195) does not feed the recurrence and runs as plain GEMMs over all
 // frames, as do all weight gradients.
 #include "rnn_common.cuh"
@@ -17,7 +17,6 @@ using namespace rnn;
 
 namespace {
 
-constexpr int DEC_NC3 = 20;    // P3 weight-slice pitch: 2 mean + 2 log-var columns for up to 5 pairs of x columns per CTA
 constexpr int DEC_N1P = 392;   // backward: pitch of the resident [W_hh | W_ih] rows (H + pad4(F) <= 388 for F <= 129)
 constexpr size_t SMEM_MAX = 232448;   // 227 KB of dynamic shared memory per CTA on sm_100
 constexpr float LOG_2PI = 1.8378770664093453f;

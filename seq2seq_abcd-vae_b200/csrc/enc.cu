@@ -2,10 +2,10 @@
 // only the final states, i.e. RNN_Variational_Encoder.forward (ABCD-VAE/modules/model.py:60-66) and its
 // backward.  Gate order follows torch.nn.LSTM (i,f,g,o) / torch.nn.GRU (r,z,n) (model.py:53).
 //
-// Forward = hoisted input projection (sgemm NT over all packed frames, gates stored unit-major interleaved)
+// Forward = hoisted input projection (tensor-core GEMM over all packed frames, gates stored unit-major interleaved)
 //         + one persistent cluster kernel per launch that runs both directions concurrently.
-// Backward = persistent BPTT kernel producing pre-activation gate gradients for every frame
-//         + weight/bias gradients as large TN GEMMs over all frames.
+// Backward = persistent BPTT kernel (K-split local GEMM + in-cluster reduction) producing pre-activation gate
+//         gradients for every frame and the bias-gradient sums + weight gradients as tensor-core TN GEMMs over all frames.
 #include <stdlib.h>
 #include "rnn_common.cuh"
 #include "rnn_tc.cuh"
@@ -22,23 +22,10 @@ constexpr int ENC_CL = 8;
 constexpr int ENC_U = ABCD_H / ENC_CL;
 constexpr int ENC_NT = NRG * ENC_U;
 constexpr int ENC_KC_FWD = 128;
-constexpr int ENC_KC_BWD = 64;
 
 // -------------------------------------------------------------------------------------------------
 // small helper kernels
 // -------------------------------------------------------------------------------------------------
-// Combined projection bias: LSTM b_ih+b_hh (4H); GRU [b_ir+b_hr, b_iz+b_hz, b_in] (3H) -- b_hn stays inside
-// the r*(W_hn h + b_hn) term.
-__global__ void combine_bias_kernel(int cell, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
-                                    float* __restrict__ out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int n = (cell == 0 ? 4 : 3) * ABCD_H;
-    if (i >= n) return;
-    float v = b_ih[i];
-    if (cell == 0 || i < 2 * ABCD_H) v += b_hh[i];
-    out[i] = v;
-}
-
 // Input-projection operands for the tensor-core GEMM: weight_ih re-homed as [4H physical columns (u*4+slot)][Fpad]
 // (16-byte aligned rows, zero padded) and the combined bias in the same interleaved order.
 __global__ void prep_ih_kernel(int cell, int F, int Fpad, const float* __restrict__ w_ih, const float* __restrict__ b_ih,
