@@ -616,11 +616,14 @@ class _DecoderFn(torch.autograd.Function):
 		feat_in, eps, gt, is_offset, *params = ctx.saved_tensors
 		F, H, M = ctx.dims
 		dev = feat_in.device
-		g = torch.zeros(2, dtype=torch.float32, device=dev)
-		if g_em is not None:
-			g[0] = g_em
-		if g_off is not None:
-			g[1] = g_off
+		if g_em is not None and g_off is not None:
+			g = torch.stack((g_em.reshape(()), g_off.reshape(()))).to(torch.float32)   # one kernel instead of fill + 2 copies
+		else:
+			g = torch.zeros(2, dtype=torch.float32, device=dev)
+			if g_em is not None:
+				g[0] = g_em
+			if g_off is not None:
+				g[1] = g_off
 		grads, rets = _grad_buffers(params)
 		d_feat = torch.empty_like(feat_in)
 		dp, dg = _dec_structs(ctx.cell, F, H, M, feat_in.shape[1], params, grads)
