@@ -41,6 +41,7 @@ struct DecK {
     // backward only
     float* dML; float* dHidPre; float* dG; const float* dHoff; float* dHC0;
     float* dbias;   // [n_tiles][4H]: per-tile column sums of dG (recurrent bias gradients), interleaved layout
+    float* dbias1;  // [n_tiles][2M]: per-tile column sums of dHidPre (bias gradients of the two MLP input layers)
     float* Pb2;     // [n_tiles][CL][ROWS][H]     partial dh from the MLP input layers, exchanged inside a cluster
     float* Pb1;     // [n_tiles][CL][ROWS][H+Fp]  partial [dh_prev | dx] from the cell
 };
@@ -370,6 +371,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
     float* Pb1 = p.Pb1 + (long)blockIdx.x * ROWS * N1;
     const float* Pb1t = p.Pb1 + (long)tile * CL * ROWS * N1;
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);   // this thread's share of sum(dG) over rows and steps
+    float4 hsum = make_float4(0.f, 0.f, 0.f, 0.f);   // ... and of sum(dHidPre) (bias gradients of the MLP input layers)
     __syncthreads();
     const bool timing = p.timing && blockIdx.x == 0 && tid == 0;
     unsigned long long tacc[16];
@@ -442,6 +444,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
                                            acc[i][2] * (1.f - hd.z * hd.z), acc[i][3] * (1.f - hd.w * hd.w));
                     *reinterpret_cast<float4*>(p.dHidPre + o) = v;
                     *reinterpret_cast<float4*>(Ds + r * DSP + col) = v;
+                    hsum.x += v.x; hsum.y += v.y; hsum.z += v.z; hsum.w += v.w;
                 }
             }
             __syncthreads();
@@ -575,6 +578,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
                 a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
             }
             *reinterpret_cast<float4*>(p.dbias + (long)tile * (4 * H) + (u0 + tid) * 4) = a;
+        }
+        // MLP input-layer bias gradients: threads of the B3 epilogue hold sums for (4 columns, their row group)
+        __syncthreads();
+        if (tm3.active && tm3.ks == 0) red[tm3.rg * (2 * U / 4) + tm3.cg] = hsum;
+        __syncthreads();
+        if (tid < 2 * U / 4) {
+            float4 a = red[tid];
+            for (int g = 1; g < NRG; ++g) {
+                const float4 b = red[g * (2 * U / 4) + tid];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            const int col = tid * 4;   // column of this CTA's slice: [which][u0 + col % U]
+            *reinterpret_cast<float4*>(p.dbias1 + (long)tile * (2 * M) + (col / U) * M + u0 + col % U) = a;
         }
     }
 }
@@ -712,7 +728,7 @@ int launch_cluster_dec(K kernel, int n_clusters, size_t smem, cudaStream_t strea
 
 struct DecWs {
     float *hc0, *Hall, *Call, *Xall, *Gs, *Hid, *Mean, *Lv, *HidOff, *OffLogit, *nll_partial, *bce_partial, *Pbuf;
-    float *dML, *dHidPre, *dG, *dHoff, *dHidOffPre, *dLogit, *dHC0, *dbias, *Pb2, *Pb1, *partials;
+    float *dML, *dHidPre, *dG, *dHoff, *dHidOffPre, *dLogit, *dHC0, *dbias, *dbias1, *Pb2, *Pb1, *partials;
     int* prev;
     size_t partial_floats;
     size_t bytes;
@@ -747,6 +763,7 @@ DecWs dec_carve(void* base, size_t cap, int cell, int F, int fin, int B, int sum
     w.dLogit = a.take<float>((size_t)sumT);
     w.dHC0 = a.take<float>((size_t)B * hc);
     w.dbias = a.take<float>((size_t)n_tiles * 4 * H);
+    w.dbias1 = a.take<float>((size_t)n_tiles * 2 * M);
     w.Pb2 = a.take<float>((size_t)n_tiles * CL * ROWS * H);
     w.Pb1 = a.take<float>((size_t)n_tiles * CL * ROWS * (H + Fp));
     w.prev = a.take<int>((size_t)sumT);
@@ -776,7 +793,7 @@ DecK make_k(const DecParams& P, const PackedMeta& pk, const DecWs& w) {
     k.Hall = w.Hall; k.Call = w.Call; k.Xall = w.Xall; k.Gs = w.Gs; k.Hid = w.Hid; k.Mean = w.Mean; k.Lv = w.Lv;
     k.nll_partial = w.nll_partial; k.Pbuf = w.Pbuf;
     k.timing = getenv("ABCD_TIMING") != nullptr;
-    k.dML = w.dML; k.dHidPre = w.dHidPre; k.dG = w.dG; k.dHoff = w.dHoff; k.dHC0 = w.dHC0; k.dbias = w.dbias; k.Pb2 = w.Pb2; k.Pb1 = w.Pb1;
+    k.dML = w.dML; k.dHidPre = w.dHidPre; k.dG = w.dG; k.dHoff = w.dHoff; k.dHC0 = w.dHC0; k.dbias = w.dbias; k.dbias1 = w.dbias1; k.Pb2 = w.Pb2; k.Pb1 = w.Pb1;
     return k;
 }
 
@@ -958,7 +975,8 @@ int dec_backward(const DecParams& P, const DecGrads& G, const PackedMeta& pk, co
     TRY(colsum_launch(w.dbias, 4 * H, (pk.B + ROWS - 1) / ROWS, 4 * H, 1.f, G.b_hh, 1, map_hh, stream));
     for (int i = 0; i < 2; ++i) {
         TRY(tn(M, H, w.dHidPre + i * M, 2 * M, Hfr, H, nullptr, gate_map_none(), G.em_w1[i], H, sumT));
-        TRY(colsum_launch(w.dHidPre + i * M, 2 * M, sumT, M, 1.f, G.em_b1[i], 1, gate_map_none(), stream));
+        // the BPTT kernel already reduced dHidPre over the frames of every tile
+        TRY(colsum_launch(w.dbias1 + i * M, 2 * M, (pk.B + ROWS - 1) / ROWS, M, 1.f, G.em_b1[i], 1, gate_map_none(), stream));
         TRY(tn(F, M, w.dML + i * Fp, 2 * Fp, w.Hid + i * M, 2 * M, nullptr, gate_map_none(), G.em_w2[i], M, sumT));
         TRY(colsum_launch(w.dML + i * Fp, 2 * Fp, sumT, F, 1.f, G.em_b2[i], 1, gate_map_none(), stream));
     }
