@@ -95,6 +95,9 @@ int abcd_debug_enc_timing(unsigned long long* out10);
 /* same for the last dec_fwd launch: out16[0..9] = P1 setup, P1 gemm, P1 cell, barrier, P2 gemm, P2 store, barrier, P3 setup+gemm,
  * P3 sample, barrier; out16[10..14] = breakdown of the P1 gemm; out16[15] = steps */
 int abcd_debug_dec_timing(unsigned long long* out16);
+/* probe (tools/ts_probe.py): D[128,N] = A[128,K] B[K,N] with the A operand of tcgen05.mma read from tensor memory (TS form),
+ * single-pass TF32; variant bit 0 selects the a_major bit of the instruction descriptor */
+int abcd_debug_ts_probe(const float* A, const float* B, float* D, int K, int N, int variant, void* stream);
 /* Encoder forward recurrence (model.py:60-66) on the tensor cores (tcgen05 kind::tf32, 3xTF32 split, fp32-grade) instead
  * of the FFMA path.  on = 1/0; -1 only queries.  Returns the previous setting.  Initial value: env ABCD_RNN_TC (default 0:
  * the FFMA path is currently the faster one). */

@@ -73,6 +73,7 @@ SIGNATURES = {
 	'abcd_debug_enc_timing': (C.c_int, [P(C.c_ulonglong)]),
 	'abcd_set_rnn_tensorcore': (C.c_int, [C.c_int]),
 	'abcd_debug_dec_timing': (C.c_int, [P(C.c_ulonglong)]),
+	'abcd_debug_ts_probe': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 	'abcd_launch_count': (C.c_longlong, []),
 	'abcd_profile_groups': (C.c_int, []),
 	'abcd_profile_name': (C.c_char_p, [C.c_int]),

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libabcd_b200.so')
-SOURCES = ['api.cu', 'sgemm.cu', 'umma_gemm.cu', 'umma_rm_gemm.cu', 'enc.cu', 'dec.cu', 'sampler.cu', 'stft.cu', 'optim.cu']
+SOURCES = ['api.cu', 'sgemm.cu', 'umma_gemm.cu', 'umma_rm_gemm.cu', 'umma_probe.cu', 'enc.cu', 'dec.cu', 'sampler.cu', 'stft.cu', 'optim.cu']
 NVCC_FLAGS = [
 	'-gencode', 'arch=compute_100a,code=sm_100a',
 	'-O3', '-std=c++17', '-lineinfo',

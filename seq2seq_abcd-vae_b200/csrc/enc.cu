@@ -8,7 +8,7 @@
 //         gradients for every frame and the bias-gradient sums + weight gradients as tensor-core TN GEMMs over all frames.
 #include <stdlib.h>
 #include "rnn_common.cuh"
-#include "rnn_tc.cuh"
+#include "rnn_ts.cuh"
 #include "sgemm.cuh"
 #include "enc.cuh"
 
@@ -86,32 +86,40 @@ struct EncFwdK {
     float* out;              // [B][out_ld]
 };
 
-// TC = true: the per-step gate contraction runs on the tensor cores (rnn_tc.cuh); shared memory is then
-// [operand tiles][W_hh slice][raw staging ring] instead of [W_hh slice][staging buffers].
+// TC = true: the per-step gate contraction runs on the tensor cores with the recurrent weights resident in tensor
+// memory (rnn_ts.cuh); shared memory is then [activation tiles][W_lo tiles][raw staging ring] instead of
+// [W_hh slice][staging buffers].
 template <int CELL, bool TC>
 __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
     constexpr int CL = ENC_CL, U = ENC_U, NTHREADS = ENC_NT;   // 8-CTA clusters, 32 units per CTA, 256 threads
     extern __shared__ __align__(1024) float smem[];
-    using TS = TcShape<ENC_U * 4>;
-    float* Wsm = TC ? smem + TS::TILE_BYTES / 4 : smem;        // [H][U*4]
+    float* Wsm = smem;                                         // FFMA path: [H][U*4]
     const Stage st = make_stage(Wsm + ABCD_H * (U * 4), ENC_KC_FWD);
-    __shared__ uint64_t tc_bars[3];
-    __shared__ uint32_t tc_tmem_slot;
-    TcCtx tc;
+    __shared__ uint64_t ts_bars[TS_STAGES + 1];
+    __shared__ uint32_t ts_tmem_slot;
+    TsCtx ts;
 
     const int tid = threadIdx.x;
-    if (TC) {
-        if ((umma::smem_u32(smem) & 1023u) != 0) __trap();      // operand tiles need 1024-byte alignment
-        tc_init<TS::TMEM_COLS>(tc, reinterpret_cast<char*>(smem), Wsm + ABCD_H * (U * 4), tc_bars, &tc_tmem_slot, tid);
-    }
     const int rank = (int)cluster_ctarank();
     const int cid = blockIdx.x / CL;
     const int tile = cid % p.n_tiles, dir = cid / p.n_tiles;
     const int u0 = rank * U;
     const int H = ABCD_H;
 
-    // resident recurrent weights: Wsm[k][u*4+slot] = W_hh[gate(slot)*H + u0+u][k]
-    {
+    if (TC) {
+        static_assert(ENC_U * 4 == TS_M, "one CTA = 128 gate columns = the tensor-memory lanes");
+        if ((umma::smem_u32(smem) & 1023u) != 0) __trap();      // operand tiles need 1024-byte alignment
+        char* base = reinterpret_cast<char*>(smem);
+        const float* W = p.w_hh[dir];
+        auto wrow = [=](int col) -> const float* {
+            const int u = col >> 2, s = col & 3;
+            const int gate = CELL == 0 ? s : (s == 0 ? 0 : s == 1 ? 1 : s == 3 ? 2 : -1);
+            return gate >= 0 ? W + (long)(gate * ABCD_H + u0 + u) * ABCD_H : nullptr;
+        };
+        ts_init<ABCD_H>(ts, base, base + ts_tiles_bytes(), reinterpret_cast<float*>(base + ts_tiles_bytes() + ts_wlo_bytes(ABCD_H)),
+                        ts_bars, &ts_tmem_slot, wrow, tid);
+    } else {
+        // resident recurrent weights: Wsm[k][u*4+slot] = W_hh[gate(slot)*H + u0+u][k]
         const float* W = p.w_hh[dir];
         for (int idx = tid; idx < U * 4 * (H / 4); idx += NTHREADS) {
             int kq = idx % (H / 4), col = idx / (H / 4);
@@ -179,7 +187,7 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
                 long row = save ? (long)off_prev + b : (long)((s - 1) & 1) * B + b;
                 return hs + row * ABCD_H;
             };
-            if (TC) phase_gemm_tc<ENC_NT, ENC_U * 4, ENC_U * 4>(acc, tc, H, rp, 0, NullRow(), na, Wsm, tm, tid, timing ? pg : nullptr);
+            if (TC) phase_gemm_ts<ABCD_H>(acc, ts, rp, na, tm, tid);
             else phase_gemm<ENC_NT, ENC_KC_FWD, ENC_U * 4>(acc, st, H, rp, 0, NullRow(), na, Wsm, tm, 1, tid, timing ? pg : nullptr);
         }
         long long c2 = timing ? clock64() : 0;
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
     }
     if (Tt > 0) cluster_wait_acquire();
     if (timing) for (int i = 0; i < 5; ++i) { g_enc_timing[i] = tacc[i]; g_enc_timing[5 + i] = pg[i]; }
-    if (TC) tc_fini<TS::TMEM_COLS>(tc, tid);
+    if (TC) ts_fini(ts, tid);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -416,7 +424,7 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
 }
 
 size_t enc_fwd_smem(bool tc) {
-    if (tc) return (size_t)TcShape<ENC_U * 4>::TILE_BYTES + (size_t)ABCD_H * ENC_U * 4 * sizeof(float) + tc_raw_bytes();
+    if (tc) return ts_tiles_bytes() + ts_wlo_bytes(ABCD_H) + ts_raw_bytes();
     return (size_t)(ABCD_H * ENC_U * 4 + stage_floats(ENC_KC_FWD)) * sizeof(float);
 }
 // tensor-core recurrence: env ABCD_RNN_TC=1 or abcd_set_rnn_tensorcore(1)

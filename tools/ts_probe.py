@@ -1,0 +1,24 @@
+# coding: utf-8
+"""Does tcgen05.mma accept its A operand from tensor memory laid out "lane = row, one 32-bit column per k" for kind::tf32?
+    python tools/ts_probe.py"""
+import importlib, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module('seq2seq_abcd-vae_b200')
+L = pkg._lib
+L.ensure_device(torch.device('cuda'))
+torch.manual_seed(0)
+for (K, N) in ((8, 16), (32, 64), (64, 96), (256, 80)):
+	A = torch.randn(128, K, device='cuda'); B = torch.randn(K, N, device='cuda')
+	want = (A.double() @ B.double())
+	for variant in (0,):   # a_major = 1 (MN) with a tensor-memory A operand is an illegal instruction
+		D = torch.full((128, N), 7.0, device='cuda')
+		try:
+			L.call('abcd_debug_ts_probe', L.ptr(A), L.ptr(B), L.ptr(D), K, N, variant, L.stream_ptr())
+			torch.cuda.synchronize()
+			err = float((D.double() - want).abs().max() / want.abs().max())
+			print('K %3d N %3d a_major %d: max rel err %.3e %s' % (K, N, variant, err, 'OK (tf32 single pass)' if err < 5e-3 else 'MISMATCH'))
+		except Exception as e:
+			print('K %3d N %3d a_major %d: FAILED %r' % (K, N, variant, e))
+			raise SystemExit(1)
