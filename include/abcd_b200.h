@@ -98,9 +98,9 @@ int abcd_debug_dec_timing(unsigned long long* out16);
 /* probe (tools/ts_probe.py): D[128,N] = A[128,K] B[K,N] with the A operand of tcgen05.mma read from tensor memory (TS form),
  * single-pass TF32; variant bit 0 selects the a_major bit of the instruction descriptor */
 int abcd_debug_ts_probe(const float* A, const float* B, float* D, int K, int N, int variant, void* stream);
-/* Encoder forward recurrence (model.py:60-66) on the tensor cores (tcgen05 kind::tf32, 3xTF32 split, fp32-grade) instead
- * of the FFMA path.  on = 1/0; -1 only queries.  Returns the previous setting.  Initial value: env ABCD_RNN_TC (default 0:
- * the FFMA path is currently the faster one). */
+/* Encoder forward recurrence (model.py:60-66): per-step gate contraction on the tensor cores (tcgen05 kind::tf32, weights
+ * resident in tensor memory, 3xTF32 split, fp32-grade; default) or on the FFMA path.  on = 1/0; -1 only queries.  Returns
+ * the previous setting.  Initial value: env ABCD_RNN_TC (default 1). */
 int abcd_set_rnn_tensorcore(int on);
 /* kernel launches enqueued by this library since load (what bench.py reports as gpu_launches) */
 long long abcd_launch_count(void);

@@ -168,13 +168,15 @@ def test_encoder_large_ragged_batch_matches_oracle(abcd):
 		assert rel_to_max(got, want) < TOL
 
 
-def test_encoder_tensorcore_recurrence_matches_oracle(abcd):
-	"""Encoder forward with the per-step gate contraction on tcgen05 (kind::tf32, 3xTF32 split; rnn_tc.cuh), both the
-	training (saving) path -- checked through the full backward -- and the inference path; same fp32-grade tolerance."""
+@pytest.mark.parametrize('tensorcore', [1, 0])
+def test_encoder_recurrence_paths_match_oracle(abcd, tensorcore):
+	"""Encoder forward with the per-step gate contraction on tcgen05 (kind::tf32, recurrent weights resident in tensor
+	memory, 3xTF32 split; rnn_ts.cuh -- the default) and on the FFMA path: the training (saving) path -- checked through
+	the full backward -- and the inference path; same fp32-grade tolerance for both."""
 	lib = abcd._lib.load()
-	prev = lib.abcd_set_rnn_tensorcore(1)
+	prev = lib.abcd_set_rnn_tensorcore(tensorcore)
 	try:
-		assert lib.abcd_set_rnn_tensorcore(-1) == 1
+		assert lib.abcd_set_rnn_tensorcore(-1) == tensorcore
 		for rnn, seed in (('LSTM', 21), ('GRU', 22)):
 			lengths = sorted([1, 2, 3, 5, 8, 8, 13, 21, 34, 55] * 9 + [60, 47, 3], reverse=True)   # B = 93: two row tiles
 			F = 65
