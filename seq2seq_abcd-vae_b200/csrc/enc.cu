@@ -423,6 +423,291 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_kernel(EncBwdK p) {
     }
 }
 
+// Tensor-core version of the BPTT kernel: the K-split product  partial dh[rows, H] = dG[rows, my 4U] * W_hh[my 4U, H]  is
+// computed transposed,  D^T[H units, rows] = W^T[H, 4U] * dG^T[4U, rows],  with W^T (two blocks of 128 units x 128 gate
+// rows) resident in tensor memory as the A operand of tcgen05.mma (TS form, rnn_ts.cuh), its low part W - trunc_tf32(W)
+// resident in shared memory, and the gate gradients -- produced by this CTA's own cell backward -- re-laid into hi/lo
+// B-operand tiles straight from shared memory (no global round trip).  The recurrent carries dh / dc live in registers.
+constexpr int EB_GSP = 4 * ENC_U + 4;                      // pitch of the dG slice in shared memory
+constexpr int EB_HALF_K = 2 * TS_SLAB;                     // gate rows per sub-phase (the operand tiles hold half of K)
+constexpr int EB_TILE_BYTES = 2 * TS_B_BYTES;              // two 32-k slabs of [k][rows] tiles (hi or lo)
+constexpr int EB_DCOLS = 96;                               // accumulator columns per 128-unit block
+size_t enc_bwd_ts_smem() { return (size_t)2 * EB_TILE_BYTES + ts_wlo_bytes(4 * ENC_U) * 2 + (size_t)ROWS * EB_GSP * sizeof(float); }
+
+template <int CELL>
+__global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_ts_kernel(EncBwdK p) {
+    constexpr int CL = ENC_CL, U = ENC_U, NTHREADS = ENC_NT;
+    constexpr int KG = 4 * U;                              // 128 gate rows of this CTA = reduction length
+    extern __shared__ __align__(1024) float smem[];
+    const int H = ABCD_H;
+    char* b_hi = reinterpret_cast<char*>(smem);            // [2 slabs][3 chunks][4 KB]
+    char* b_lo = b_hi + EB_TILE_BYTES;
+    char* wlo = b_lo + EB_TILE_BYTES;                      // [KG/32 slabs][8 chunks (256 units)][4 KB]
+    float* Gsm = reinterpret_cast<float*>(wlo + (size_t)(KG / TS_SLAB) * (H / 32) * TS_CHUNK);   // [ROWS][EB_GSP], piece-swizzled
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = (int)cluster_ctarank();
+    const int cid = blockIdx.x / CL;
+    const int tile = cid % p.n_tiles, dir = cid / p.n_tiles;
+    const int u0 = rank * U;
+    if ((umma::smem_u32(smem) & 1023u) != 0) __trap();
+    if (warp == 0) umma::tmem_alloc<512>(&tmem_slot);
+    if (tid == 0) {
+        umma::mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    uint32_t bar_uses = 0;
+    {
+        // gate row k (= uu*4 + slot) of this CTA -> row of W_hh (or -1)
+        const float* W = p.w_hh[dir];
+        auto wrow = [=](int k) -> const float* {
+            const int uu = u0 + (k >> 2), s = k & 3;
+            const int gate = CELL == 0 ? s : (s == 0 ? 0 : s == 1 ? 1 : s == 3 ? 2 : -1);
+            return gate >= 0 ? W + (long)(gate * ABCD_H + uu) * ABCD_H : nullptr;
+        };
+        // hi: W^T into tensor memory, block b = warp >> 2, lane = unit within the block
+        {
+            const int b = warp >> 2, lq = warp & 3;
+            const int j = b * 128 + lq * 32 + lane;
+            for (int k0 = 0; k0 < KG; k0 += 16) {
+                uint32_t r[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float* w = wrow(k0 + q);
+                    r[q] = __float_as_uint(w ? __ldg(w + j) : 0.f);
+                }
+                const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(TS_A_COL + b * KG + k0);
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+                    ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        }
+        // lo: MN-major tiles [k][unit]
+        for (int idx = tid; idx < KG * (H / 4); idx += NTHREADS) {
+            const int j4 = idx % (H / 4), k = idx / (H / 4);
+            const float* w = wrow(k);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (w) v = umma::lo_of(__ldg(reinterpret_cast<const float4*>(w + j4 * 4)));
+            *reinterpret_cast<float4*>(wlo + (size_t)(k / TS_SLAB) * (H / 32) * TS_CHUNK + umma::tile_off<TS_CHUNK>(k % TS_SLAB, j4)) = v;
+        }
+        umma::fence_proxy_async();
+    }
+    // pointwise mapping: thread -> (unit pu, rows prg + i*RG); a warp holds the 32 units of one row group
+    const int pu = tid % U, prg = tid / U;
+    const int unit = u0 + pu;
+    int len[RT];
+    float dh_reg[RT], dc_reg[RT];   // recurrent carries of this thread's (row, unit) pairs
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+        int b = tile + p.n_tiles * (prg + i * RG);
+        len[i] = b < p.B ? p.lengths[b] : 0;
+        dh_reg[i] = 0.f; dc_reg[i] = 0.f;
+    }
+    const int Tt = p.lengths[tile];
+    const float* gs = p.gs[dir];
+    const float* cs = p.cs[dir];
+    const float* hs = p.hs[dir];
+    float* dg = p.dg[dir];
+    const long pb_stride = (long)gridDim.x * ROWS * H;             // one parity buffer
+    float* Pmine = p.pbuf + (long)blockIdx.x * ROWS * H;
+    const float* Pclu = p.pbuf + (long)cid * CL * ROWS * H;
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+
+    float4 g4v[RT];
+    float cv[RT], pv[RT], doh[RT], doc[RT];
+    auto step_geometry = [&](int s, int& t, int& na, int& off_t, int& na_src, int& off_src) {
+        t = dir == 0 ? Tt - 1 - s : s;
+        na = active_rows(p.batch_sizes[t], tile, p.n_tiles);
+        off_t = p.offsets[t];
+        if (dir == 0) { na_src = t > 0 ? na : 0; off_src = t > 0 ? p.offsets[t - 1] : 0; }
+        else { na_src = (t + 1 < Tt) ? active_rows(p.batch_sizes[t + 1], tile, p.n_tiles) : 0; off_src = (t + 1 < Tt) ? p.offsets[t + 1] : 0; }
+    };
+    auto prefetch = [&](int s) {
+        int t, na, off_t, na_src, off_src;
+        step_geometry(s, t, na, off_t, na_src, off_src);
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            int r = prg + i * RG;
+            g4v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            cv[i] = pv[i] = doh[i] = doc[i] = 0.f;
+            if (r >= na) continue;
+            long b = tile + p.n_tiles * r;
+            long frame = off_t + b;
+            g4v[i] = __ldg(reinterpret_cast<const float4*>(gs + frame * (4 * H) + unit * 4));
+            const bool is_final = dir == 0 ? (t == len[i] - 1) : (t == 0);
+            const float* dout = p.d_out + b * p.out_ld;
+            if (CELL == 0) {
+                cv[i] = __ldg(cs + frame * H + unit);
+                if (r < na_src) pv[i] = __ldg(cs + ((long)off_src + b) * H + unit);
+                if (is_final) { doh[i] = __ldg(dout + dir * 2 * H + unit); doc[i] = __ldg(dout + dir * 2 * H + H + unit); }
+            } else {
+                if (r < na_src) pv[i] = __ldg(hs + ((long)off_src + b) * H + unit);
+                if (is_final) doh[i] = __ldg(dout + dir * H + unit);
+            }
+        }
+    };
+    if (Tt > 0) prefetch(0);
+
+    for (int s = 0; s < Tt; ++s) {
+        int t, na, off_t, na_src, off_src;
+        step_geometry(s, t, na, off_t, na_src, off_src);
+        (void)off_src;
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            int r = prg + i * RG;
+            if (r >= na) continue;
+            long b = tile + p.n_tiles * r;
+            long frame = off_t + b;
+            float dh = dh_reg[i];
+            float carry = dc_reg[i];
+            const float4 g4 = g4v[i];
+            float4 dgv;
+            if (CELL == 0) {
+                float dc = carry;
+                dh += doh[i]; dc += doc[i];
+                float c = cv[i];
+                float c_prev = pv[i];
+                float tc = tanhf(c);
+                float ig = g4.x, fg = g4.y, gg = g4.z, og = g4.w;
+                dc += dh * og * (1.f - tc * tc);
+                dgv.x = dc * gg * ig * (1.f - ig);
+                dgv.y = dc * c_prev * fg * (1.f - fg);
+                dgv.z = dc * ig * (1.f - gg * gg);
+                dgv.w = dh * tc * og * (1.f - og);
+                dc_reg[i] = dc * fg;
+            } else {
+                dh += carry + doh[i];
+                float h_prev = pv[i];
+                float rg_ = g4.x, zg = g4.y, ng = g4.z, hn = g4.w;
+                float dn_pre = dh * (1.f - zg) * (1.f - ng * ng);
+                dgv.x = dn_pre * hn * rg_ * (1.f - rg_);
+                dgv.y = dh * (h_prev - ng) * zg * (1.f - zg);
+                dgv.z = dn_pre;
+                dgv.w = dn_pre * rg_;
+                dc_reg[i] = dh * zg;
+            }
+            dh_reg[i] = 0.f;   // consumed; rows without a previous frame restart from zero
+            *reinterpret_cast<float4*>(dg + frame * (4 * H) + unit * 4) = dgv;
+            *reinterpret_cast<float4*>(Gsm + r * EB_GSP + ((pu ^ ((r >> 3) & 3)) << 2)) = dgv;
+            bsum.x += dgv.x; bsum.y += dgv.y; bsum.z += dgv.z; bsum.w += dgv.w;
+        }
+        __syncthreads();
+        if (s + 1 < Tt) prefetch(s + 1);
+        const long par = (long)(s & 1) * pb_stride;
+        if (na_src > 0) {
+            const int nq = (na_src + 3) >> 2;
+            const int n_mma = (na_src + 15) & ~15;
+            const uint32_t idesc_ts = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc_ss = idesc_ts | (1u << 15);
+            for (int half = 0; half < 2; ++half) {
+                if (half == 1) umma::mbar_wait(&bar, (bar_uses - 1) & 1);   // the MMAs of the first half have read the tiles
+                // re-lay gate rows [64 half, 64 half + 64) of the dG slice into [k][row] operand tiles (4x4 transposes)
+                for (int idx = tid; idx < (ROWS / 4) * (EB_HALF_K / 4); idx += NTHREADS) {
+                    const int q = idx % (ROWS / 4), kq = idx / (ROWS / 4);   // row quad, k quad within the half
+                    if (q >= nq) continue;
+                    const int pc = half * (EB_HALF_K / 4) + kq;            // 16-byte piece (= unit) within a Gsm row
+                    const int sw = (q >> 1) & 3;
+                    const float* rb = Gsm + (4 * q) * EB_GSP + ((pc ^ sw) << 2);
+                    const float4 r0 = *reinterpret_cast<const float4*>(rb);
+                    const float4 r1 = *reinterpret_cast<const float4*>(rb + EB_GSP);
+                    const float4 r2 = *reinterpret_cast<const float4*>(rb + 2 * EB_GSP);
+                    const float4 r3 = *reinterpret_cast<const float4*>(rb + 3 * EB_GSP);
+                    const uint32_t base = (uint32_t)((kq >> 3) * TS_B_BYTES);
+                    const int kl = (kq & 7) * 4;
+                    umma::split_store(b_hi, b_lo, base + umma::tile_off<TS_CHUNK>(kl + 0, q), make_float4(r0.x, r1.x, r2.x, r3.x));
+                    umma::split_store(b_hi, b_lo, base + umma::tile_off<TS_CHUNK>(kl + 1, q), make_float4(r0.y, r1.y, r2.y, r3.y));
+                    umma::split_store(b_hi, b_lo, base + umma::tile_off<TS_CHUNK>(kl + 2, q), make_float4(r0.z, r1.z, r2.z, r3.z));
+                    umma::split_store(b_hi, b_lo, base + umma::tile_off<TS_CHUNK>(kl + 3, q), make_float4(r0.w, r1.w, r2.w, r3.w));
+                }
+                umma::fence_proxy_async();
+                umma::fence_before_sync();
+                __syncthreads();
+                if (tid == 0) {
+                    umma::fence_after_sync();
+                    const uint32_t bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo), wl = umma::smem_u32(wlo);
+#pragma unroll 1
+                    for (int b = 0; b < 2; ++b) {
+#pragma unroll
+                        for (int sl = 0; sl < 2; ++sl) {
+#pragma unroll
+                            for (int kg = 0; kg < TS_SLAB / 8; ++kg) {
+                                const uint64_t dbh = umma::make_desc(bh + sl * TS_B_BYTES + kg * 1024, TS_CHUNK, 512);
+                                const uint64_t dbl = umma::make_desc(bl + sl * TS_B_BYTES + kg * 1024, TS_CHUNK, 512);
+                                const uint64_t dwl = umma::make_desc(wl + (half * 2 + sl) * ((H / 32) * TS_CHUNK) + b * 4 * TS_CHUNK + kg * 1024, TS_CHUNK, 512);
+                                const uint32_t ta = tmem + (uint32_t)(TS_A_COL + b * KG + half * EB_HALF_K + sl * TS_SLAB + kg * 8);
+                                const uint32_t td = tmem + (uint32_t)(b * EB_DCOLS);
+                                mma_tf32_ts(td, ta, dbh, idesc_ts, (half > 0 || sl > 0 || kg > 0) ? 1u : 0u);
+                                mma_tf32_ts(td, ta, dbl, idesc_ts, 1u);
+                                umma::mma_tf32(td, dwl, dbh, idesc_ss, 1u);
+                            }
+                        }
+                    }
+                    umma::commit(&bar);
+                }
+                bar_uses += 1;
+            }
+            umma::mbar_wait(&bar, (bar_uses - 1) & 1);
+            umma::fence_after_sync();
+            // accumulators D^T[unit][row] -> partial dh[row][unit] (global, reduced by the owners after the barrier)
+            {
+                const int b = warp >> 2, lq = warp & 3;
+                const int j = b * 128 + lq * 32 + lane;
+#pragma unroll 1
+                for (int r0 = 0; r0 < na_src; r0 += 16) {
+                    uint32_t r[16];
+                    umma::tmem_ld16(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * EB_DCOLS + r0), r);
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj)
+                        if (r0 + jj < na_src) Pmine[par + (long)(r0 + jj) * H + j] = __uint_as_float(r[jj]);
+                }
+            }
+            umma::fence_before_sync();
+        }
+        cluster_sync_all();
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            const int r = prg + i * RG;
+            if (r >= na_src) continue;
+            float v[CL];
+#pragma unroll
+            for (int src = 0; src < CL; ++src) v[src] = ld_cg(Pclu + par + ((long)src * ROWS + r) * H + unit);
+            float a = v[0];
+#pragma unroll
+            for (int src = 1; src < CL; ++src) a += v[src];
+            dh_reg[i] = a;
+        }
+    }
+    // bias gradients: fixed-order reduction over the row groups, one row of partial sums per tile
+    {
+        __syncthreads();
+        float4* red = reinterpret_cast<float4*>(Gsm);
+        red[prg * U + pu] = bsum;
+        __syncthreads();
+        if (tid < U) {
+            float4 a = red[tid];
+            for (int g = 1; g < NTHREADS / U; ++g) {
+                const float4 b = red[g * U + tid];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            *reinterpret_cast<float4*>(p.dbias[dir] + (long)tile * (4 * H) + (u0 + tid) * 4) = a;
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc<512>(tmem);
+}
+
 size_t enc_fwd_smem(bool tc) {
     if (tc) return ts_tiles_bytes() + ts_wlo_bytes(ABCD_H) + ts_raw_bytes();
     return (size_t)(ABCD_H * ENC_U * 4 + stage_floats(ENC_KC_FWD)) * sizeof(float);
@@ -496,6 +781,8 @@ int enc_init() {
     TRY(rnn_prepare_kernel((const void*)enc_fwd_kernel<1, false>, enc_fwd_smem(false)));
     TRY(rnn_prepare_kernel((const void*)enc_fwd_kernel<0, true>, enc_fwd_smem(true)));
     TRY(rnn_prepare_kernel((const void*)enc_fwd_kernel<1, true>, enc_fwd_smem(true)));
+    TRY(rnn_prepare_kernel((const void*)enc_bwd_ts_kernel<0>, enc_bwd_ts_smem()));
+    TRY(rnn_prepare_kernel((const void*)enc_bwd_ts_kernel<1>, enc_bwd_ts_smem()));
     TRY(rnn_prepare_kernel((const void*)enc_bwd_kernel<0>, enc_bwd_smem()));
     TRY(rnn_prepare_kernel((const void*)enc_bwd_kernel<1>, enc_bwd_smem()));
     return ABCD_OK;
@@ -632,8 +919,13 @@ int enc_backward(const EncParams& P, const EncGrads& G, const PackedMeta& pk, co
     }
     {
         ProfScope ps(PROF_ENC_BWD, stream);
-        if (P.cell == 0) TRY(launch_cluster(enc_bwd_kernel<0>, n_tiles * ndirs, enc_bwd_smem(), stream, k));
-        else TRY(launch_cluster(enc_bwd_kernel<1>, n_tiles * ndirs, enc_bwd_smem(), stream, k));
+        if (rnn_use_tc()) {
+            if (P.cell == 0) TRY(launch_cluster(enc_bwd_ts_kernel<0>, n_tiles * ndirs, enc_bwd_ts_smem(), stream, k));
+            else TRY(launch_cluster(enc_bwd_ts_kernel<1>, n_tiles * ndirs, enc_bwd_ts_smem(), stream, k));
+        } else {
+            if (P.cell == 0) TRY(launch_cluster(enc_bwd_kernel<0>, n_tiles * ndirs, enc_bwd_smem(), stream, k));
+            else TRY(launch_cluster(enc_bwd_kernel<1>, n_tiles * ndirs, enc_bwd_smem(), stream, k));
+        }
     }
 
     prev_index_kernel<<<min(pk.T_max, 592), 128, 0, stream>>>(pk.T_max, pk.batch_sizes, pk.offsets, w.prev_fwd, w.prev_bwd);
