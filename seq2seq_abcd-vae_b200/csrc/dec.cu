@@ -10,6 +10,7 @@
 // The offset predictor (model.py:191-195) does not feed the recurrence and runs as plain GEMMs over all
 // frames, as do all weight gradients.
 #include "rnn_common.cuh"
+#include "rnn_ts.cuh"
 #include "sgemm.cuh"
 #include "enc.cuh"
 
@@ -595,6 +596,459 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
     }
 }
 
+// geometry of the tensor-core backward kernel
+constexpr int DBT_M1 = 384;                                          // padded columns of the B1' result (3 blocks of 128)
+constexpr int DBT_DCOLS = 80;                                        // accumulator columns per block (N <= ROWS)
+constexpr int DBT_A1_COL = 256, DBT_A2_COL = 256 + 3 * 4 * U;        // tensor-memory columns of the resident weights
+constexpr int DBT_WLO1_BYTES = (4 * U / TS_SLAB) * (DBT_M1 / 32) * TS_CHUNK;   // 96 KB
+constexpr int DBT_WLO2_BYTES = (ABCD_H / 32) * TS_CHUNK;             // 32 KB (2U = 32 = one slab)
+static_assert(3 * DBT_DCOLS <= 256 && DBT_A2_COL + 2 * 2 * U <= 512, "tensor-memory budget");
+static_assert(2 * U == TS_SLAB && 4 * U == 2 * TS_SLAB, "slab geometry of the K-split products");
+
+// Tensor-core version (F <= 128): the two K-split products run transposed on tcgen05 with the weight rows resident in
+// tensor memory as the A operand (TS form, rnn_ts.cuh):
+//   B2'  D^T[H units, rows]        = W1^T[H, 2U]            * dHidPre^T[2U, rows]      (2 blocks of 128 lanes, K = 32)
+//   B1'  D^T[H + Fp columns, rows] = [W_hh | W_ih]^T[.., 4U] * dG^T[4U, rows]           (3 blocks, K = 64 in two halves)
+// Tensor memory: accumulators 3 x 80 columns, W_hi of B1' 3 x 64 columns, W_hi of B2' 2 x 32 columns (496 of 512).  The low
+// parts of the weights live in shared memory as MN-major tiles; the CTA's own dHidPre / dG slices are re-laid from shared
+// memory into hi/lo B-operand tiles (4x4 register transposes).  B3 stays a staged FFMA GEMM.
+template <int CELL, int KC>
+__global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_ts_kernel(DecK p) {
+    // (a distinct symbol: the alignment of an extern shared array is a property of the symbol, and `smem` is declared
+    // 16-byte aligned by the FFMA kernels of this file)
+    extern __shared__ __align__(1024) float smem_ts[];
+    float* const smem = smem_ts;
+    const int H = ABCD_H, M = ABCD_M;
+    const int F = p.F, Fp = p.Fp;
+    const int XC = xcols_per_cta(F);
+    const int N1 = H + Fp;                    // columns of the B1' partial: [dh_prev (H) | dx (Fp)]
+    constexpr int DSP = 2 * U + 4;            // pitch of the dHidPre slice in shared memory
+    constexpr int GSP = 4 * U + 4;            // pitch of the dG slice in shared memory
+    char* b_hi = reinterpret_cast<char*>(smem);                     // one 32-k slab of [k][rows] operand tiles
+    char* b_lo = b_hi + TS_B_BYTES;
+    char* wlo1 = b_lo + TS_B_BYTES;                                 // B1': [2 slabs][12 chunks (384 columns)][4 KB]
+    char* wlo2 = wlo1 + DBT_WLO1_BYTES;                             // B2': [1 slab][8 chunks (256 units)][4 KB]
+    float* WB3 = reinterpret_cast<float*>(wlo2 + DBT_WLO2_BYTES);   // [2Fp][2U]
+    float* dh_sm = WB3 + 2 * Fp * (2 * U);    // [ROWS][U]
+    float* dc_sm = dh_sm + ROWS * U;          // [ROWS][U]
+    const Stage st = make_stage(dc_sm + ROWS * U, KC);
+    float* Ds = st.buf0;                      // [ROWS][DSP]  (staging is idle outside B3), piece-swizzled
+    float* Gsm = st.buf0;                     // [ROWS][GSP]  (Ds is dead by then; may run into buf1), piece-swizzled
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x;
+    const int rank = (int)cluster_ctarank();
+    const int tile = blockIdx.x / CL;
+    const int u0 = rank * U;
+    const int xc0 = rank * XC;
+    const int xc1 = min(F, xc0 + XC);
+
+    for (int idx = tid; idx < 2 * Fp * 2 * U; idx += NTHREADS) {
+        int col = idx % (2 * U), k = idx / (2 * U);
+        int which = col / U, u = col % U;
+        int kk = which == 0 ? k : k - Fp;
+        float v = 0.f;
+        if (kk >= 0 && kk < F) v = p.em_w2[which][(long)kk * M + u0 + u];
+        WB3[idx] = v;
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+    if ((umma::smem_u32(smem) & 1023u) != 0) __trap();
+    if (warp == 0) umma::tmem_alloc<512>(&tmem_slot);
+    if (tid == 0) {
+        umma::mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    uint32_t bar_uses = 0;
+    {
+        // element (gate row kphys of this CTA, column j of [W_hh | W_ih]); columns >= H + F are zero
+        auto w1 = [&](int kphys, int j) -> float {
+            const int uu = u0 + (kphys >> 2), s = kphys & 3;
+            if (j < H) {
+                const int gate = CELL == 0 ? s : (s == 0 ? 0 : s == 1 ? 1 : s == 3 ? 2 : -1);
+                return gate >= 0 ? __ldg(p.w_hh + (long)(gate * H + uu) * H + j) : 0.f;
+            }
+            const int c = j - H;
+            const int gate = CELL == 0 ? s : (s == 3 ? -1 : s);
+            return (gate >= 0 && c < F) ? __ldg(p.w_ih + (long)(gate * H + uu) * F + c) : 0.f;
+        };
+        auto w2 = [&](int k, int j) -> float { return __ldg(p.em_w1[k / U] + (long)(u0 + k % U) * H + j); };
+        auto tmem_store16 = [&](uint32_t taddr, const uint32_t (&r)[16]) {
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                  "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+        };
+        const int lq = warp & 3;
+        // hi parts into tensor memory: lane = output column / unit within a 128-wide block
+        for (int b = warp >> 2; b < 3; b += 2) {
+            const int j = b * 128 + lq * 32 + lane;
+            for (int k0 = 0; k0 < 4 * U; k0 += 16) {
+                uint32_t r[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) r[q] = __float_as_uint(j < N1 ? w1(k0 + q, j) : 0.f);
+                tmem_store16(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(DBT_A1_COL + b * 4 * U + k0), r);
+            }
+        }
+        {
+            const int b = warp >> 2;
+            const int j = b * 128 + lq * 32 + lane;
+            for (int k0 = 0; k0 < 2 * U; k0 += 16) {
+                uint32_t r[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) r[q] = __float_as_uint(w2(k0 + q, j));
+                tmem_store16(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(DBT_A2_COL + b * 2 * U + k0), r);
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        // lo parts: MN-major tiles [k][column]
+        for (int idx = tid; idx < 4 * U * (DBT_M1 / 4); idx += NTHREADS) {
+            const int j4 = idx % (DBT_M1 / 4), k = idx / (DBT_M1 / 4);
+            float4 v;
+            v.x = 4 * j4 + 0 < N1 ? w1(k, 4 * j4 + 0) : 0.f; v.y = 4 * j4 + 1 < N1 ? w1(k, 4 * j4 + 1) : 0.f;
+            v.z = 4 * j4 + 2 < N1 ? w1(k, 4 * j4 + 2) : 0.f; v.w = 4 * j4 + 3 < N1 ? w1(k, 4 * j4 + 3) : 0.f;
+            *reinterpret_cast<float4*>(wlo1 + (size_t)(k / TS_SLAB) * (DBT_M1 / 32) * TS_CHUNK + umma::tile_off<TS_CHUNK>(k % TS_SLAB, j4)) = umma::lo_of(v);
+        }
+        for (int idx = tid; idx < 2 * U * (H / 4); idx += NTHREADS) {
+            const int j4 = idx % (H / 4), k = idx / (H / 4);
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.em_w1[k / U] + (long)(u0 + k % U) * H + j4 * 4));
+            *reinterpret_cast<float4*>(wlo2 + umma::tile_off<TS_CHUNK>(k, j4)) = umma::lo_of(v);
+        }
+        umma::fence_proxy_async();
+    }
+    for (int idx = tid; idx < ROWS * U; idx += NTHREADS) { dh_sm[idx] = 0.f; dc_sm[idx] = 0.f; }
+
+    const int KS3 = pick_ks_fit(2 * U / 4, 2 * U, KC);
+    const ThreadMap tm3 = make_map(tid, 2 * U / 4, KS3);
+    constexpr int PRG = NTHREADS / U;   // pointwise mapping: 16 row groups x 16 units, rows prg + i*PRG
+    constexpr int PR = ROWS / PRG;      // rows per pointwise thread
+    const int pu = tid % U, prg = tid / U;
+    const int unit = u0 + pu;
+
+    const int Tt = p.lengths[tile];
+    const int n_tiles = p.n_tiles, B = p.B;
+    const float* dML = p.dML;
+    float* Pb2 = p.Pb2 + (long)blockIdx.x * ROWS * H;
+    const float* Pb2t = p.Pb2 + (long)tile * CL * ROWS * H;
+    float* Pb1 = p.Pb1 + (long)blockIdx.x * ROWS * N1;
+    const float* Pb1t = p.Pb1 + (long)tile * CL * ROWS * N1;
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);   // this thread's share of sum(dG) over rows and steps
+    float4 hsum = make_float4(0.f, 0.f, 0.f, 0.f);   // ... and of sum(dHidPre) (bias gradients of the MLP input layers)
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+
+    for (int t = Tt - 1; t >= 0; --t) {
+        const int na = active_rows(p.batch_sizes[t], tile, n_tiles);
+        const long off_t = p.offsets[t];
+        const long prev_base = t == 0 ? 0 : (long)B + p.offsets[t - 1];
+
+        // saved forward activations for the gate-gradient step: fetched now, consumed after the first barrier
+        float4 g4v[PR];
+        float cv[PR], pv[PR], hov[PR];
+#pragma unroll
+        for (int i = 0; i < PR; ++i) {
+            int r = prg + i * PRG;
+            g4v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            cv[i] = pv[i] = hov[i] = 0.f;
+            if (r >= na) continue;
+            long b = tile + (long)n_tiles * r;
+            long frame = off_t + b;
+            long prow = prev_base + b;
+            g4v[i] = __ldg(reinterpret_cast<const float4*>(p.Gs + frame * (4 * H) + unit * 4));
+            hov[i] = __ldg(p.dHoff + frame * H + unit);
+            if (CELL == 0) {
+                cv[i] = __ldg(p.Call + ((long)B + frame) * H + unit);
+                pv[i] = __ldg(p.Call + prow * H + unit);
+            } else {
+                pv[i] = __ldg(p.Hall + prow * H + unit);
+            }
+        }
+
+        // ---- B3: gradient w.r.t. this CTA's MLP hidden pre-activations ----
+        {
+            float acc[RT][4];
+            zero_acc(acc);
+            auto rp = [=](int r) -> const float* { return dML + (off_t + tile + (long)n_tiles * r) * (2 * Fp); };
+            // tanh outputs of this thread's tile: fetched before the GEMM so the latency hides behind it
+            float4 hdv[RT];
+            if (tm3.active && tm3.ks == 0) {
+#pragma unroll
+                for (int i = 0; i < RT; ++i) {
+                    int r = tm3.rg + i * RG;
+                    hdv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r >= na) continue;
+                    long frame = off_t + tile + (long)n_tiles * r;
+                    int col = tm3.cg * 4;
+                    hdv[i] = __ldg(reinterpret_cast<const float4*>(p.Hid + frame * (2 * M) + (col / U) * M + u0 + col % U));
+                }
+            }
+            // the saved-activation loads above do not depend on other CTAs: they overlap the barrier that ended the
+            // previous step (whose dML updates feed the contraction below)
+            if (t < Tt - 1) cluster_wait_acquire();
+            phase_gemm<NTHREADS, KC, 2 * U>(acc, st, 2 * Fp, rp, 0, NullRow(), na, WB3, tm3, KS3, tid);
+            if (tm3.active && tm3.ks == 0) {
+#pragma unroll
+                for (int i = 0; i < RT; ++i) {
+                    int r = tm3.rg + i * RG;
+                    if (r >= na) continue;
+                    long frame = off_t + tile + (long)n_tiles * r;
+                    int col = tm3.cg * 4;
+                    int which = col / U, uu = col % U;
+                    long o = frame * (2 * M) + which * M + u0 + uu;
+                    float4 hd = hdv[i];
+                    float4 v = make_float4(acc[i][0] * (1.f - hd.x * hd.x), acc[i][1] * (1.f - hd.y * hd.y),
+                                           acc[i][2] * (1.f - hd.z * hd.z), acc[i][3] * (1.f - hd.w * hd.w));
+                    *reinterpret_cast<float4*>(p.dHidPre + o) = v;
+                    *reinterpret_cast<float4*>(Ds + r * DSP + ((((col >> 2) ^ ((r >> 3) & 3))) << 2)) = v;
+                    hsum.x += v.x; hsum.y += v.y; hsum.z += v.z; hsum.w += v.w;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- B2': partial dh over all H units from this CTA's hidden slice ----
+        const int nq = (na + 3) >> 2;
+        const int n_mma = (na + 15) & ~15;
+        const uint32_t idesc_ts = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_ss = idesc_ts | (1u << 15);
+        // re-lay `pieces` 16-byte pieces (4 k each) starting at piece `pc0` of the rows of `src` (pitch SP, piece-swizzled)
+        // into the [k][row] operand tiles
+        auto relayout = [&](const float* src, int SP, int pc0) {
+            for (int idx = tid; idx < (ROWS / 4) * (TS_SLAB / 4); idx += NTHREADS) {
+                const int q = idx % (ROWS / 4), kq = idx / (ROWS / 4);
+                if (q >= nq) continue;
+                const float* rb = src + (4 * q) * SP + (((pc0 + kq) ^ ((q >> 1) & 3)) << 2);
+                const float4 r0 = *reinterpret_cast<const float4*>(rb);
+                const float4 r1 = *reinterpret_cast<const float4*>(rb + SP);
+                const float4 r2 = *reinterpret_cast<const float4*>(rb + 2 * SP);
+                const float4 r3 = *reinterpret_cast<const float4*>(rb + 3 * SP);
+                umma::split_store(b_hi, b_lo, umma::tile_off<TS_CHUNK>(kq * 4 + 0, q), make_float4(r0.x, r1.x, r2.x, r3.x));
+                umma::split_store(b_hi, b_lo, umma::tile_off<TS_CHUNK>(kq * 4 + 1, q), make_float4(r0.y, r1.y, r2.y, r3.y));
+                umma::split_store(b_hi, b_lo, umma::tile_off<TS_CHUNK>(kq * 4 + 2, q), make_float4(r0.z, r1.z, r2.z, r3.z));
+                umma::split_store(b_hi, b_lo, umma::tile_off<TS_CHUNK>(kq * 4 + 3, q), make_float4(r0.w, r1.w, r2.w, r3.w));
+            }
+            umma::fence_proxy_async();
+            umma::fence_before_sync();
+            __syncthreads();
+        };
+        // accumulator blocks D^T[column][row] -> out[column][ROWS] (global partials stay transposed: every thread writes 64
+        // contiguous bytes per tcgen05.ld; the owners reduce them after the barrier)
+        auto push_blocks = [&](int nblk, int ncols, float* out) {
+            const int lq = warp & 3;
+            for (int b = warp >> 2; b < nblk; b += 2) {
+                const int j = b * 128 + lq * 32 + lane;
+#pragma unroll 1
+                for (int r0 = 0; r0 < na; r0 += 16) {
+                    uint32_t r[16];
+                    umma::tmem_ld16(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * DBT_DCOLS + r0), r);
+                    if (j < ncols) {
+                        float4* o = reinterpret_cast<float4*>(out + (long)j * ROWS + r0);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v)
+                            o[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                    }
+                }
+            }
+            umma::fence_before_sync();
+        };
+        // ---- B2' on the tensor cores: partial dh over all H units from this CTA's hidden slice (K = 2U = 32) ----
+        relayout(Ds, DSP, 0);
+        if (tid == 0) {
+            umma::fence_after_sync();
+            const uint32_t bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo), wl = umma::smem_u32(wlo2);
+#pragma unroll 1
+            for (int b = 0; b < 2; ++b) {
+#pragma unroll
+                for (int kg = 0; kg < TS_SLAB / 8; ++kg) {
+                    const uint64_t dbh = umma::make_desc(bh + kg * 1024, TS_CHUNK, 512);
+                    const uint64_t dbl = umma::make_desc(bl + kg * 1024, TS_CHUNK, 512);
+                    const uint64_t dwl = umma::make_desc(wl + b * 4 * TS_CHUNK + kg * 1024, TS_CHUNK, 512);
+                    const uint32_t ta = tmem + (uint32_t)(DBT_A2_COL + b * 2 * U + kg * 8);
+                    const uint32_t td = tmem + (uint32_t)(b * DBT_DCOLS);
+                    mma_tf32_ts(td, ta, dbh, idesc_ts, kg > 0 ? 1u : 0u);
+                    mma_tf32_ts(td, ta, dbl, idesc_ts, 1u);
+                    umma::mma_tf32(td, dwl, dbh, idesc_ss, 1u);
+                }
+            }
+            umma::commit(&bar);
+        }
+        bar_uses += 1;
+        umma::mbar_wait(&bar, (bar_uses - 1) & 1);
+        umma::fence_after_sync();
+        push_blocks(2, H, Pb2);
+        cluster_sync_all();
+
+        // ---- dh of this CTA's units = sum of the partials (+ carry), then the gate gradients ----
+        for (int idx = tid; idx < ((na + 3) >> 2) * U; idx += NTHREADS) {
+            const int rq = idx % ((na + 3) >> 2), j = idx / ((na + 3) >> 2);   // 4 rows of one unit: contiguous in the transposed partials
+            float4 v[CL];
+#pragma unroll
+            for (int src = 0; src < CL; ++src) v[src] = ld_cg4(Pb2t + ((long)src * H + u0 + j) * ROWS + 4 * rq);
+            float4 a = v[0];
+#pragma unroll
+            for (int src = 1; src < CL; ++src) { a.x += v[src].x; a.y += v[src].y; a.z += v[src].z; a.w += v[src].w; }
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (4 * rq + i < na) dh_sm[(4 * rq + i) * U + j] += av[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < PR; ++i) {
+            int r = prg + i * PRG;
+            if (r >= na) continue;
+            long frame = off_t + tile + (long)n_tiles * r;
+            float dh = dh_sm[r * U + pu] + hov[i];
+            float carry = dc_sm[r * U + pu];
+            const float4 g4 = g4v[i];
+            float4 dgv;
+            if (CELL == 0) {
+                float c = cv[i];
+                float c_prev = pv[i];
+                float tc = tanhf(c);
+                float ig = g4.x, fg = g4.y, gg = g4.z, og = g4.w;
+                float dc = carry + dh * og * (1.f - tc * tc);
+                dgv.x = dc * gg * ig * (1.f - ig);
+                dgv.y = dc * c_prev * fg * (1.f - fg);
+                dgv.z = dc * ig * (1.f - gg * gg);
+                dgv.w = dh * tc * og * (1.f - og);
+                dc_sm[r * U + pu] = dc * fg;
+            } else {
+                dh += carry;
+                float h_prev = pv[i];
+                float rg_ = g4.x, zg = g4.y, ng = g4.z, hn = g4.w;
+                float dn_pre = dh * (1.f - zg) * (1.f - ng * ng);
+                dgv.x = dn_pre * hn * rg_ * (1.f - rg_);
+                dgv.y = dh * (h_prev - ng) * zg * (1.f - zg);
+                dgv.z = dn_pre;
+                dgv.w = dn_pre * rg_;
+                dc_sm[r * U + pu] = dh * zg;
+            }
+            *reinterpret_cast<float4*>(p.dG + frame * (4 * H) + unit * 4) = dgv;
+            *reinterpret_cast<float4*>(Gsm + r * GSP + ((pu ^ ((r >> 3) & 3)) << 2)) = dgv;
+            bsum.x += dgv.x; bsum.y += dgv.y; bsum.z += dgv.z; bsum.w += dgv.w;
+        }
+        __syncthreads();
+
+        // ---- B1': partial [dh_{t-1} | dx_t] from this CTA's gate columns ----
+        // ---- B1' on the tensor cores: partial [dh_{t-1} | dx_t] from this CTA's gate columns (K = 4U = 64, two halves) ----
+        for (int half = 0; half < 2; ++half) {
+            if (half == 1) umma::mbar_wait(&bar, (bar_uses - 1) & 1);   // the MMAs of the first half have read the tiles
+            relayout(Gsm, GSP, half * (TS_SLAB / 4));
+            if (tid == 0) {
+                umma::fence_after_sync();
+                const uint32_t bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo), wl = umma::smem_u32(wlo1);
+#pragma unroll 1
+                for (int b = 0; b < 3; ++b) {
+#pragma unroll
+                    for (int kg = 0; kg < TS_SLAB / 8; ++kg) {
+                        const uint64_t dbh = umma::make_desc(bh + kg * 1024, TS_CHUNK, 512);
+                        const uint64_t dbl = umma::make_desc(bl + kg * 1024, TS_CHUNK, 512);
+                        const uint64_t dwl = umma::make_desc(wl + half * ((DBT_M1 / 32) * TS_CHUNK) + b * 4 * TS_CHUNK + kg * 1024, TS_CHUNK, 512);
+                        const uint32_t ta = tmem + (uint32_t)(DBT_A1_COL + b * 4 * U + half * TS_SLAB + kg * 8);
+                        const uint32_t td = tmem + (uint32_t)(b * DBT_DCOLS);
+                        mma_tf32_ts(td, ta, dbh, idesc_ts, (half > 0 || kg > 0) ? 1u : 0u);
+                        mma_tf32_ts(td, ta, dbl, idesc_ts, 1u);
+                        umma::mma_tf32(td, dwl, dbh, idesc_ss, 1u);
+                    }
+                }
+                umma::commit(&bar);
+            }
+            bar_uses += 1;
+        }
+        umma::mbar_wait(&bar, (bar_uses - 1) & 1);
+        umma::fence_after_sync();
+        push_blocks(3, N1, Pb1);
+        cluster_sync_all();
+
+        // ---- recurrent carry for this CTA's units, dx for its x columns (folded into dML of the previous frame) ----
+        // x columns first (longest dependency chain: partials + saved activations + read-modify-write), one column per
+        // thread; then the dh quads.  All loads of an item are issued before its first use.
+        if (t > 0) {
+            const long pbase = p.offsets[t - 1] + tile;
+            for (int idx = tid; idx < na * XC; idx += NTHREADS) {
+                const int r = idx % na, c = xc0 + idx / na;   // rows fastest: contiguous in the transposed partials
+                if (c >= xc1) continue;
+                const long pf = pbase + (long)n_tiles * r;   // frame that produced x_t
+                float v[CL];
+#pragma unroll
+                for (int src = 0; src < CL; ++src) v[src] = ld_cg(Pb1t + ((long)src * N1 + H + c) * ROWS + r);
+                const float lv = __ldg(p.Lv + pf * Fp + c);
+                const float e = __ldg(p.eps + pf * p.ld_eps + c);
+                float* dm = p.dML + pf * (2 * Fp) + c;
+                const float m0 = dm[0], m1 = dm[Fp];
+                float dx = v[0];
+#pragma unroll
+                for (int src = 1; src < CL; ++src) dx += v[src];
+                dm[0] = m0 + dx;
+                dm[Fp] = m1 + dx * 0.5f * expf(0.5f * lv) * e;
+            }
+        }
+        for (int idx = tid; idx < ((na + 3) >> 2) * U; idx += NTHREADS) {
+            const int rq = idx % ((na + 3) >> 2), j = idx / ((na + 3) >> 2);
+            float4 v[CL];
+#pragma unroll
+            for (int src = 0; src < CL; ++src) v[src] = ld_cg4(Pb1t + ((long)src * N1 + u0 + j) * ROWS + 4 * rq);
+            float4 a = v[0];
+#pragma unroll
+            for (int src = 1; src < CL; ++src) { a.x += v[src].x; a.y += v[src].y; a.z += v[src].z; a.w += v[src].w; }
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (4 * rq + i < na) dh_sm[(4 * rq + i) * U + j] = av[i];
+        }
+        cluster_arrive_release();   // matched by the wait after the next step's prefetch (or the one after the loop)
+    }
+    if (Tt > 0) cluster_wait_acquire();
+    // gradient w.r.t. the initial state produced by feature2hidden (h0 = even, c0 = odd columns; model.py:100)
+    for (int i = 0; i < PR; ++i) {
+        int r = prg + i * PRG;
+        long b = tile + (long)n_tiles * r;
+        if (b >= B || r >= ROWS) continue;
+        if (CELL == 0) {
+            p.dHC0[b * (2 * H) + 2 * unit] = dh_sm[r * U + pu];
+            p.dHC0[b * (2 * H) + 2 * unit + 1] = dc_sm[r * U + pu];
+        } else {
+            p.dHC0[b * H + unit] = dh_sm[r * U + pu] + dc_sm[r * U + pu];
+        }
+    }
+    // recurrent bias gradients: fixed-order reduction over the row groups, one row of partial sums per tile
+    {
+        __syncthreads();
+        float4* red = reinterpret_cast<float4*>(st.buf0);
+        red[prg * U + pu] = bsum;
+        __syncthreads();
+        if (tid < U) {
+            float4 a = red[tid];
+            for (int g = 1; g < PRG; ++g) {
+                const float4 b = red[g * U + tid];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            *reinterpret_cast<float4*>(p.dbias + (long)tile * (4 * H) + (u0 + tid) * 4) = a;
+        }
+        // MLP input-layer bias gradients: threads of the B3 epilogue hold sums for (4 columns, their row group)
+        __syncthreads();
+        if (tm3.active && tm3.ks == 0) red[tm3.rg * (2 * U / 4) + tm3.cg] = hsum;
+        __syncthreads();
+        if (tid < 2 * U / 4) {
+            float4 a = red[tid];
+            for (int g = 1; g < NRG; ++g) {
+                const float4 b = red[g * (2 * U / 4) + tid];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            const int col = tid * 4;   // column of this CTA's slice: [which][u0 + col % U]
+            *reinterpret_cast<float4*>(p.dbias1 + (long)tile * (2 * M) + (col / U) * M + u0 + col % U) = a;
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc<512>(tmem);
+}
+
 // -------------------------------------------------------------------------------------------------
 // helper kernels outside the time loop
 // -------------------------------------------------------------------------------------------------
@@ -708,6 +1162,18 @@ int dec_bwd_kc(int F) { return pick_kc(dec_bwd_fixed_floats(F)); }
 size_t dec_fwd_smem(int F) { return (dec_fwd_fixed_floats(F) + stage_floats(dec_fwd_kc(F))) * sizeof(float); }
 size_t dec_bwd_smem(int F) { return (dec_bwd_fixed_floats(F) + stage_floats(dec_bwd_kc(F))) * sizeof(float); }
 constexpr int DEC_MAX_F = 129;
+// tensor-core backward: [operand tiles | W_lo tiles | WB3 | dh/dc carries | B3 staging (also the dHidPre / dG slices)]
+size_t dec_bwd_ts_fixed_bytes(int F) {
+    const int Fp = pad4(F);
+    return (size_t)2 * TS_B_BYTES + DBT_WLO1_BYTES + DBT_WLO2_BYTES + (size_t)(2 * Fp * 2 * U + 2 * ROWS * U) * sizeof(float);
+}
+int dec_bwd_ts_kc(int F) {
+    for (int kc : {64, 32})
+        if (dec_bwd_ts_fixed_bytes(F) + stage_floats(kc) * sizeof(float) <= SMEM_MAX - 1024) return kc;
+    return 0;
+}
+bool dec_bwd_use_ts(int F) { return rnn_use_tc() && ABCD_H + pad4(F) <= DBT_M1 && dec_bwd_ts_kc(F) != 0; }
+size_t dec_bwd_ts_smem(int F) { return dec_bwd_ts_fixed_bytes(F) + stage_floats(dec_bwd_ts_kc(F)) * sizeof(float); }
 
 template <class K>
 int launch_cluster_dec(K kernel, int n_clusters, size_t smem, cudaStream_t stream, const DecK& params) {
@@ -820,6 +1286,10 @@ int dec_max_clusters(int which, int F, int* out) {
 }
 
 int dec_init() {
+    TRY(rnn_prepare_kernel((const void*)dec_bwd_ts_kernel<0, 64>, SMEM_MAX - 1024));   // the kernel also has static shared memory
+    TRY(rnn_prepare_kernel((const void*)dec_bwd_ts_kernel<1, 64>, SMEM_MAX - 1024));   // the kernel also has static shared memory
+    TRY(rnn_prepare_kernel((const void*)dec_bwd_ts_kernel<0, 32>, SMEM_MAX - 1024));   // the kernel also has static shared memory
+    TRY(rnn_prepare_kernel((const void*)dec_bwd_ts_kernel<1, 32>, SMEM_MAX - 1024));   // the kernel also has static shared memory
     TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0, 128>, SMEM_MAX));
     TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1, 128>, SMEM_MAX));
     TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<0, 128>, SMEM_MAX));
@@ -940,7 +1410,17 @@ int dec_backward(const DecParams& P, const DecGrads& G, const PackedMeta& pk, co
     {
         ProfScope ps(PROF_DEC_BWD, stream);
         const size_t sm = dec_bwd_smem(P.F);
-        if (k.kc == 128) {
+        if (dec_bwd_use_ts(P.F)) {
+            k.kc = dec_bwd_ts_kc(P.F);
+            const size_t smt = dec_bwd_ts_smem(P.F);
+            if (k.kc == 64) {
+                if (P.cell == 0) TRY(launch_cluster_dec(dec_bwd_ts_kernel<0, 64>, n_tiles, smt, stream, k));
+                else TRY(launch_cluster_dec(dec_bwd_ts_kernel<1, 64>, n_tiles, smt, stream, k));
+            } else {
+                if (P.cell == 0) TRY(launch_cluster_dec(dec_bwd_ts_kernel<0, 32>, n_tiles, smt, stream, k));
+                else TRY(launch_cluster_dec(dec_bwd_ts_kernel<1, 32>, n_tiles, smt, stream, k));
+            }
+        } else if (k.kc == 128) {
             if (P.cell == 0) TRY(launch_cluster_dec(dec_bwd_kernel<0, 128>, n_tiles, sm, stream, k));
             else TRY(launch_cluster_dec(dec_bwd_kernel<1, 128>, n_tiles, sm, stream, k));
         } else if (k.kc == 64) {

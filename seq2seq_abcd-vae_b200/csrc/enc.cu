@@ -713,11 +713,13 @@ size_t enc_fwd_smem(bool tc) {
     return (size_t)(ABCD_H * ENC_U * 4 + stage_floats(ENC_KC_FWD)) * sizeof(float);
 }
 // tensor-core recurrence (default); env ABCD_RNN_TC=0 or abcd_set_rnn_tensorcore(0) selects the FFMA path
-int g_rnn_tc = -1;
+}  // namespace
+static int g_rnn_tc = -1;
 bool rnn_use_tc() {
     if (g_rnn_tc < 0) { const char* e = getenv("ABCD_RNN_TC"); g_rnn_tc = (e && e[0] == '0') ? 0 : 1; }
     return g_rnn_tc == 1;
 }
+namespace {
 size_t enc_bwd_smem() { return (size_t)(4 * ENC_U * ABCD_H + 2 * ROWS * ENC_U + ROWS * (4 * ENC_U + 4)) * sizeof(float); }
 
 template <class K, class P>

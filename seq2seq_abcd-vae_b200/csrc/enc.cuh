@@ -26,6 +26,7 @@ int enc_backward(const EncParams& P, const EncGrads& G, const PackedMeta& pk, co
                  const float* d_last_hidden, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 int rnn_prepare_kernel(const void* fn, size_t smem);
+bool rnn_use_tc();   // tensor-core recurrences selected (default; env ABCD_RNN_TC=0 / abcd_set_rnn_tensorcore(0) -> FFMA)
 
 struct DecParams {
     int cell;           // 0 LSTM, 1 GRU
