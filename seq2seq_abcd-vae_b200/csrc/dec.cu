@@ -742,7 +742,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_ts_kernel(DecK p) {
     __syncthreads();
     umma::fence_after_sync();
 
+    const bool timing = p.timing && blockIdx.x == 0 && tid == 32;
+    unsigned long long tacc[16];
+    for (int i = 0; i < 16; ++i) tacc[i] = 0;
+#define DEC_TICK(slot) if (timing) { long long now_ = clock64(); tacc[slot] += now_ - tick_; tick_ = now_; }
     for (int t = Tt - 1; t >= 0; --t) {
+        long long tick_ = timing ? clock64() : 0;
         const int na = active_rows(p.batch_sizes[t], tile, n_tiles);
         const long off_t = p.offsets[t];
         const long prev_base = t == 0 ? 0 : (long)B + p.offsets[t - 1];
@@ -790,7 +795,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_ts_kernel(DecK p) {
             // the saved-activation loads above do not depend on other CTAs: they overlap the barrier that ended the
             // previous step (whose dML updates feed the contraction below)
             if (t < Tt - 1) cluster_wait_acquire();
+            DEC_TICK(0)
             phase_gemm<NTHREADS, KC, 2 * U>(acc, st, 2 * Fp, rp, 0, NullRow(), na, WB3, tm3, KS3, tid);
+            DEC_TICK(1)
             if (tm3.active && tm3.ks == 0) {
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
@@ -855,6 +862,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_ts_kernel(DecK p) {
             }
             umma::fence_before_sync();
         };
+        DEC_TICK(2)
         // ---- B2' on the tensor cores: partial dh over all H units from this CTA's hidden slice (K = 2U = 32) ----
         relayout(Ds, DSP, 0);
         if (tid == 0) {
@@ -880,7 +888,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_ts_kernel(DecK p) {
         umma::mbar_wait(&bar, (bar_uses - 1) & 1);
         umma::fence_after_sync();
         push_blocks(2, H, Pb2);
+        DEC_TICK(3)
         cluster_sync_all();
+        DEC_TICK(4)
 
         // ---- dh of this CTA's units = sum of the partials (+ carry), then the gate gradients ----
         for (int idx = tid; idx < ((na + 3) >> 2) * U; idx += NTHREADS) {
@@ -935,6 +945,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_ts_kernel(DecK p) {
         __syncthreads();
 
         // ---- B1': partial [dh_{t-1} | dx_t] from this CTA's gate columns ----
+        DEC_TICK(6)
         // ---- B1' on the tensor cores: partial [dh_{t-1} | dx_t] from this CTA's gate columns (K = 4U = 64, two halves) ----
         for (int half = 0; half < 2; ++half) {
             if (half == 1) umma::mbar_wait(&bar, (bar_uses - 1) & 1);   // the MMAs of the first half have read the tiles
@@ -963,7 +974,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_ts_kernel(DecK p) {
         umma::mbar_wait(&bar, (bar_uses - 1) & 1);
         umma::fence_after_sync();
         push_blocks(3, N1, Pb1);
+        DEC_TICK(7)
         cluster_sync_all();
+        DEC_TICK(8)
 
         // ---- recurrent carry for this CTA's units, dx for its x columns (folded into dML of the previous frame) ----
         // x columns first (longest dependency chain: partials + saved activations + read-modify-write), one column per
@@ -1001,9 +1014,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_ts_kernel(DecK p) {
             for (int i = 0; i < 4; ++i)
                 if (4 * rq + i < na) dh_sm[(4 * rq + i) * U + j] = av[i];
         }
+        DEC_TICK(9)
         cluster_arrive_release();   // matched by the wait after the next step's prefetch (or the one after the loop)
+        DEC_TICK(10)
     }
+#undef DEC_TICK
     if (Tt > 0) cluster_wait_acquire();
+    if (timing) { tacc[15] = Tt; for (int i = 0; i < 16; ++i) g_dec_timing[i] = tacc[i]; }
     // gradient w.r.t. the initial state produced by feature2hidden (h0 = even, c0 = odd columns; model.py:100)
     for (int i = 0; i < PR; ++i) {
         int r = prg + i * PRG;
