@@ -11,8 +11,8 @@
  *  - functions only enqueue work on `stream` (a cudaStream_t passed as void*); they never synchronise;
  *  - return 0 on success, a negative code otherwise; abcd_last_error() returns a thread-local message;
  *  - nothing throws across the ABI; re-entrant across streams/threads after abcd_init();
- *  - fp32 throughout: the recurrent kernels are IEEE fp32 FFMA, the GEMMs outside the time loops run on the tensor
- *    cores as 3xTF32 (hi/lo split, fp32 accumulation; <= 3e-6 + 1.5e-8*K relative to the largest output), special
+ *  - fp32 throughout: the recurrent contractions (weights resident in tensor memory) and the GEMMs outside the time loops
+ *    run on the tensor cores as 3xTF32; the decoder forward and the FFMA fallbacks are IEEE fp32 FFMA (hi/lo split, fp32 accumulation; <= 3e-6 + 1.5e-8*K relative to the largest output), special
  *    functions of the Dirichlet KL in fp64;
  *  - recurrent kernels are specialised for rnn_hidden_size = mlp_hidden_size = 256 and output_size <= 129;
  *    anything else is rejected with ABCD_ERR_UNSUPPORTED/ABCD_ERR_ARG -- there is no fallback path.
@@ -98,8 +98,8 @@ int abcd_debug_dec_timing(unsigned long long* out16);
 /* probe (tools/ts_probe.py): D[128,N] = A[128,K] B[K,N] with the A operand of tcgen05.mma read from tensor memory (TS form),
  * single-pass TF32; variant bit 0 selects the a_major bit of the instruction descriptor */
 int abcd_debug_ts_probe(const float* A, const float* B, float* D, int K, int N, int variant, void* stream);
-/* Encoder forward recurrence (model.py:60-66): per-step gate contraction on the tensor cores (tcgen05 kind::tf32, weights
- * resident in tensor memory, 3xTF32 split, fp32-grade; default) or on the FFMA path.  on = 1/0; -1 only queries.  Returns
+/* Recurrent contractions of the encoder forward / backward and the decoder backward (model.py:60-66, 165-196): on the tensor
+ * cores (tcgen05 kind::tf32, weights resident in tensor memory, 3xTF32 split, fp32-grade; default) or on the FFMA path.  on = 1/0; -1 only queries.  Returns
  * the previous setting.  Initial value: env ABCD_RNN_TC (default 1). */
 int abcd_set_rnn_tensorcore(int on);
 /* kernel launches enqueued by this library since load (what bench.py reports as gpu_launches) */
