@@ -12,8 +12,8 @@
  *  - return 0 on success, a negative code otherwise; abcd_last_error() returns a thread-local message;
  *  - nothing throws across the ABI; re-entrant across streams/threads after abcd_init();
  *  - fp32 throughout: the recurrent contractions (weights resident in tensor memory) and the GEMMs outside the time loops
- *    run on the tensor cores as 3xTF32; the decoder forward and the FFMA fallbacks are IEEE fp32 FFMA (hi/lo split, fp32 accumulation; <= 3e-6 + 1.5e-8*K relative to the largest output), special
- *    functions of the Dirichlet KL in fp64;
+ *    run on the tensor cores as 3xTF32 (hi/lo split, fp32 accumulation; <= 3e-6 + 1.5e-8*K relative to the largest
+ *    output); the decoder forward and the FFMA fallbacks are IEEE fp32 FFMA; special functions of the Dirichlet KL in fp64;
  *  - recurrent kernels are specialised for rnn_hidden_size = mlp_hidden_size = 256 and output_size <= 129;
  *    anything else is rejected with ABCD_ERR_UNSUPPORTED/ABCD_ERR_ARG -- there is no fallback path.
  *
