@@ -9,6 +9,7 @@
 //   bwd  B3 d(hidden pre-act) (K=2Fp)  B2' dh + gate gradients             B1' [dh_prev | dx]   (both K-split over the CTA's own slice)
 // The offset predictor (model.py:191-195) does not feed the recurrence and runs as plain GEMMs over all
 // frames, as do all weight gradients.
+#include <stdlib.h>
 #include "rnn_common.cuh"
 #include "rnn_ts.cuh"
 #include "sgemm.cuh"
@@ -52,19 +53,31 @@ struct DecK {
 // -------------------------------------------------------------------------------------------------
 __device__ unsigned long long g_dec_timing[16];
 
-template <int CELL, int KC>
+// TC = true: the gate contraction P1 runs on tcgen05 with [W_hh | W_ih]^T of this CTA's 64 gate columns resident in tensor
+// memory (TS form, M = 64; rnn_ts.cuh); shared memory is then
+// [activation tiles + raw staging ring (also the P2 staging buffers) | W_lo tiles | W1 | W2s | reduction scratch].
+template <int CELL, int KC, bool TC = false>
 __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(1024) float smem_fwd[];
+    float* const smem = smem_fwd;
     const int H = ABCD_H, M = ABCD_M;
     const int F = p.F, Fp = p.Fp;
     const int XC = xcols_per_cta(F);
     constexpr int HSP = 2 * U + 4;            // pitch of the CTA's own hidden-layer slice kept in shared memory
-    float* Wg = smem;                         // [H+Fp][U*4]: recurrent rows first, then the input rows
-    float* W1 = Wg + (Fp + H) * (U * 4);      // [H][2U]
+    const int ts_nsl = (H + Fp + TS_SLAB - 1) / TS_SLAB;               // K slabs of the gate contraction
+    // TC: [activation tiles (aliased by the P2 staging) | W_lo tiles | raw ring | W1 | W2s]; the operand tiles must stay
+    // 1024-byte aligned (the swizzle is a function of the absolute shared-memory address)
+    char* ts_wlo = reinterpret_cast<char*>(smem) + ts_tiles_bytes();
+    float* ts_raw = reinterpret_cast<float*>(ts_wlo + ts_wlo_bytes_m<U * 4>(H + Fp));
+    float* Wg = smem;                         // FFMA: [H+Fp][U*4]: recurrent rows first, then the input rows
+    float* W1 = TC ? ts_raw + ts_raw_bytes() / sizeof(float) : Wg + (Fp + H) * (U * 4);   // [H][2U]
     float* W2s = W1 + H * (2 * U);            // [U][2Fp]: rows of the output layers that multiply this CTA's hidden units
-    const Stage st = make_stage(W2s + U * 2 * Fp, KC);
-    float* red = W2s + U * 2 * Fp + stage_floats(KC);   // 40 floats
+    const Stage st = make_stage(TC ? smem : W2s + U * 2 * Fp, KC);
+    float* red = TC ? W2s + U * 2 * Fp : W2s + U * 2 * Fp + stage_floats(KC);   // 40 floats
     float* Hs = st.buf0;                      // [ROWS][HSP] (the staging buffers are idle between phases)
+    __shared__ uint64_t ts_bars[TS_STAGES + 1];
+    __shared__ uint32_t ts_tmem_slot;
+    TsCtx ts;
 
     const int tid = threadIdx.x;
     const int rank = (int)cluster_ctarank();
@@ -74,7 +87,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
     const int xc1 = min(F, xc0 + XC);
 
     // ---- resident weights ----
-    for (int idx = tid; idx < (Fp + H) * (U * 4); idx += NTHREADS) {
+    if (TC) {
+        static_assert(!TC || (size_t)2 * ROWS * (KC + 4) * sizeof(float) <= ts_tiles_bytes(), "P2 staging must fit in the activation tiles");
+        if ((umma::smem_u32(smem) & 1023u) != 0) __trap();
+        auto wval = [&](int col, int k) -> float {
+            const int u = col >> 2, s = col & 3;
+            if (k < H) {
+                const int gate = CELL == 0 ? s : (s == 0 ? 0 : s == 1 ? 1 : s == 3 ? 2 : -1);
+                return gate >= 0 ? __ldg(p.w_hh + (long)(gate * H + u0 + u) * H + k) : 0.f;
+            }
+            const int gate = CELL == 0 ? s : (s == 3 ? -1 : s);
+            return (gate >= 0 && k - H < F) ? __ldg(p.w_ih + (long)(gate * H + u0 + u) * F + (k - H)) : 0.f;
+        };
+        ts_init_m<U * 4>(ts, reinterpret_cast<char*>(smem), ts_wlo, ts_raw, ts_bars, &ts_tmem_slot, ts_nsl, wval, tid);
+    }
+    for (int idx = tid; !TC && idx < (Fp + H) * (U * 4); idx += NTHREADS) {
         int col = idx % (U * 4), k = idx / (U * 4);
         int u = col >> 2, s = col & 3;
         float v = 0.f;
@@ -160,7 +187,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
             DEC_TICK(0)
             // h_{t-1} has been visible since the first barrier of the previous step; x_t only after the barrier whose
             // arrive ended that step: the h part of the contraction overlaps that barrier
-            phase_gemm<NTHREADS, KC, U * 4>(acc, st, H, rph, Fp, rpx, na, Wg, tm1, KS1, tid, timing ? tacc + 10 : nullptr, t > 0 ? H / KC : -1);
+            if (TC) phase_gemm_ts2<U * 4>(acc, ts, H, rph, Fp, rpx, na, tm1, tid, t > 0 ? H / TS_SLAB : -1);
+            else phase_gemm<NTHREADS, KC, U * 4>(acc, st, H, rph, Fp, rpx, na, Wg, tm1, KS1, tid, timing ? tacc + 10 : nullptr, t > 0 ? H / KC : -1);
             DEC_TICK(1)
 #pragma unroll
             for (int i = 0; i < RT; ++i) {
@@ -290,6 +318,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
     if (timing) { tacc[15] = Tt; for (int i = 0; i < 16; ++i) g_dec_timing[i] = tacc[i]; }
     float tot = block_sum(nll, red);
     if (tid == 0) p.nll_partial[blockIdx.x] = tot;
+    if (TC) ts_fini(ts, tid);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1169,16 +1198,29 @@ size_t dec_bwd_fixed_floats(int F) {   // resident weights + dh/dc carries
     int Fp = pad4(F);
     return (size_t)(2 * Fp * 2 * U + 2 * U * ABCD_H + 4 * U * DEC_N1P + 2 * ROWS * U);
 }
-int pick_kc(size_t fixed_floats) {
+int pick_kc(size_t fixed_floats, size_t limit = SMEM_MAX) {
     for (int kc : {128, 64, 32})
-        if ((fixed_floats + stage_floats(kc)) * sizeof(float) <= SMEM_MAX) return kc;
+        if ((fixed_floats + stage_floats(kc)) * sizeof(float) <= limit) return kc;
     return 0;
 }
-int dec_fwd_kc(int F) { return pick_kc(dec_fwd_fixed_floats(F)); }
+int dec_fwd_kc(int F) { return pick_kc(dec_fwd_fixed_floats(F), SMEM_MAX - 1024); }   // the forward kernel also has static shared memory
 int dec_bwd_kc(int F) { return pick_kc(dec_bwd_fixed_floats(F)); }
 size_t dec_fwd_smem(int F) { return (dec_fwd_fixed_floats(F) + stage_floats(dec_fwd_kc(F))) * sizeof(float); }
 size_t dec_bwd_smem(int F) { return (dec_bwd_fixed_floats(F) + stage_floats(dec_bwd_kc(F))) * sizeof(float); }
 constexpr int DEC_MAX_F = 129;
+// tensor-core forward: [tiles + raw ring | W_lo | W1 | W2s | scratch]
+size_t dec_fwd_ts_smem(int F) {
+    const int Fp = pad4(F);
+    return ts_tiles_bytes() + ts_raw_bytes() + ts_wlo_bytes_m<U * 4>(ABCD_H + Fp) + (size_t)(ABCD_H * 2 * U + U * 2 * Fp + 64) * sizeof(float);
+}
+// The M = 64 tensor-core gate contraction of the forward kernel is parity-green but not yet faster than the FFMA phase
+// (1.68 vs 1.52 ms: eleven serial split -> barrier -> issue rounds per step): opt-in with ABCD_DEC_FWD_TC=1.
+bool dec_fwd_use_ts(int F) {
+    static int opt = -1;
+    if (opt < 0) { const char* e = getenv("ABCD_DEC_FWD_TC"); opt = (e && e[0] == '1') ? 1 : 0; }
+    const int nsl = (ABCD_H + pad4(F) + TS_SLAB - 1) / TS_SLAB;
+    return opt == 1 && rnn_use_tc() && TS_D_COLS_M + nsl * TS_SLAB <= 512 && dec_fwd_ts_smem(F) <= SMEM_MAX - 1024;
+}
 // tensor-core backward: [operand tiles | W_lo tiles | WB3 | dh/dc carries | B3 staging (also the dHidPre / dG slices)]
 size_t dec_bwd_ts_fixed_bytes(int F) {
     const int Fp = pad4(F);
@@ -1307,14 +1349,16 @@ int dec_init() {
     TRY(rnn_prepare_kernel((const void*)dec_bwd_ts_kernel<1, 64>, SMEM_MAX - 1024));   // the kernel also has static shared memory
     TRY(rnn_prepare_kernel((const void*)dec_bwd_ts_kernel<0, 32>, SMEM_MAX - 1024));   // the kernel also has static shared memory
     TRY(rnn_prepare_kernel((const void*)dec_bwd_ts_kernel<1, 32>, SMEM_MAX - 1024));   // the kernel also has static shared memory
-    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0, 128>, SMEM_MAX));
-    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1, 128>, SMEM_MAX));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0, 64, true>, SMEM_MAX - 1024));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1, 64, true>, SMEM_MAX - 1024));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0, 128>, SMEM_MAX - 1024));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1, 128>, SMEM_MAX - 1024));
     TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<0, 128>, SMEM_MAX));
     TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<1, 128>, SMEM_MAX));
-    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0, 64>, SMEM_MAX));
-    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1, 64>, SMEM_MAX));
-    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0, 32>, SMEM_MAX));
-    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1, 32>, SMEM_MAX));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0, 64>, SMEM_MAX - 1024));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1, 64>, SMEM_MAX - 1024));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0, 32>, SMEM_MAX - 1024));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1, 32>, SMEM_MAX - 1024));
     TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<0, 64>, SMEM_MAX));
     TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<1, 64>, SMEM_MAX));
     TRY(rnn_prepare_kernel((const void*)dec_bwd_kernel<0, 32>, SMEM_MAX));
@@ -1356,7 +1400,11 @@ int dec_forward(const DecParams& P, const PackedMeta& pk, const float* feat_in, 
     {
         ProfScope ps(PROF_DEC_FWD, stream);
         const size_t sm = dec_fwd_smem(P.F);
-        if (k.kc == 128) {
+        if (dec_fwd_use_ts(P.F)) {
+            k.kc = 64;
+            if (P.cell == 0) TRY(launch_cluster_dec(dec_fwd_kernel<0, 64, true>, n_tiles, dec_fwd_ts_smem(P.F), stream, k));
+            else TRY(launch_cluster_dec(dec_fwd_kernel<1, 64, true>, n_tiles, dec_fwd_ts_smem(P.F), stream, k));
+        } else if (k.kc == 128) {
             if (P.cell == 0) TRY(launch_cluster_dec(dec_fwd_kernel<0, 128>, n_tiles, sm, stream, k));
             else TRY(launch_cluster_dec(dec_fwd_kernel<1, 128>, n_tiles, sm, stream, k));
         } else if (k.kc == 64) {

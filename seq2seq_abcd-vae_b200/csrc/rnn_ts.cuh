@@ -33,6 +33,7 @@ constexpr int TS_RAW_PITCH = TS_SLAB + 4;                  // floats
 constexpr int TS_RAW_RING = 3;
 constexpr int TS_BOUNCE_PITCH = TS_M + 4;
 constexpr int TS_D_COL = 0, TS_A_COL = 256;                // tensor-memory columns: accumulator, weights
+constexpr int TS_D_COLS_M = 96;                            // two-source variant: accumulator in columns [0, 96), weights from 96
 constexpr int TS_WORKERS = NTHREADS - 32;                  // warp 0 only issues MMAs
 static_assert(ROWS % 16 == 0, "MMA N granularity");
 static_assert(ROWS * TS_BOUNCE_PITCH * 4 <= TS_STAGES * TS_STAGE_BYTES, "accumulator bounce must fit in the activation tiles");
@@ -247,6 +248,201 @@ __device__ __forceinline__ void phase_gemm_ts(float (&acc)[RT][4], TsCtx& c, RP 
         }
     }
     __syncthreads();   // bounce (= activation tiles) free for the next phase
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Two-source variant with M weight columns per CTA (M = 64 or 128): rows are the concatenation [rp0(r)[0,K0) | rp1(r)[0,K1)]
+// (K0 a multiple of TS_SLAB, K1 a multiple of 4; the tail of the last slab is zero-filled).  Used by the decoder forward
+// gate contraction, [h_{t-1} | x_t] * [W_hh | W_ih]^T.  `wait_slab` >= 1: a cluster arrive is pending and the matching wait
+// is executed just before the first slab >= wait_slab is staged (the rows of rp1 are produced by other CTAs).
+// ---------------------------------------------------------------------------------------------------------------
+template <int M>
+constexpr size_t ts_wlo_bytes_m(int Ktot) { return (size_t)((Ktot + TS_SLAB - 1) / TS_SLAB) * (M / 32) * TS_CHUNK; }
+
+// wval(col, k): weight of output column col (< M) at reduction index k (< nsl * TS_SLAB; zero beyond the real K).
+template <int M, class WVal>
+__device__ __forceinline__ void ts_init_m(TsCtx& c, char* tiles, char* wlo, float* raw, uint64_t* bars, uint32_t* tmem_slot,
+                                          int nsl, WVal wval, int tid) {
+    static_assert(M == 64 || M == 128, "tensor-memory block height");
+    c.tiles = tiles; c.wlo = wlo; c.raw = raw; c.bars = bars;
+#pragma unroll
+    for (int i = 0; i <= TS_STAGES; ++i) c.uses[i] = 0;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) umma::tmem_alloc<512>(tmem_slot);
+    if (tid == 0) {
+        for (int i = 0; i <= TS_STAGES; ++i) umma::mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    c.tmem = *tmem_slot;
+    const int Kp = nsl * TS_SLAB;
+    if (warp < 4) {
+        // M = 128: row (output column) m lives in lane m.  M = 64 (tools/ts_probe.py): row m lives in lane 32 (m / 16) + m % 16,
+        // for the A operand and for the accumulator alike; lanes 16..31 of every quadrant are unused (zero-filled here).
+        const int col = M == 128 ? warp * 32 + lane : (lane < 16 ? warp * 16 + lane : -1);
+        for (int k0 = 0; k0 < Kp; k0 += 16) {
+            uint32_t r[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) r[q] = __float_as_uint(col >= 0 ? wval(col, k0 + q) : 0.f);
+            const uint32_t taddr = c.tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(TS_D_COLS_M + k0);
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                  "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+    }
+    for (int idx = tid; idx < M * Kp; idx += NTHREADS) {
+        const int col = idx % M, k = idx / M;
+        const float w = wval(col, k);
+        const float lo = w - __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+        char* slab = wlo + (size_t)(k / TS_SLAB) * (M / 32) * TS_CHUNK;
+        *reinterpret_cast<float*>(slab + umma::tile_off<TS_CHUNK>(k % TS_SLAB, col >> 2) + (col & 3) * 4) = lo;
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+}
+
+template <int M, class RP0, class RP1>
+__device__ __forceinline__ void phase_gemm_ts2(float (&acc)[RT][4], TsCtx& c, int K0, RP0 rp0, int K1, RP1 rp1, int nrows,
+                                               const ThreadMap& tm, int tid, int wait_slab = -1) {
+    static_assert(NTHREADS == 256, "role mapping");
+    constexpr int RAW_ROUNDS = (ROWS * (TS_SLAB / 4) + TS_WORKERS - 1) / TS_WORKERS;
+    constexpr int BOUNCE_PITCH = M + 4;
+    const int nsl = (K0 + K1 + TS_SLAB - 1) / TS_SLAB;
+    const int warp = tid >> 5, wt = tid - 32;
+    const int nq = (nrows + 3) >> 2;
+    const int n_mma = (nrows + 15) & ~15;
+    const uint32_t idesc_ts = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    const uint32_t idesc_ss = idesc_ts | (1u << 15);
+
+    const float* src0[RAW_ROUNDS]; const float* src1[RAW_ROUNDS]; int dst[RAW_ROUNDS]; int piece[RAW_ROUNDS];
+#pragma unroll
+    for (int j = 0; j < RAW_ROUNDS; ++j) {
+        const int idx = wt + j * TS_WORKERS;
+        const int r = idx >> 3, pc = idx & 7;
+        dst[j] = -1; src0[j] = nullptr; src1[j] = nullptr; piece[j] = pc;
+        if (wt >= 0 && r < nrows && idx < ROWS * 8) { dst[j] = ts_raw_off(r, pc); src0[j] = rp0(r); src1[j] = rp1(r); }
+    }
+    auto stage_raw = [&](int s) {
+        if (s < nsl) {
+            float* slot = c.raw + (s % TS_RAW_RING) * (ROWS * TS_RAW_PITCH);
+#pragma unroll
+            for (int j = 0; j < RAW_ROUNDS; ++j) {
+                if (dst[j] < 0) continue;
+                const int k = s * TS_SLAB + piece[j] * 4;
+                const float* sp = nullptr;
+                if (k < K0) { if (src0[j]) sp = src0[j] + k; }
+                else if (k - K0 < K1) { if (src1[j]) sp = src1[j] + (k - K0); }
+                if (sp) cp_async16(slot + dst[j], sp);
+                else *reinterpret_cast<float4*>(slot + dst[j]) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        cp_async_commit();
+    };
+    const int q = wt % (ROWS / 4), kq = wt / (ROWS / 4);
+    const bool split_on = wt >= 0 && kq < TS_SLAB / 4 && q < nq;
+    uint32_t b_off[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b_off[j] = umma::tile_off<TS_CHUNK>((kq & 7) * 4 + j, q);
+
+    bool waited = wait_slab < 0;
+    for (int s = 0; s < TS_RAW_RING; ++s) {
+        if (!waited && s >= wait_slab) { cluster_wait_acquire(); waited = true; }
+        stage_raw(s);
+    }
+    cp_async_wait<TS_RAW_RING - 1>();
+    __syncthreads();
+
+    for (int s = 0; s < nsl; ++s) {
+        const int stg = s & 1;
+        char* b_hi = c.tiles + stg * TS_STAGE_BYTES;
+        char* b_lo = b_hi + TS_B_BYTES;
+        if (wt >= 0) {
+            if (c.uses[stg] > 0) umma::mbar_wait(&c.bars[stg], (c.uses[stg] - 1) & 1);
+            if (split_on) {
+                const float* rb = c.raw + (s % TS_RAW_RING) * (ROWS * TS_RAW_PITCH);
+                const float4 r0 = *reinterpret_cast<const float4*>(rb + ts_raw_off(4 * q + 0, kq & 7));
+                const float4 r1 = *reinterpret_cast<const float4*>(rb + ts_raw_off(4 * q + 1, kq & 7));
+                const float4 r2 = *reinterpret_cast<const float4*>(rb + ts_raw_off(4 * q + 2, kq & 7));
+                const float4 r3 = *reinterpret_cast<const float4*>(rb + ts_raw_off(4 * q + 3, kq & 7));
+                umma::split_store(b_hi, b_lo, b_off[0], make_float4(r0.x, r1.x, r2.x, r3.x));
+                umma::split_store(b_hi, b_lo, b_off[1], make_float4(r0.y, r1.y, r2.y, r3.y));
+                umma::split_store(b_hi, b_lo, b_off[2], make_float4(r0.z, r1.z, r2.z, r3.z));
+                umma::split_store(b_hi, b_lo, b_off[3], make_float4(r0.w, r1.w, r2.w, r3.w));
+            }
+            umma::fence_proxy_async();
+            cp_async_wait<TS_RAW_RING - 2>();
+        }
+        umma::fence_before_sync();
+        __syncthreads();
+        c.uses[stg] += 1;
+        if (tid == 0) {
+            umma::fence_after_sync();
+            const uint32_t bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo);
+            const uint32_t wl = umma::smem_u32(c.wlo + (size_t)s * (M / 32) * TS_CHUNK);
+#pragma unroll
+            for (int kg = 0; kg < TS_SLAB / 8; ++kg) {
+                const uint64_t dbh = umma::make_desc(bh + kg * 1024, TS_CHUNK, 512);
+                const uint64_t dbl = umma::make_desc(bl + kg * 1024, TS_CHUNK, 512);
+                const uint64_t dwl = umma::make_desc(wl + kg * 1024, TS_CHUNK, 512);
+                const uint32_t ta = c.tmem + (uint32_t)(TS_D_COLS_M + s * TS_SLAB + kg * 8);
+                mma_tf32_ts(c.tmem, ta, dbh, idesc_ts, (s > 0 || kg > 0) ? 1u : 0u);
+#ifndef TS2_SKIP2
+                mma_tf32_ts(c.tmem, ta, dbl, idesc_ts, 1u);
+#endif
+#ifndef TS2_SKIP3
+                umma::mma_tf32(c.tmem, dwl, dbh, idesc_ss, 1u);
+#endif
+            }
+            umma::commit(&c.bars[stg]);
+            if (s == nsl - 1) umma::commit(&c.bars[TS_STAGES]);
+        }
+        if (s + TS_RAW_RING < nsl && !waited && s + TS_RAW_RING >= wait_slab) { cluster_wait_acquire(); waited = true; }
+        if (wt >= 0) stage_raw(s + TS_RAW_RING);
+        else cp_async_commit();
+    }
+    if (!waited) cluster_wait_acquire();
+    cp_async_wait<0>();
+    c.uses[TS_STAGES] += 1;
+    umma::mbar_wait(&c.bars[TS_STAGES], (c.uses[TS_STAGES] - 1) & 1);
+    umma::fence_after_sync();
+
+    float* bounce = reinterpret_cast<float*>(c.tiles);
+    {
+        const int lane = tid & 31;
+        const int lq = warp & 3, half = warp >> 2;
+        const int col = M == 128 ? lq * 32 + lane : (lane < 16 ? lq * 16 + lane : -1);   // M = 64: 16 accumulator rows per lane quadrant
+        constexpr int HALF_ROWS = ((ROWS / 2 + 15) / 16) * 16;
+#pragma unroll 1
+        for (int r0 = half * HALF_ROWS; r0 < min(ROWS, (half + 1) * HALF_ROWS); r0 += 16) {
+            if (r0 >= nrows) break;
+            uint32_t r[16];
+            umma::tmem_ld16(c.tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)r0, r);
+            if (col >= 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (r0 + j < nrows) bounce[(r0 + j) * BOUNCE_PITCH + col] = __uint_as_float(r[j]);
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tm.active && tm.ks == 0) {
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            const int r = tm.rg + i * RG;
+            if (r < nrows) {
+                const float4 v = *reinterpret_cast<const float4*>(bounce + r * BOUNCE_PITCH + tm.cg * 4);
+                acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
+            }
+        }
+    }
+    __syncthreads();
 }
 
 }  // namespace rnn

@@ -22,3 +22,18 @@ for (K, N) in ((8, 16), (32, 64), (64, 96), (256, 80)):
 		except Exception as e:
 			print('K %3d N %3d a_major %d: FAILED %r' % (K, N, variant, e))
 			raise SystemExit(1)
+
+# M = 64: where do the 64 accumulator rows land in tensor memory, for two placements of the A rows?
+K, N = 32, 32
+A = torch.randn(128, K, device='cuda'); B = torch.randn(K, N, device='cuda')
+want = (A.double() @ B.double())
+for variant, what in ((2, 'TS, A rows 0..63 in lanes 0..63'), (6, 'TS, A row 16q+i in lane 32q+i (i<16)'), (10, 'SS, A rows 0..63 as MN-major smem tiles')):
+	D = torch.full((128, N), 7.0, device='cuda')
+	L.call('abcd_debug_ts_probe', L.ptr(A), L.ptr(B), L.ptr(D), K, N, variant, L.stream_ptr())
+	torch.cuda.synchronize()
+	Dd = D.double()
+	rows = []
+	for lane in range(128):
+		hit = [m for m in range(128) if float((Dd[lane] - want[m]).abs().max()) < 5e-3 * float(want.abs().max())]
+		rows.append(hit[0] if hit else -1)
+	print('M=64,', what, ': accumulator lane -> A row:', rows)
