@@ -635,16 +635,18 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_ts_kernel(EncBwdK p) {
                 __syncthreads();
                 if (tid == 0) {
                     umma::fence_after_sync();
-                    const uint32_t bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo), wl = umma::smem_u32(wlo);
+                    const uint64_t d_bh0 = umma::make_desc(umma::smem_u32(b_hi), TS_CHUNK, 512);
+                    const uint64_t d_bl0 = umma::make_desc(umma::smem_u32(b_lo), TS_CHUNK, 512);
+                    const uint64_t d_wl0 = umma::make_desc(umma::smem_u32(wlo), TS_CHUNK, 512);
 #pragma unroll 1
                     for (int b = 0; b < 2; ++b) {
 #pragma unroll
                         for (int sl = 0; sl < 2; ++sl) {
 #pragma unroll
                             for (int kg = 0; kg < TS_SLAB / 8; ++kg) {
-                                const uint64_t dbh = umma::make_desc(bh + sl * TS_B_BYTES + kg * 1024, TS_CHUNK, 512);
-                                const uint64_t dbl = umma::make_desc(bl + sl * TS_B_BYTES + kg * 1024, TS_CHUNK, 512);
-                                const uint64_t dwl = umma::make_desc(wl + (half * 2 + sl) * ((H / 32) * TS_CHUNK) + b * 4 * TS_CHUNK + kg * 1024, TS_CHUNK, 512);
+                                const uint64_t dbh = d_bh0 + (uint64_t)((sl * TS_B_BYTES + kg * 1024) >> 4);
+                                const uint64_t dbl = d_bl0 + (uint64_t)((sl * TS_B_BYTES + kg * 1024) >> 4);
+                                const uint64_t dwl = d_wl0 + (uint64_t)(((half * 2 + sl) * ((H / 32) * TS_CHUNK) + b * 4 * TS_CHUNK + kg * 1024) >> 4);
                                 const uint32_t ta = tmem + (uint32_t)(TS_A_COL + b * KG + half * EB_HALF_K + sl * TS_SLAB + kg * 8);
                                 const uint32_t td = tmem + (uint32_t)(b * EB_DCOLS);
                                 mma_tf32_ts(td, ta, dbh, idesc_ts, (half > 0 || sl > 0 || kg > 0) ? 1u : 0u);

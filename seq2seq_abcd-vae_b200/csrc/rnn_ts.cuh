@@ -167,6 +167,10 @@ __device__ __forceinline__ void phase_gemm_ts(float (&acc)[RT][4], TsCtx& c, RP 
     for (int j = 0; j < 4; ++j) b_off[j] = umma::tile_off<TS_CHUNK>((kq & 7) * 4 + j, q);
     const int raw0 = ts_raw_off(4 * q, kq & 7);
 
+    // descriptors of stage 0 / slab 0; the others differ by constant address offsets (>> 4) in the low 14 bits
+    const uint64_t d_bh0 = umma::make_desc(umma::smem_u32(c.tiles), TS_CHUNK, 512);
+    const uint64_t d_wl0 = umma::make_desc(umma::smem_u32(c.wlo), TS_CHUNK, 512);
+
     for (int s = 0; s < TS_RAW_RING; ++s) stage_raw(s);
     cp_async_wait<TS_RAW_RING - 1>();
     __syncthreads();                                       // raw slab 0 visible to all
@@ -196,13 +200,13 @@ __device__ __forceinline__ void phase_gemm_ts(float (&acc)[RT][4], TsCtx& c, RP 
         c.uses[stg] += 1;
         if (tid == 0) {
             umma::fence_after_sync();
-            const uint32_t bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo);
-            const uint32_t wl = umma::smem_u32(c.wlo + (size_t)s * (TS_M / 32) * TS_CHUNK);
+            const uint64_t sbh = d_bh0 + (uint64_t)((stg * TS_STAGE_BYTES) >> 4);
+            const uint64_t swl = d_wl0 + (uint64_t)((s * (TS_M / 32) * TS_CHUNK) >> 4);
 #pragma unroll
             for (int kg = 0; kg < TS_SLAB / 8; ++kg) {
-                const uint64_t dbh = umma::make_desc(bh + kg * 1024, TS_CHUNK, 512);
-                const uint64_t dbl = umma::make_desc(bl + kg * 1024, TS_CHUNK, 512);
-                const uint64_t dwl = umma::make_desc(wl + kg * 1024, TS_CHUNK, 512);
+                const uint64_t dbh = sbh + (uint64_t)((kg * 1024) >> 4);
+                const uint64_t dbl = dbh + (uint64_t)(TS_B_BYTES >> 4);
+                const uint64_t dwl = swl + (uint64_t)((kg * 1024) >> 4);
                 const uint32_t ta = c.tmem + (uint32_t)(TS_A_COL + s * TS_SLAB + kg * 8);
                 mma_tf32_ts(c.tmem + TS_D_COL, ta, dbh, idesc_ts, (s > 0 || kg > 0) ? 1u : 0u);
                 mma_tf32_ts(c.tmem + TS_D_COL, ta, dbl, idesc_ts, 1u);
@@ -350,6 +354,8 @@ __device__ __forceinline__ void phase_gemm_ts2(float (&acc)[RT][4], TsCtx& c, in
 #pragma unroll
     for (int j = 0; j < 4; ++j) b_off[j] = umma::tile_off<TS_CHUNK>((kq & 7) * 4 + j, q);
 
+    const uint64_t d_bh0 = umma::make_desc(umma::smem_u32(c.tiles), TS_CHUNK, 512);
+    const uint64_t d_wl0 = umma::make_desc(umma::smem_u32(c.wlo), TS_CHUNK, 512);
     bool waited = wait_slab < 0;
     for (int s = 0; s < TS_RAW_RING; ++s) {
         if (!waited && s >= wait_slab) { cluster_wait_acquire(); waited = true; }
@@ -383,13 +389,13 @@ __device__ __forceinline__ void phase_gemm_ts2(float (&acc)[RT][4], TsCtx& c, in
         c.uses[stg] += 1;
         if (tid == 0) {
             umma::fence_after_sync();
-            const uint32_t bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo);
-            const uint32_t wl = umma::smem_u32(c.wlo + (size_t)s * (M / 32) * TS_CHUNK);
+            const uint64_t sbh = d_bh0 + (uint64_t)((stg * TS_STAGE_BYTES) >> 4);
+            const uint64_t swl = d_wl0 + (uint64_t)((s * (M / 32) * TS_CHUNK) >> 4);
 #pragma unroll
             for (int kg = 0; kg < TS_SLAB / 8; ++kg) {
-                const uint64_t dbh = umma::make_desc(bh + kg * 1024, TS_CHUNK, 512);
-                const uint64_t dbl = umma::make_desc(bl + kg * 1024, TS_CHUNK, 512);
-                const uint64_t dwl = umma::make_desc(wl + kg * 1024, TS_CHUNK, 512);
+                const uint64_t dbh = sbh + (uint64_t)((kg * 1024) >> 4);
+                const uint64_t dbl = dbh + (uint64_t)(TS_B_BYTES >> 4);
+                const uint64_t dwl = swl + (uint64_t)((kg * 1024) >> 4);
                 const uint32_t ta = c.tmem + (uint32_t)(TS_D_COLS_M + s * TS_SLAB + kg * 8);
                 mma_tf32_ts(c.tmem, ta, dbh, idesc_ts, (s > 0 || kg > 0) ? 1u : 0u);
 #ifndef TS2_SKIP2
