@@ -922,9 +922,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_ts_kernel(DecK p) {
         DEC_TICK(4)
 
         // ---- dh of this CTA's units = sum of the partials (+ carry), then the gate gradients ----
-        for (int idx = tid; idx < (ROWS / 4) * U; idx += NTHREADS) {
-            const int rq = idx % (ROWS / 4), j = idx / (ROWS / 4);   // 4 rows of one unit: contiguous in the transposed partials
-            if (4 * rq >= na) continue;
+        for (int idx = tid; idx < ((na + 3) >> 2) * U; idx += NTHREADS) {
+            const int rq = idx % ((na + 3) >> 2), j = idx / ((na + 3) >> 2);   // 4 rows of one unit: contiguous in the transposed partials
             float4 v[CL];
 #pragma unroll
             for (int src = 0; src < CL; ++src) v[src] = ld_cg4(Pb2t + ((long)src * H + u0 + j) * ROWS + 4 * rq);
@@ -1013,9 +1012,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_ts_kernel(DecK p) {
         // thread; then the dh quads.  All loads of an item are issued before its first use.
         if (t > 0) {
             const long pbase = p.offsets[t - 1] + tile;
-            for (int idx = tid; idx < ROWS * XC; idx += NTHREADS) {
-                const int r = idx % ROWS, c = xc0 + idx / ROWS;   // rows fastest: contiguous in the transposed partials
-                if (r >= na || c >= xc1) continue;
+            for (int idx = tid; idx < na * XC; idx += NTHREADS) {
+                const int r = idx % na, c = xc0 + idx / na;   // rows fastest: contiguous in the transposed partials
+                if (c >= xc1) continue;
                 const long pf = pbase + (long)n_tiles * r;   // frame that produced x_t
                 float v[CL];
 #pragma unroll
@@ -1031,9 +1030,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_ts_kernel(DecK p) {
                 dm[Fp] = m1 + dx * 0.5f * expf(0.5f * lv) * e;
             }
         }
-        for (int idx = tid; idx < (ROWS / 4) * U; idx += NTHREADS) {
-            const int rq = idx % (ROWS / 4), j = idx / (ROWS / 4);
-            if (4 * rq >= na) continue;
+        for (int idx = tid; idx < ((na + 3) >> 2) * U; idx += NTHREADS) {
+            const int rq = idx % ((na + 3) >> 2), j = idx / ((na + 3) >> 2);
             float4 v[CL];
 #pragma unroll
             for (int src = 0; src < CL; ++src) v[src] = ld_cg4(Pb1t + ((long)src * N1 + u0 + j) * ROWS + 4 * rq);
