@@ -84,6 +84,7 @@ struct EncFwdK {
     float* gs[2];            // save: [sumT][4H] interleaved activations
     float* cs[2];            // save (LSTM): [sumT][H]
     float* out;              // [B][out_ld]
+    char* himg[2];           // tensor-core path: [clusters of the direction][2 parities] operand-tile images of h (rnn_ts.cuh)
 };
 
 // TC = true: the per-step gate contraction runs on the tensor cores with the recurrent weights resident in tensor
@@ -96,8 +97,11 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
     float* Wsm = smem;                                         // FFMA path: [H][U*4]
     const Stage st = make_stage(Wsm + ABCD_H * (U * 4), ENC_KC_FWD);
     __shared__ uint64_t ts_bars[TS_STAGES + 1];
+    __shared__ uint64_t tsi_bars[2 * TSI_STAGES + 1];
     __shared__ uint32_t ts_tmem_slot;
     TsCtx ts;
+    TsImgCtx tsi;
+    char* img[2] = {nullptr, nullptr};       // this cluster's two h images (written in step s, read in step s+1)
 
     const int tid = threadIdx.x;
     const int rank = (int)cluster_ctarank();
@@ -116,8 +120,21 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
             const int gate = CELL == 0 ? s : (s == 0 ? 0 : s == 1 ? 1 : s == 3 ? 2 : -1);
             return gate >= 0 ? W + (long)(gate * ABCD_H + u0 + u) * ABCD_H : nullptr;
         };
-        ts_init<ABCD_H>(ts, base, base + ts_tiles_bytes(), reinterpret_cast<float*>(base + ts_tiles_bytes() + ts_wlo_bytes(ABCD_H)),
-                        ts_bars, &ts_tmem_slot, wrow, tid);
+        char* wlo = base + (size_t)TSI_STAGES * TS_STAGE_BYTES;
+        ts_init<ABCD_H>(ts, base, wlo, nullptr, ts_bars, &ts_tmem_slot, wrow, tid);
+        ts_img_init_bars(tsi, base, wlo, tsi_bars, ts.tmem, tid);
+        // rows that join later (reverse direction) must read h_prev = 0: clear both images once
+        img[0] = p.himg[dir] + (size_t)(tile * 2) * ts_image_bytes(ABCD_H);
+        img[1] = img[0] + ts_image_bytes(ABCD_H);
+        {
+            float4* z = reinterpret_cast<float4*>(img[0]);
+            const size_t n16 = 2 * ts_image_bytes(ABCD_H) / 16;
+            for (size_t i = (size_t)rank * NTHREADS + tid; i < n16; i += (size_t)CL * NTHREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        ts_image_publish();
+        umma::fence_before_sync();
+        cluster_sync_all();
+        umma::fence_after_sync();
     } else {
         // resident recurrent weights: Wsm[k][u*4+slot] = W_hh[gate(slot)*H + u0+u][k]
         const float* W = p.w_hh[dir];
@@ -187,7 +204,7 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
                 long row = save ? (long)off_prev + b : (long)((s - 1) & 1) * B + b;
                 return hs + row * ABCD_H;
             };
-            if (TC) phase_gemm_ts<ABCD_H>(acc, ts, rp, na, tm, tid);
+            if (TC) phase_gemm_ts_img<ABCD_H>(acc, tsi, img[(s - 1) & 1], na, tm, tid);
             else phase_gemm<ENC_NT, ENC_KC_FWD, ENC_U * 4>(acc, st, H, rp, 0, NullRow(), na, Wsm, tm, 1, tid, timing ? pg : nullptr);
         }
         long long c2 = timing ? clock64() : 0;
@@ -222,6 +239,7 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
             hreg[i] = h;
             long row = p.save ? frame : (long)(s & 1) * p.B + b;
             hs[row * H + unit] = h;
+            if (TC) ts_image_store(img[s & 1], unit, r, h);
             const bool last = dir == 0 ? (t == len[i] - 1) : (t == 0);
             if (last) {
                 float* o = p.out + b * p.out_ld;
@@ -230,6 +248,7 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_fwd_kernel(EncFwdK p) {
             }
         }
         long long c3 = timing ? clock64() : 0;
+        if (TC) ts_image_publish();
         cluster_arrive_release();   // matched by the wait after the next step's input loads (or the one after the loop)
         if (timing) {
             long long c4 = clock64();
@@ -711,7 +730,7 @@ __global__ void __launch_bounds__(ENC_NT, 1) enc_bwd_ts_kernel(EncBwdK p) {
 }
 
 size_t enc_fwd_smem(bool tc) {
-    if (tc) return ts_tiles_bytes() + ts_wlo_bytes(ABCD_H) + ts_raw_bytes();
+    if (tc) return (size_t)TSI_STAGES * TS_STAGE_BYTES + ts_wlo_bytes(ABCD_H);
     return (size_t)(ABCD_H * ENC_U * 4 + stage_floats(ENC_KC_FWD)) * sizeof(float);
 }
 // tensor-core recurrence (default); env ABCD_RNN_TC=0 or abcd_set_rnn_tensorcore(0) selects the FFMA path
@@ -795,6 +814,7 @@ int enc_init() {
 // ---- workspace layout --------------------------------------------------------------------------
 struct EncWs {
     float* bias_comb[2];
+    char* himg[2];      // operand-tile images of h for the tensor-core forward kernel
     float* wih_pad[2];  // [4H][pad4(F)] interleaved, zero-padded copy of weight_ih
     float* xproj[2];
     float* hs[2];
@@ -819,6 +839,7 @@ static EncWs enc_carve(void* base, size_t cap, int cell, int F, int B, int sumT,
     for (int d = 0; d < ndirs; ++d) {
         w.bias_comb[d] = a.take<float>(4 * H);
         w.wih_pad[d] = a.take<float>((size_t)4 * H * ((F + 3) & ~3));
+        w.himg[d] = reinterpret_cast<char*>(a.take<float>((size_t)((B + ROWS - 1) / ROWS) * 2 * ts_image_bytes(H) / sizeof(float)));
         w.xproj[d] = a.take<float>((size_t)sumT * 4 * H);
         w.hs[d] = a.take<float>(save ? (size_t)sumT * H : (size_t)2 * B * H);
         if (save) {
@@ -884,7 +905,7 @@ int enc_forward(const EncParams& P, const PackedMeta& pk, const float* x, int ld
         g.bias = w.bias_comb[d];
         TRY(sgemm_launch(g, stream));
         k.w_hh[d] = P.w_hh[d]; k.b_hh[d] = P.b_hh[d];
-        k.xproj[d] = w.xproj[d]; k.hs[d] = w.hs[d]; k.gs[d] = w.gs[d]; k.cs[d] = w.cs[d];
+        k.xproj[d] = w.xproj[d]; k.hs[d] = w.hs[d]; k.gs[d] = w.gs[d]; k.cs[d] = w.cs[d]; k.himg[d] = w.himg[d];
     }
     (void)ngates;
     {

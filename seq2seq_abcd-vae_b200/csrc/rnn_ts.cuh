@@ -255,6 +255,135 @@ __device__ __forceinline__ void phase_gemm_ts(float (&acc)[RT][4], TsCtx& c, RP 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Image variant: the PRODUCERS of the activations write them (hi = raw fp32, lo = x - trunc_tf32(x)) straight in the
+// B-operand tile layout to a global "image" ([K/32 slabs][hi 12 KB | lo 12 KB], one image per cluster and step parity);
+// the consumer fetches whole 24 KB stages with two cp.async.bulk copies that complete on an mbarrier -- no staging ring, no
+// per-step split pass, no generic->async proxy fence in the loop.  One thread produces (copies), one thread issues MMAs.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TSI_STAGES = 4;
+constexpr size_t ts_image_bytes(int K) { return (size_t)(K / TS_SLAB) * TS_STAGE_BYTES; }   // one image (hi + lo of all slabs)
+
+// byte offset of activation element (k, row) inside an image, hi part (the lo part is TS_B_BYTES further)
+__device__ __forceinline__ size_t ts_image_off(int k, int row) {
+    return (size_t)(k / TS_SLAB) * TS_STAGE_BYTES + umma::tile_off<TS_CHUNK>(k % TS_SLAB, row >> 2) + (size_t)(row & 3) * 4;
+}
+__device__ __forceinline__ void ts_image_store(char* image, int k, int row, float v) {
+    char* p = image + ts_image_off(k, row);
+    *reinterpret_cast<float*>(p) = v;
+    *reinterpret_cast<float*>(p + TS_B_BYTES) = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+}
+// make this thread's image stores visible to the bulk-copy engine (async proxy) of other CTAs; call before the cluster arrive
+__device__ __forceinline__ void ts_image_publish() { asm volatile("fence.proxy.async.global;\n" ::: "memory"); }
+
+struct TsImgCtx {
+    char* tiles;          // TSI_STAGES stages of [h_hi | h_lo] (1024-byte aligned)
+    char* wlo;
+    uint64_t* full;       // [TSI_STAGES] bytes landed
+    uint64_t* empty;      // [TSI_STAGES] MMAs consumed the stage
+    uint64_t* done;       // phase done
+    uint32_t tmem;
+    uint32_t n_full[TSI_STAGES], n_empty[TSI_STAGES], n_done;   // completed phases (uniform bookkeeping)
+};
+__device__ __forceinline__ void ts_img_init_bars(TsImgCtx& c, char* tiles, char* wlo, uint64_t* bars, uint32_t tmem, int tid) {
+    c.tiles = tiles; c.wlo = wlo; c.full = bars; c.empty = bars + TSI_STAGES; c.done = bars + 2 * TSI_STAGES; c.tmem = tmem;
+#pragma unroll
+    for (int i = 0; i < TSI_STAGES; ++i) { c.n_full[i] = 0; c.n_empty[i] = 0; }
+    c.n_done = 0;
+    if (tid == 0) {
+        for (int i = 0; i < 2 * TSI_STAGES + 1; ++i) umma::mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+}
+
+// acc += act[rows, K] * W[K, my 128 gate columns]; the activations come from `image` (see above).
+template <int K>
+__device__ __forceinline__ void phase_gemm_ts_img(float (&acc)[RT][4], TsImgCtx& c, const char* image, int nrows,
+                                                  const ThreadMap& tm, int tid) {
+    constexpr int NSL = K / TS_SLAB;
+    const int warp = tid >> 5;
+    const int n_mma = (nrows + 15) & ~15;
+    const uint32_t idesc_ts = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(TS_M >> 4) << 24);
+    const uint32_t idesc_ss = idesc_ts | (1u << 15);
+    if (tid == 32) {
+        // ---- copy thread: two bulk copies per slab into the ring ----
+        for (int s = 0; s < NSL; ++s) {
+            const int stg = s % TSI_STAGES;
+            if (s >= TSI_STAGES) umma::mbar_wait(&c.empty[stg], (c.n_empty[stg] + (s / TSI_STAGES) - 1) & 1);
+            const uint32_t bar = umma::smem_u32(&c.full[stg]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"((uint32_t)TS_STAGE_BYTES) : "memory");
+            const uint32_t dst = umma::smem_u32(c.tiles + (size_t)stg * TS_STAGE_BYTES);
+            const char* src = image + (size_t)s * TS_STAGE_BYTES;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                         ::"r"(dst), "l"(src), "r"((uint32_t)TS_STAGE_BYTES), "r"(bar) : "memory");
+        }
+    } else if (tid == 0) {
+        // ---- MMA thread ----
+        const uint64_t d_bh0 = umma::make_desc(umma::smem_u32(c.tiles), TS_CHUNK, 512);
+        const uint64_t d_wl0 = umma::make_desc(umma::smem_u32(c.wlo), TS_CHUNK, 512);
+        for (int s = 0; s < NSL; ++s) {
+            const int stg = s % TSI_STAGES;
+            umma::mbar_wait(&c.full[stg], (c.n_full[stg] + s / TSI_STAGES) & 1);
+            umma::fence_after_sync();
+            const uint64_t sbh = d_bh0 + (uint64_t)((stg * TS_STAGE_BYTES) >> 4);
+            const uint64_t swl = d_wl0 + (uint64_t)((s * (TS_M / 32) * TS_CHUNK) >> 4);
+#pragma unroll
+            for (int kg = 0; kg < TS_SLAB / 8; ++kg) {
+                const uint64_t dbh = sbh + (uint64_t)((kg * 1024) >> 4);
+                const uint64_t dbl = dbh + (uint64_t)(TS_B_BYTES >> 4);
+                const uint64_t dwl = swl + (uint64_t)((kg * 1024) >> 4);
+                const uint32_t ta = c.tmem + (uint32_t)(TS_A_COL + s * TS_SLAB + kg * 8);
+                mma_tf32_ts(c.tmem + TS_D_COL, ta, dbh, idesc_ts, (s > 0 || kg > 0) ? 1u : 0u);
+                mma_tf32_ts(c.tmem + TS_D_COL, ta, dbl, idesc_ts, 1u);
+                umma::mma_tf32(c.tmem + TS_D_COL, dwl, dbh, idesc_ss, 1u);
+            }
+            umma::commit(&c.empty[stg]);
+            if (s == NSL - 1) umma::commit(c.done);
+        }
+    }
+    // uniform bookkeeping of the barrier phases this call went through
+#pragma unroll
+    for (int i = 0; i < TSI_STAGES; ++i) {
+        const uint32_t uses = (NSL - i + TSI_STAGES - 1) / TSI_STAGES;   // slabs that used stage i
+        c.n_full[i] += uses; c.n_empty[i] += uses;
+    }
+    umma::mbar_wait(c.done, c.n_done & 1);
+    c.n_done += 1;
+    umma::fence_after_sync();
+
+    float* bounce = reinterpret_cast<float*>(c.tiles);
+    {
+        const int lane = tid & 31;
+        const int lq = warp & 3, half = warp >> 2;
+        const int col = lq * 32 + lane;
+        constexpr int HALF_ROWS = ((ROWS / 2 + 15) / 16) * 16;
+#pragma unroll 1
+        for (int r0 = half * HALF_ROWS; r0 < min(ROWS, (half + 1) * HALF_ROWS); r0 += 16) {
+            if (r0 >= nrows) break;
+            uint32_t r[16];
+            umma::tmem_ld16(c.tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(TS_D_COL + r0), r);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (r0 + j < nrows) bounce[(r0 + j) * TS_BOUNCE_PITCH + col] = __uint_as_float(r[j]);
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tm.active && tm.ks == 0) {
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            const int r = tm.rg + i * RG;
+            if (r < nrows) {
+                const float4 v = *reinterpret_cast<const float4*>(bounce + r * TS_BOUNCE_PITCH + tm.cg * 4);
+                acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
+            }
+        }
+    }
+    // the bounce aliases the ring: the next phase's bulk copies (async proxy) must not overtake these generic reads
+    umma::fence_proxy_async();
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Two-source variant with M weight columns per CTA (M = 64 or 128): rows are the concatenation [rp0(r)[0,K0) | rp1(r)[0,K1)]
 // (K0 a multiple of TS_SLAB, K1 a multiple of 4; the tail of the last slab is zero-filled).  Used by the decoder forward
 // gate contraction, [h_{t-1} | x_t] * [W_hh | W_ih]^T.  `wait_slab` >= 1: a cluster arrive is pending and the matching wait
