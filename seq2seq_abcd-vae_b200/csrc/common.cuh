@@ -91,6 +91,10 @@ __device__ __forceinline__ void cluster_arrive_release() {
 __device__ __forceinline__ void cluster_wait_acquire() {
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
+// same, for code where the threads of a warp reach the wait at different points (no .aligned)
+__device__ __forceinline__ void cluster_wait_acquire_divergent() {
+    asm volatile("barrier.cluster.wait.acquire;\n" ::: "memory");
+}
 // Full cluster barrier with release/acquire semantics at cluster scope: global-memory writes made
 // by any thread of any CTA of the cluster before the barrier are visible to every thread after it.
 __device__ __forceinline__ void cluster_sync_all() {

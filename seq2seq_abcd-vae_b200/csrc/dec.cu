@@ -40,6 +40,7 @@ struct DecK {
     int timing;   // debug: per-phase clock cycles of CTA 0 -> g_dec_timing
     float* nll_partial;   // [gridDim.x]
     float* Pbuf;          // [n_tiles][CL][ROWS][2Fp] partial emission parameters exchanged inside a cluster
+    char* himg; char* ximg;   // tensor-core forward: per tile, 2 parities of operand-tile images of h (K = H) and x (K = Fp)
     // backward only
     float* dML; float* dHidPre; float* dG; const float* dHoff; float* dHC0;
     float* dbias;   // [n_tiles][4H]: per-tile column sums of dG (recurrent bias gradients), interleaved layout
@@ -67,17 +68,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
     const int ts_nsl = (H + Fp + TS_SLAB - 1) / TS_SLAB;               // K slabs of the gate contraction
     // TC: [activation tiles (aliased by the P2 staging) | W_lo tiles | raw ring | W1 | W2s]; the operand tiles must stay
     // 1024-byte aligned (the swizzle is a function of the absolute shared-memory address)
-    char* ts_wlo = reinterpret_cast<char*>(smem) + ts_tiles_bytes();
-    float* ts_raw = reinterpret_cast<float*>(ts_wlo + ts_wlo_bytes_m<U * 4>(H + Fp));
+    char* ts_wlo = reinterpret_cast<char*>(smem) + (size_t)TSI_STAGES * TS_STAGE_BYTES;
+    const int ts_nslx = (Fp + TS_SLAB - 1) / TS_SLAB;                  // slabs of the x image
     float* Wg = smem;                         // FFMA: [H+Fp][U*4]: recurrent rows first, then the input rows
-    float* W1 = TC ? ts_raw + ts_raw_bytes() / sizeof(float) : Wg + (Fp + H) * (U * 4);   // [H][2U]
+    float* W1 = TC ? reinterpret_cast<float*>(ts_wlo + ts_wlo_bytes_m<U * 4>(H + Fp)) : Wg + (Fp + H) * (U * 4);   // [H][2U]
     float* W2s = W1 + H * (2 * U);            // [U][2Fp]: rows of the output layers that multiply this CTA's hidden units
     const Stage st = make_stage(TC ? smem : W2s + U * 2 * Fp, KC);
     float* red = TC ? W2s + U * 2 * Fp : W2s + U * 2 * Fp + stage_floats(KC);   // 40 floats
     float* Hs = st.buf0;                      // [ROWS][HSP] (the staging buffers are idle between phases)
     __shared__ uint64_t ts_bars[TS_STAGES + 1];
+    __shared__ uint64_t tsi_bars[2 * TSI_STAGES + 1];
     __shared__ uint32_t ts_tmem_slot;
     TsCtx ts;
+    TsImgCtx tsi;
+    char* himg[2] = {nullptr, nullptr};
+    char* ximg[2] = {nullptr, nullptr};
 
     const int tid = threadIdx.x;
     const int rank = (int)cluster_ctarank();
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
 
     // ---- resident weights ----
     if (TC) {
-        static_assert(!TC || (size_t)2 * ROWS * (KC + 4) * sizeof(float) <= ts_tiles_bytes(), "P2 staging must fit in the activation tiles");
+        static_assert(!TC || (size_t)2 * ROWS * (KC + 4) * sizeof(float) <= (size_t)TSI_STAGES * TS_STAGE_BYTES, "P2 staging must fit in the activation tiles");
         if ((umma::smem_u32(smem) & 1023u) != 0) __trap();
         auto wval = [&](int col, int k) -> float {
             const int u = col >> 2, s = col & 3;
@@ -99,7 +104,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
             const int gate = CELL == 0 ? s : (s == 3 ? -1 : s);
             return (gate >= 0 && k - H < F) ? __ldg(p.w_ih + (long)(gate * H + u0 + u) * F + (k - H)) : 0.f;
         };
-        ts_init_m<U * 4>(ts, reinterpret_cast<char*>(smem), ts_wlo, ts_raw, ts_bars, &ts_tmem_slot, ts_nsl, wval, tid);
+        ts_init_m<U * 4>(ts, reinterpret_cast<char*>(smem), ts_wlo, nullptr, ts_bars, &ts_tmem_slot, ts_nsl, wval, tid);
+        ts_img_init_bars(tsi, reinterpret_cast<char*>(smem), ts_wlo, tsi_bars, ts.tmem, tid);
+        himg[0] = p.himg + (size_t)(tile * 2) * ts_image_bytes(ABCD_H); himg[1] = himg[0] + ts_image_bytes(ABCD_H);
+        ximg[0] = p.ximg + (size_t)(tile * 2) * ts_nslx * TS_STAGE_BYTES; ximg[1] = ximg[0] + (size_t)ts_nslx * TS_STAGE_BYTES;
+        // clear the images once (padding k >= F of the x image must be zero; stale rows must at least be finite)
+        {
+            float4* z = reinterpret_cast<float4*>(himg[0]);
+            const size_t n16 = 2 * ts_image_bytes(ABCD_H) / 16;
+            for (size_t i = (size_t)rank * NTHREADS + tid; i < n16; i += (size_t)CL * NTHREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4* zx = reinterpret_cast<float4*>(ximg[0]);
+            const size_t nx16 = (size_t)2 * ts_nslx * TS_STAGE_BYTES / 16;
+            for (size_t i = (size_t)rank * NTHREADS + tid; i < nx16; i += (size_t)CL * NTHREADS) zx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        ts_image_publish();
+        cluster_sync_all();
     }
     for (int idx = tid; !TC && idx < (Fp + H) * (U * 4); idx += NTHREADS) {
         int col = idx % (U * 4), k = idx / (U * 4);
@@ -166,6 +185,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
     float nll = 0.f;
     const int n_tiles = p.n_tiles, B = p.B;
     const float* Hall = p.Hall; const float* Xall = p.Xall;
+    if (TC) {
+        // images of the initial state (read by step 0 with parity (0 - 1) & 1 = 1)
+        if (tm1.ks == 0) {
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+                const int r = tm1.rg + i * RG;
+                if (tile + p.n_tiles * r < p.B) ts_image_store(himg[1], unit, r, hreg[i]);
+            }
+        }
+        for (int o = tid; o < ROWS * XC; o += NTHREADS) {
+            const int r = o / XC, c = xc0 + o % XC;
+            const long b = tile + (long)n_tiles * r;
+            if (c < xc1 && b < B) ts_image_store(ximg[1], c, r, Xall[b * Fp + c]);
+        }
+        ts_image_publish();
+        cluster_sync_all();
+    }
     __syncthreads();
     const bool timing = p.timing && blockIdx.x == 0 && tid == 0;
     unsigned long long tacc[16];
@@ -187,7 +223,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
             DEC_TICK(0)
             // h_{t-1} has been visible since the first barrier of the previous step; x_t only after the barrier whose
             // arrive ended that step: the h part of the contraction overlaps that barrier
-            if (TC) phase_gemm_ts2<U * 4>(acc, ts, H, rph, Fp, rpx, na, tm1, tid, t > 0 ? H / TS_SLAB : -1);
+            if (TC) phase_gemm_ts_img2<U * 4>(acc, tsi, himg[(t - 1) & 1], H / TS_SLAB, ximg[(t - 1) & 1], ts_nslx, na, tm1, tid, t > 0);
             else phase_gemm<NTHREADS, KC, U * 4>(acc, st, H, rph, Fp, rpx, na, Wg, tm1, KS1, tid, timing ? tacc + 10 : nullptr, t > 0 ? H / KC : -1);
             DEC_TICK(1)
 #pragma unroll
@@ -216,8 +252,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
                 }
                 hreg[i] = h;
                 p.Hall[((long)B + frame) * H + unit] = h;
+                if (TC) ts_image_store(himg[t & 1], unit, r, h);
             }
         }
+        if (TC) ts_image_publish();
         DEC_TICK(2)
         cluster_sync_all();
         DEC_TICK(3)
@@ -303,12 +341,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
             p.Mean[frame * Fp + c] = mean;
             p.Lv[frame * Fp + c] = lv;
             p.Xall[((long)B + frame) * Fp + c] = x;
+            if (TC) ts_image_store(ximg[t & 1], c, r, x);
             if (p.gt) {
                 const float d = g - mean;
                 nll += 0.5f * (LOG_2PI + lv + d * expf(-lv) * d);
             }
         }
         DEC_TICK(7)
+        if (TC) ts_image_publish();
         DEC_TICK(8)
         cluster_arrive_release();   // matched by the wait inside the next step's P1 (or the one after the loop)
         DEC_TICK(9)
@@ -1211,7 +1251,7 @@ constexpr int DEC_MAX_F = 129;
 // tensor-core forward: [tiles + raw ring | W_lo | W1 | W2s | scratch]
 size_t dec_fwd_ts_smem(int F) {
     const int Fp = pad4(F);
-    return ts_tiles_bytes() + ts_raw_bytes() + ts_wlo_bytes_m<U * 4>(ABCD_H + Fp) + (size_t)(ABCD_H * 2 * U + U * 2 * Fp + 64) * sizeof(float);
+    return (size_t)TSI_STAGES * TS_STAGE_BYTES + ts_wlo_bytes_m<U * 4>(ABCD_H + Fp) + (size_t)(ABCD_H * 2 * U + U * 2 * Fp + 64) * sizeof(float);
 }
 // The M = 64 tensor-core gate contraction of the forward kernel is parity-green but not yet faster than the FFMA phase
 // (1.68 vs 1.52 ms: eleven serial split -> barrier -> issue rounds per step): opt-in with ABCD_DEC_FWD_TC=1.
@@ -1253,6 +1293,7 @@ int launch_cluster_dec(K kernel, int n_clusters, size_t smem, cudaStream_t strea
 
 struct DecWs {
     float *hc0, *Hall, *Call, *Xall, *Gs, *Hid, *Mean, *Lv, *HidOff, *OffLogit, *nll_partial, *bce_partial, *Pbuf;
+    char *himg, *ximg;
     float *dML, *dHidPre, *dG, *dHoff, *dHidOffPre, *dLogit, *dHC0, *dbias, *dbias1, *Pb2, *Pb1, *partials;
     int* prev;
     size_t partial_floats;
@@ -1280,6 +1321,8 @@ DecWs dec_carve(void* base, size_t cap, int cell, int F, int fin, int B, int sum
     w.nll_partial = a.take<float>((size_t)n_tiles * CL);
     w.bce_partial = a.take<float>(BCE_BLOCKS);
     w.Pbuf = a.take<float>((size_t)n_tiles * CL * ROWS * 2 * Fp);
+    w.himg = reinterpret_cast<char*>(a.take<float>((size_t)n_tiles * 2 * ts_image_bytes(H) / sizeof(float)));
+    w.ximg = reinterpret_cast<char*>(a.take<float>((size_t)n_tiles * 2 * ((Fp + TS_SLAB - 1) / TS_SLAB) * TS_STAGE_BYTES / sizeof(float)));
     w.dML = a.take<float>((size_t)sumT * 2 * Fp);
     w.dHidPre = a.take<float>((size_t)sumT * 2 * M);
     w.dG = a.take<float>((size_t)sumT * 4 * H);
@@ -1316,7 +1359,7 @@ DecK make_k(const DecParams& P, const PackedMeta& pk, const DecWs& w) {
     k.w_ih = P.w_ih; k.w_hh = P.w_hh; k.b_ih = P.b_ih; k.b_hh = P.b_hh;
     for (int i = 0; i < 2; ++i) { k.em_w1[i] = P.em_w1[i]; k.em_b1[i] = P.em_b1[i]; k.em_w2[i] = P.em_w2[i]; k.em_b2[i] = P.em_b2[i]; }
     k.Hall = w.Hall; k.Call = w.Call; k.Xall = w.Xall; k.Gs = w.Gs; k.Hid = w.Hid; k.Mean = w.Mean; k.Lv = w.Lv;
-    k.nll_partial = w.nll_partial; k.Pbuf = w.Pbuf;
+    k.nll_partial = w.nll_partial; k.Pbuf = w.Pbuf; k.himg = w.himg; k.ximg = w.ximg;
     k.timing = getenv("ABCD_TIMING") != nullptr;
     k.dML = w.dML; k.dHidPre = w.dHidPre; k.dG = w.dG; k.dHoff = w.dHoff; k.dHC0 = w.dHC0; k.dbias = w.dbias; k.dbias1 = w.dbias1; k.Pb2 = w.Pb2; k.Pb1 = w.Pb1;
     return k;

@@ -304,17 +304,21 @@ __device__ __forceinline__ void phase_gemm_ts_img(float (&acc)[RT][4], TsImgCtx&
     const int n_mma = (nrows + 15) & ~15;
     const uint32_t idesc_ts = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(TS_M >> 4) << 24);
     const uint32_t idesc_ss = idesc_ts | (1u << 15);
+    const uint32_t cbytes = (uint32_t)((n_mma + 31) / 32) * TS_CHUNK;   // bytes of the row chunks the MMAs read (per hi / lo tile)
     if (tid == 32) {
         // ---- copy thread: two bulk copies per slab into the ring ----
         for (int s = 0; s < NSL; ++s) {
             const int stg = s % TSI_STAGES;
             if (s >= TSI_STAGES) umma::mbar_wait(&c.empty[stg], (c.n_empty[stg] + (s / TSI_STAGES) - 1) & 1);
             const uint32_t bar = umma::smem_u32(&c.full[stg]);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"((uint32_t)TS_STAGE_BYTES) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(2u * cbytes) : "memory");
             const uint32_t dst = umma::smem_u32(c.tiles + (size_t)stg * TS_STAGE_BYTES);
             const char* src = image + (size_t)s * TS_STAGE_BYTES;
+            // only the 32-row chunks that hold active rows: hi part, then lo part
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                         ::"r"(dst), "l"(src), "r"((uint32_t)TS_STAGE_BYTES), "r"(bar) : "memory");
+                         ::"r"(dst), "l"(src), "r"(cbytes), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                         ::"r"(dst + (uint32_t)TS_B_BYTES), "l"(src + TS_B_BYTES), "r"(cbytes), "r"(bar) : "memory");
         }
     } else if (tid == 0) {
         // ---- MMA thread ----
@@ -379,6 +383,107 @@ __device__ __forceinline__ void phase_gemm_ts_img(float (&acc)[RT][4], TsImgCtx&
         }
     }
     // the bounce aliases the ring: the next phase's bulk copies (async proxy) must not overtake these generic reads
+    umma::fence_proxy_async();
+    __syncthreads();
+}
+
+// Two-image variant with M weight columns (decoder forward): slabs [0, nsl0) come from `image0` (h_{t-1}), slabs
+// [nsl0, nsl0 + nsl1) from `image1` (x_t).  `wait_cluster`: a cluster arrive is pending and image1 is only valid after the
+// matching wait; every thread executes that wait, the copy and MMA threads after their first TSI_STAGES slabs so that the
+// image0 part of the contraction overlaps the barrier.  Requires nsl0 >= TSI_STAGES.
+template <int M>
+__device__ __forceinline__ void phase_gemm_ts_img2(float (&acc)[RT][4], TsImgCtx& c, const char* image0, int nsl0,
+                                                   const char* image1, int nsl1, int nrows, const ThreadMap& tm, int tid,
+                                                   bool wait_cluster) {
+    constexpr int BOUNCE_PITCH = M + 4;
+    const int nsl = nsl0 + nsl1;
+    const int warp = tid >> 5;
+    // the ring may have been used through the generic proxy since the last call (staging buffers of other phases alias it)
+    umma::fence_proxy_async();
+    __syncthreads();
+    const int n_mma = (nrows + 15) & ~15;
+    const uint32_t idesc_ts = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    const uint32_t idesc_ss = idesc_ts | (1u << 15);
+    const uint32_t cbytes = (uint32_t)((n_mma + 31) / 32) * TS_CHUNK;
+    if (tid == 32) {
+        for (int s = 0; s < nsl; ++s) {
+            if (s == TSI_STAGES && wait_cluster) cluster_wait_acquire_divergent();
+            const int stg = s % TSI_STAGES;
+            if (s >= TSI_STAGES) umma::mbar_wait(&c.empty[stg], (c.n_empty[stg] + (s / TSI_STAGES) - 1) & 1);
+            const uint32_t bar = umma::smem_u32(&c.full[stg]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(2u * cbytes) : "memory");
+            const uint32_t dst = umma::smem_u32(c.tiles + (size_t)stg * TS_STAGE_BYTES);
+            const char* src = s < nsl0 ? image0 + (size_t)s * TS_STAGE_BYTES : image1 + (size_t)(s - nsl0) * TS_STAGE_BYTES;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                         ::"r"(dst), "l"(src), "r"(cbytes), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                         ::"r"(dst + (uint32_t)TS_B_BYTES), "l"(src + TS_B_BYTES), "r"(cbytes), "r"(bar) : "memory");
+        }
+    } else if (tid == 0) {
+        const uint64_t d_bh0 = umma::make_desc(umma::smem_u32(c.tiles), TS_CHUNK, 512);
+        const uint64_t d_wl0 = umma::make_desc(umma::smem_u32(c.wlo), TS_CHUNK, 512);
+        for (int s = 0; s < nsl; ++s) {
+            if (s == TSI_STAGES && wait_cluster) cluster_wait_acquire_divergent();
+            const int stg = s % TSI_STAGES;
+            umma::mbar_wait(&c.full[stg], (c.n_full[stg] + s / TSI_STAGES) & 1);
+            umma::fence_after_sync();
+            const uint64_t sbh = d_bh0 + (uint64_t)((stg * TS_STAGE_BYTES) >> 4);
+            const uint64_t swl = d_wl0 + (uint64_t)((s * (M / 32) * TS_CHUNK) >> 4);
+#pragma unroll
+            for (int kg = 0; kg < TS_SLAB / 8; ++kg) {
+                const uint64_t dbh = sbh + (uint64_t)((kg * 1024) >> 4);
+                const uint64_t dbl = dbh + (uint64_t)(TS_B_BYTES >> 4);
+                const uint64_t dwl = swl + (uint64_t)((kg * 1024) >> 4);
+                const uint32_t ta = c.tmem + (uint32_t)(TS_D_COLS_M + s * TS_SLAB + kg * 8);
+                mma_tf32_ts(c.tmem, ta, dbh, idesc_ts, (s > 0 || kg > 0) ? 1u : 0u);
+                mma_tf32_ts(c.tmem, ta, dbl, idesc_ts, 1u);
+                umma::mma_tf32(c.tmem, dwl, dbh, idesc_ss, 1u);
+            }
+            umma::commit(&c.empty[stg]);
+            if (s == nsl - 1) umma::commit(c.done);
+        }
+    } else if (wait_cluster) {
+        cluster_wait_acquire_divergent();
+    }
+#pragma unroll
+    for (int i = 0; i < TSI_STAGES; ++i) {
+        const uint32_t uses = (nsl - i + TSI_STAGES - 1) / TSI_STAGES;
+        c.n_full[i] += uses; c.n_empty[i] += uses;
+    }
+    umma::mbar_wait(c.done, c.n_done & 1);
+    c.n_done += 1;
+    umma::fence_after_sync();
+
+    float* bounce = reinterpret_cast<float*>(c.tiles);
+    {
+        const int lane = tid & 31;
+        const int lq = warp & 3, half = warp >> 2;
+        const int col = M == 128 ? lq * 32 + lane : (lane < 16 ? lq * 16 + lane : -1);   // M = 64: 16 accumulator rows per lane quadrant
+        constexpr int HALF_ROWS = ((ROWS / 2 + 15) / 16) * 16;
+#pragma unroll 1
+        for (int r0 = half * HALF_ROWS; r0 < min(ROWS, (half + 1) * HALF_ROWS); r0 += 16) {
+            if (r0 >= nrows) break;
+            uint32_t r[16];
+            umma::tmem_ld16(c.tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)r0, r);
+            if (col >= 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (r0 + j < nrows) bounce[(r0 + j) * BOUNCE_PITCH + col] = __uint_as_float(r[j]);
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tm.active && tm.ks == 0) {
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            const int r = tm.rg + i * RG;
+            if (r < nrows) {
+                const float4 v = *reinterpret_cast<const float4*>(bounce + r * BOUNCE_PITCH + tm.cg * 4);
+                acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
+            }
+        }
+    }
     umma::fence_proxy_async();
     __syncthreads();
 }
