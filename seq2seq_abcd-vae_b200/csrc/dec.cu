@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
         cluster_sync_all();
     }
     __syncthreads();
-    const bool timing = p.timing && blockIdx.x == 0 && tid == 0;
+    const bool timing = p.timing == 1 && blockIdx.x == 0 && tid == (TC ? 64 : 0);
     unsigned long long tacc[16];
     for (int i = 0; i < 16; ++i) tacc[i] = 0;
 #define DEC_TICK(slot) if (timing) { long long now_ = clock64(); tacc[slot] += now_ - tick_; tick_ = now_; }
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_kernel(DecK p) {
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);   // this thread's share of sum(dG) over rows and steps
     float4 hsum = make_float4(0.f, 0.f, 0.f, 0.f);   // ... and of sum(dHidPre) (bias gradients of the MLP input layers)
     __syncthreads();
-    const bool timing = p.timing && blockIdx.x == 0 && tid == 0;
+    const bool timing = p.timing == 3 && blockIdx.x == 0 && tid == 0;
     unsigned long long tacc[16];
     for (int i = 0; i < 16; ++i) tacc[i] = 0;
 #define DEC_TICK(slot) if (timing) { long long now_ = clock64(); tacc[slot] += now_ - tick_; tick_ = now_; }
@@ -811,7 +811,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_ts_kernel(DecK p) {
     __syncthreads();
     umma::fence_after_sync();
 
-    const bool timing = p.timing && blockIdx.x == 0 && tid == 32;
+    const bool timing = p.timing == 3 && blockIdx.x == 0 && tid == 32;
     unsigned long long tacc[16];
     for (int i = 0; i < 16; ++i) tacc[i] = 0;
 #define DEC_TICK(slot) if (timing) { long long now_ = clock64(); tacc[slot] += now_ - tick_; tick_ = now_; }
@@ -1360,7 +1360,7 @@ DecK make_k(const DecParams& P, const PackedMeta& pk, const DecWs& w) {
     for (int i = 0; i < 2; ++i) { k.em_w1[i] = P.em_w1[i]; k.em_b1[i] = P.em_b1[i]; k.em_w2[i] = P.em_w2[i]; k.em_b2[i] = P.em_b2[i]; }
     k.Hall = w.Hall; k.Call = w.Call; k.Xall = w.Xall; k.Gs = w.Gs; k.Hid = w.Hid; k.Mean = w.Mean; k.Lv = w.Lv;
     k.nll_partial = w.nll_partial; k.Pbuf = w.Pbuf; k.himg = w.himg; k.ximg = w.ximg;
-    k.timing = getenv("ABCD_TIMING") != nullptr;
+    k.timing = getenv("ABCD_TIMING") ? atoi(getenv("ABCD_TIMING")) : 0;   // 1: forward kernel, 3: backward kernel
     k.dML = w.dML; k.dHidPre = w.dHidPre; k.dG = w.dG; k.dHoff = w.dHoff; k.dHC0 = w.dHC0; k.dbias = w.dbias; k.dbias1 = w.dbias1; k.Pb2 = w.Pb2; k.Pb1 = w.Pb1;
     return k;
 }
