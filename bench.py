@@ -30,15 +30,15 @@ if ROOT not in sys.path:
 
 METRIC = 'train segments/sec (fwd+bwd+step)'
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the persistent kernels on this workload, from the
-# `ncu --set full` capture summarised in profiles/r01_e_tensor_memory_recurrences_B512.txt (B=512, F=65, LSTM)
+# `ncu --set full` capture summarised in profiles/r01_f_operand_images_B512.txt (B=512, F=65, LSTM)
 NCU_TRAFFIC_BYTES = {
-	'enc_fwd_kernel': 123.13e6 + 135.82e6, 'enc_bwd_kernel': 155.34e6 + 97.49e6,
-	'dec_fwd_kernel': 11.96e6 + 85.18e6, 'dec_bwd_kernel': 144.34e6 + 75.37e6,
+	'enc_fwd_kernel': 124.88e6 + 140.55e6, 'enc_bwd_kernel': 155.34e6 + 96.41e6,
+	'dec_fwd_kernel': 11.96e6 + 80.89e6, 'dec_bwd_kernel': 144.30e6 + 75.26e6,
 }
 # sm__pipe_tensor_cycles_active / sm__inst_executed_pipe_fma (% of peak sustained active) from the same capture
 NCU_PIPES = {
-	'enc_fwd_kernel': {'tensor_pct': 9.4, 'fma_pct': 7.5}, 'enc_bwd_kernel': {'tensor_pct': 9.8, 'fma_pct': 4.3},
-	'dec_fwd_kernel': {'tensor_pct': 0.0, 'fma_pct': 23.1}, 'dec_bwd_kernel': {'tensor_pct': 4.1, 'fma_pct': 5.0},
+	'enc_fwd_kernel': {'tensor_pct': 11.3, 'fma_pct': 5.8}, 'enc_bwd_kernel': {'tensor_pct': 9.8, 'fma_pct': 4.3},
+	'dec_fwd_kernel': {'tensor_pct': 0.0, 'fma_pct': 23.1}, 'dec_bwd_kernel': {'tensor_pct': 4.5, 'fma_pct': 4.7},
 }
 CFG = dict(rnn='LSTM', F=65, K=128, f=256, H=256, M=256, B=512, N_data=100000)
 
@@ -357,7 +357,7 @@ def main():
 		publication = args.batch == CFG['B'] and args.bins == CFG['F'] and args.rnn == 'LSTM'
 		roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
 					'traffic': NCU_TRAFFIC_BYTES.get(dom) if publication else None, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1400 (B200_PROFILING.md)',
-					'traffic_source': 'profiles/r01_e_tensor_memory_recurrences_B512.txt (ncu --set full, bytes per launch)' if publication else None,
+					'traffic_source': 'profiles/r01_f_operand_images_B512.txt (ncu --set full, bytes per launch)' if publication else None,
 					'ncu_pipes': NCU_PIPES.get(dom) if publication else None,
 					'note': 'fp32-grade recurrent kernel (tcgen05 3xTF32 products with the weights in tensor memory + FFMA phases); algorithmic FLOPs over the measured bf16 tensor peak; the fp32 FFMA peak is ~72 TFLOP/s',
 					'frac_of_fp32_ffma_peak': achieved / 72.0, 'avg_launch_ms': dur * 1e3}
