@@ -1,5 +1,5 @@
 // tcgen05 (5th-gen tensor core) building blocks shared by the weight-gradient GEMM (umma_gemm.cu) and the
-// recurrent kernels' tensor-core phase (rnn_tc.cuh): shared-memory / instruction descriptors for kind::tf32 with
+// recurrent kernels' tensor-core phases (rnn_ts.cuh): shared-memory / instruction descriptors for kind::tf32 with
 // MN-major operands, mbarrier helpers and the 3xTF32 operand split.
 #pragma once
 #include <stdint.h>

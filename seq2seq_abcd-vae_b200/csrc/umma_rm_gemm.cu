@@ -38,7 +38,7 @@ struct RmArgs {
 using umma::smem_u32;
 
 // raw piece p (4 floats) of row r lives at piece position p ^ ((r >> 3) & 3): reading 4 consecutive rows x one piece
-// for 32 row quads then touches every bank group equally (see rnn_tc.cuh)
+// for 32 row quads then touches every bank group equally (same scheme as rnn_ts.cuh)
 __device__ __forceinline__ int raw_off(int r, int p) { return r * RM_PITCH + ((p ^ ((r >> 3) & 3)) << 2); }
 
 // rows 4q..4q+3, k-quad kq of a k-contiguous raw block -> four MN-major 16-byte pieces
