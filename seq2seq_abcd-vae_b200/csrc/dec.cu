@@ -1381,6 +1381,9 @@ int dec_read_timing(unsigned long long* out16) {
     return ABCD_OK;
 }
 int dec_max_clusters(int which, int F, int* out) {
+    if (which == 1 && dec_bwd_use_ts(F))   // the tensor-memory backward
+        return rnn_max_active_clusters(dec_bwd_ts_kc(F) == 64 ? (const void*)dec_bwd_ts_kernel<0, 64> : (const void*)dec_bwd_ts_kernel<0, 32>,
+                                       dec_bwd_ts_smem(F), CL, NTHREADS, out);
     const int kc = which == 0 ? dec_fwd_kc(F) : dec_bwd_kc(F);
     const void* fn = which == 0 ? (kc == 128 ? (const void*)dec_fwd_kernel<0, 128> : kc == 64 ? (const void*)dec_fwd_kernel<0, 64> : (const void*)dec_fwd_kernel<0, 32>)
                                 : (kc == 128 ? (const void*)dec_bwd_kernel<0, 128> : kc == 64 ? (const void*)dec_bwd_kernel<0, 64> : (const void*)dec_bwd_kernel<0, 32>);

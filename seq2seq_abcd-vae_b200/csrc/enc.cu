@@ -784,8 +784,11 @@ int rnn_max_active_clusters(const void* fn, size_t smem, int cluster, int thread
 }
 int enc_max_clusters(int which, int* out) {
     const bool tc = rnn_use_tc();
-    const void* fn = which == 0 ? (tc ? (const void*)enc_fwd_kernel<0, true> : (const void*)enc_fwd_kernel<0, false>) : (const void*)enc_bwd_kernel<0>;
-    return rnn_max_active_clusters(fn, which == 0 ? enc_fwd_smem(tc) : enc_bwd_smem(), ENC_CL, ENC_NT, out);
+    // the kernels the launchers pick with the current tensor-core setting
+    const void* fn = which == 0 ? (tc ? (const void*)enc_fwd_kernel<0, true> : (const void*)enc_fwd_kernel<0, false>)
+                                : (tc ? (const void*)enc_bwd_ts_kernel<0> : (const void*)enc_bwd_kernel<0>);
+    const size_t smem = which == 0 ? enc_fwd_smem(tc) : (tc ? enc_bwd_ts_smem() : enc_bwd_smem());
+    return rnn_max_active_clusters(fn, smem, ENC_CL, ENC_NT, out);
 }
 
 int rnn_set_tc(int on) {
