@@ -107,11 +107,16 @@ __global__ void kl_final_kernel(int nparts, const float* __restrict__ partial, c
     if (threadIdx.x == 0) *kl_out = (float)(*prior * (double)batch_over_n + s);
 }
 
-// dKL/dlogits_bj = g * q_bj [ (log q_bj - E_j) - sum_k q_bk (log q_bk - E_k) ];  also Q_k = sum_b q_bk (atomic).
+// dKL/dlogits_bj = g * q_bj [ (log q_bj - E_j) - sum_k q_bk (log q_bk - E_k) ];  also the column sums Q_k = sum_b q_bk,
+// reproducibly: every warp adds its rows (in order) into its own row of shared memory, the block adds the warps in order
+// and writes Qpart[block][K]; kl_shape_bwd_kernel adds the blocks in order.  Dynamic shared memory: (warps) x K floats.
 __global__ void kl_rows_bwd_kernel(int B, int K, const float* __restrict__ logits, const float* __restrict__ E,
-                                   const float* __restrict__ g_kl, float* __restrict__ dlogits, float* __restrict__ Q) {
+                                   const float* __restrict__ g_kl, float* __restrict__ dlogits, float* __restrict__ Qpart) {
+    extern __shared__ float q_warp[];   // [nw][K]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const float g = *g_kl;
+    float* qw = q_warp + (size_t)w * K;
+    for (int k = lane; k < K; k += 32) qw[k] = 0.f;
     for (int b = blockIdx.x * nw + w; b < B; b += gridDim.x * nw) {
         const float* l = logits + (long)b * K;
         float mx = -INFINITY;
@@ -131,17 +136,29 @@ __global__ void kl_rows_bwd_kernel(int B, int K, const float* __restrict__ logit
             float lq = l[k] - mx - lz;
             float q = expf(lq);
             dlogits[(long)b * K + k] = g * q * ((lq - E[k]) - s);
-            atomicAdd(Q + k, q);
+            qw[k] += q;
         }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        float tot = 0.f;
+        for (int i = 0; i < nw; ++i) tot += q_warp[(size_t)i * K + k];
+        Qpart[(size_t)blockIdx.x * K + k] = tot;
     }
 }
 
 // dKL/dphi_j = g * N s_j (h_j - sum_k s_k h_k),  h_k = psi'(alpha_k) (B s_k - Q_k)   [SURVEY.md 8(a) a10]
-__global__ void kl_shape_bwd_kernel(int K, int B, const float* __restrict__ s, const float* __restrict__ Q,
-                                    float prior_c, float n_data, const float* __restrict__ g_kl,
+__global__ void kl_shape_bwd_kernel(int K, int B, const float* __restrict__ s, const float* __restrict__ Qpart, int nparts,
+                                    float* __restrict__ Q, float prior_c, float n_data, const float* __restrict__ g_kl,
                                     float* __restrict__ d_phi) {
     __shared__ double red[40];
     const int tid = threadIdx.x;
+    for (int k = tid; k < K; k += blockDim.x) {   // block partials in a fixed order
+        float tot = 0.f;
+        for (int i = 0; i < nparts; ++i) tot += Qpart[(size_t)i * K + k];
+        Q[k] = tot;
+    }
+    __syncthreads();
     double dot = 0.0;
     for (int k = tid; k < K; k += blockDim.x) {
         double ak = (double)(s[k] * n_data + prior_c);
@@ -442,8 +459,8 @@ int sampler_sample_backward(const SamplerParams& P, const SamplerGrads& G, int B
     return ABCD_OK;
 }
 
-// ABCDSampler.kl_divergence (model.py:608-639).  ws: E[K], s[K], Q[K], partial[ROW_BLOCKS] floats + 1 double.
-size_t sampler_kl_ws_floats(int K) { return (size_t)3 * K + ROW_BLOCKS + 8; }
+// ABCDSampler.kl_divergence (model.py:608-639).  ws: 1 double, E[K], s[K], Q[K], partial[ROW_BLOCKS], Qpart[ROW_BLOCKS][K].
+size_t sampler_kl_ws_floats(int K) { return (size_t)3 * K + ROW_BLOCKS + 8 + (size_t)ROW_BLOCKS * K; }
 
 static void kl_ws(float* ws, int K, float** E, float** s, float** Q, float** partial, double** prior) {
     *prior = reinterpret_cast<double*>(ws);   // first 8 bytes (ws is 256B aligned by the caller)
@@ -468,10 +485,13 @@ int sampler_kl_backward(const SamplerParams& P, const SamplerGrads& G, int B, co
                         const float* g_kl, float* dlogits, float* ws, cudaStream_t stream) {
     float *E, *s, *Q, *partial; double* prior;
     kl_ws(ws, P.K, &E, &s, &Q, &partial, &prior);
-    CUDA_TRY(cudaMemsetAsync(Q, 0, (size_t)P.K * sizeof(float), stream));
-    kl_rows_bwd_kernel<<<ROW_BLOCKS, 256, 0, stream>>>(B, P.K, logits, E, g_kl, dlogits, Q);
+    ARG_CHECK(P.K <= 4096, "sampler: too many categories");
+    float* Qpart = partial + ROW_BLOCKS;
+    int nw = 12288 / P.K;                         // warps per block: (warps) x K floats of shared memory <= 48 KB
+    nw = nw > 8 ? 8 : (nw < 1 ? 1 : nw);
+    kl_rows_bwd_kernel<<<ROW_BLOCKS, 32 * nw, (size_t)nw * P.K * sizeof(float), stream>>>(B, P.K, logits, E, g_kl, dlogits, Qpart);
     KERNEL_CHECK();
-    kl_shape_bwd_kernel<<<1, 256, 0, stream>>>(P.K, B, s, Q, P.prior_c, n_data, g_kl, G.shape_logits);
+    kl_shape_bwd_kernel<<<1, 256, 0, stream>>>(P.K, B, s, Qpart, ROW_BLOCKS, Q, P.prior_c, n_data, g_kl, G.shape_logits);
     KERNEL_CHECK();
     return ABCD_OK;
 }

@@ -375,3 +375,63 @@ def test_umma_tn_gemm_3xtf32(abcd):
 				# tensor-memory accumulation truncates (RZ): the error grows with the rows accumulated per CTA; the
 				# production split keeps that near 400 rows (a few 1e-6)
 				assert err < 3e-6 + 1.5e-8 * (K / nsplit), (M, N, K, nsplit, err)
+
+
+def test_full_size_shards_add_up_and_step_is_deterministic(abcd):
+	"""BASELINE.json's bench configuration (B = 512 segments of 0.03-0.3 s, F = 65, H = M = f = 256, K = 128), too large for
+	the fp64 oracle to finish in seconds, checked through size-independent properties of the reference's loss
+	(learning.py:147-163: sums over segments / batch size):
+	  * determinism: the same step twice gives bit-identical losses and gradients (no atomics on the product path);
+	  * additivity over segments: losses and gradients of the full batch equal the sums over its two strided shards
+	    (dist.shard_packed -- exactly what two ranks compute before the all-reduce), to fp32 summation-order round-off."""
+	import importlib
+	dist = importlib.import_module('seq2seq_abcd-vae_b200.dist')
+	F, K, B = 65, 128, 512
+	lengths = CS.synthetic_lengths(B, 1000)
+	rng = np.random.RandomState(11)
+	sumT = int(lengths.sum())
+	bs = torch.tensor(O.batch_sizes_from_lengths(lengths.tolist()), dtype=torch.int64)
+	x = torch.from_numpy(np.clip(rng.normal(0.45, 0.25, size=(sumT, F)), -0.945, 1.05).astype(np.float32))
+	eps = torch.from_numpy(rng.normal(size=(sumT, F)).astype(np.float32))
+	gumbel = torch.from_numpy(rng.gumbel(size=(B, K)).astype(np.float32))
+	is_off = O.is_offset_packed(bs.tolist())
+	torch.manual_seed(5)
+	enc = abcd.model.RNN_Variational_Encoder(F, 256).cuda()
+	smp = abcd.model.ABCDSampler(enc.hidden_size_total, 256, K, 256).cuda()
+	dec = abcd.model.RNN_Variational_Decoder(F, 256, 256, 256).cuda()
+	smp.train(); smp.temperature = 0.8
+	mods = (enc, smp, dec)
+
+	def run(rank, world):
+		for m in mods:
+			m.zero_grad(set_to_none=True)
+		d, b = dist.shard_packed(x, bs, rank, world)
+		e, _ = dist.shard_packed(eps, bs, rank, world)
+		o, _ = dist.shard_packed(is_off, bs, rank, world)
+		g = gumbel[dist.shard_indices(B, rank, world)]
+		d = d.cuda()
+		logits = smp(enc(torch.nn.utils.rnn.PackedSequence(d, b)))
+		smp.injected_gumbel_noise = g.cuda()
+		feats = smp.sample(logits)
+		kl = smp.kl_divergence(logits, 40000)
+		dec.injected_emission_noise = e.cuda()
+		em, off = dec(feats, batch_sizes=b, ground_truth_out=d, ground_truth_offset=o.cuda())[:2]
+		((em + off + kl) / B).backward()
+		torch.cuda.synchronize()
+		losses = torch.stack([em.detach(), off.detach(), kl.detach()]).double().cpu()
+		grads = [p.grad.detach().clone() for m in mods for p in m.parameters() if p.grad is not None]
+		run.names = [type(m).__name__ + '.' + k for m in mods for k, p in m.named_parameters() if p.grad is not None]
+		return losses, grads
+
+	l_full, g_full = run(0, 1)
+	l_again, g_again = run(0, 1)
+	assert torch.equal(l_full, l_again)
+	unequal = [(n, rel_to_max(a, b)) for n, a, b in zip(run.names, g_full, g_again) if not torch.equal(a, b)]
+	assert not unequal, unequal
+	l0, g0 = run(0, 2)
+	l1, g1 = run(1, 2)
+	assert len(g_full) == len(g0) == len(g1) > 20
+	# the Dirichlet term of the KL is weighted by (segments in the batch) / N_data (model.py:327-329), so it adds up too
+	assert torch.allclose(l0 + l1, l_full, rtol=2e-6, atol=0), (l0 + l1, l_full)
+	worst = max(rel_to_max(a + b, f) for a, b, f in zip(g0, g1, g_full))
+	assert worst < 2e-5, worst
