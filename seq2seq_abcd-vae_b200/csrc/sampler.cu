@@ -257,7 +257,7 @@ __global__ void stats_kernel(int B, int K, const float* __restrict__ logits, con
         for (int k = lane; k < K; k += 32) {
             float lq = l[k] - mx - lz, q = expf(lq);
             e -= q * lq;
-            atomicAdd(&colmean[k], q);
+            atomicAdd(&colmean[k], q);   // log-line statistic only: the last bits may differ between runs
         }
         e = warp_sum(e);
         if (lane == 0) ent += e;

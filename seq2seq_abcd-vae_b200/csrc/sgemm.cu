@@ -329,8 +329,19 @@ __global__ void colsum_kernel(const float* __restrict__ A, long lda, int rows, i
     const int per = (rows + gridDim.y - 1) / gridDim.y;
     const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
     float s = 0.f;
-    if (c < cols)
-        for (int r = r0 + w; r < r1; r += 8) s += A[(long)r * lda + c];
+    if (c < cols) {
+        // four independent partial sums keep four loads in flight (the loop is latency-bound); fixed order
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int r = r0 + w;
+        for (; r + 24 < r1; r += 32) {
+            s0 += A[(long)r * lda + c];
+            s1 += A[(long)(r + 8) * lda + c];
+            s2 += A[(long)(r + 16) * lda + c];
+            s3 += A[(long)(r + 24) * lda + c];
+        }
+        for (; r < r1; r += 8) s0 += A[(long)r * lda + c];
+        s = (s0 + s1) + (s2 + s3);
+    }
     red[w][threadIdx.x & 31] = s;
     __syncthreads();
     if (w == 0 && c < cols) {
@@ -352,8 +363,16 @@ __global__ void colsum_finish_kernel(const float* __restrict__ scratch, int nspl
                                      float* __restrict__ out, int accumulate, GateMap dst) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
-    float t = 0.f;
-    for (int y = 0; y < nsplit; ++y) t += scratch[(long)y * cols + c];
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    int y = 0;
+    for (; y + 3 < nsplit; y += 4) {
+        t0 += scratch[(long)y * cols + c];
+        t1 += scratch[(long)(y + 1) * cols + c];
+        t2 += scratch[(long)(y + 2) * cols + c];
+        t3 += scratch[(long)(y + 3) * cols + c];
+    }
+    for (; y < nsplit; ++y) t0 += scratch[(long)y * cols + c];
+    float t = (t0 + t1) + (t2 + t3);
     int d = gate_src_row(dst, c);
     if (d >= 0) {
         t *= alpha;
@@ -402,6 +421,7 @@ static bool use_small_tiles(int M, int N, int splits) {
 }
 
 bool umma_tn_eligible(const GemmArgs& g);
+bool umma_tn_shape_ok(int M, int N, int K);
 int umma_tn_pick_splits(int M, int K);
 int umma_tn_launch(const GemmArgs& g, int splits, cudaStream_t stream);
 bool umma_rm_eligible(const GemmArgs& g);
@@ -419,7 +439,7 @@ static bool umma_enabled() {
 
 // Split-K factor for the reduction-over-frames (TN) GEMMs; callers size their partials buffer with it.
 int sgemm_pick_splits(int M, int N, int K) {
-    if (umma_enabled() && M % 128 == 0 && N <= 256 && K >= 256) return umma_tn_pick_splits(M, K);
+    if (umma_enabled() && umma_tn_shape_ok(M, N, K)) return umma_tn_pick_splits(M, K);
     long tiles = (long)((M + 127) / 128) * ((N + 127) / 128);
     if (M <= 64 || N <= 64) tiles = (long)((M + 63) / 64) * ((N + 63) / 64);
     int ktiles = (K + BK - 1) / BK;

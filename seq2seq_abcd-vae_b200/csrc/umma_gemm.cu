@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_tn_kernel(UmmaArgs g) {
             char* st = stage + (size_t)slot * STAGE_BYTES;
             for (int idx = tid; idx < UM_SLAB * (UM_BM / 4); idx += UM_THREADS) {
                 const int k = idx >> 5, mn4 = idx & 31;
-                if (k0s + k < kend) cp_async16(st + k * (UM_BM * 4) + mn4 * 16, g.A + (long)(k0s + k) * g.lda + m0 + mn4 * 4);
+                if (k0s + k < kend && m0 + mn4 * 4 < g.M)   // a ragged last M tile: pieces past M are zero-filled by the split pass
+                    cp_async16(st + k * (UM_BM * 4) + mn4 * 16, g.A + (long)(k0s + k) * g.lda + m0 + mn4 * 4);
             }
             char* stb = st + UM_SLAB * UM_BM * 4;
             if (g.bulk_b) {
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_tn_kernel(UmmaArgs g) {
         for (int idx = tid; idx < UM_SLAB * (UM_BM / 4); idx += UM_THREADS) {
             const int k = idx >> 5, mn4 = idx & 31;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k0 + k < kend) v = *reinterpret_cast<const float4*>(st + k * (UM_BM * 4) + mn4 * 16);
+            if (k0 + k < kend && m0 + mn4 * 4 < g.M) v = *reinterpret_cast<const float4*>(st + k * (UM_BM * 4) + mn4 * 16);
             split_store(a_hi, a_lo, tile_off(k, mn4), v);
         }
         for (int idx = tid; idx < UM_SLAB * (NB / 4); idx += UM_THREADS) {
@@ -244,7 +245,7 @@ int launch_nch(const UmmaArgs& a, int splits, cudaStream_t stream) {
         CUDA_TRY(cudaFuncSetAttribute(umma_tn_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid(a.M / UM_BM, 1, splits);
+    dim3 grid((a.M + UM_BM - 1) / UM_BM, 1, splits);
     umma_tn_kernel<NCH><<<grid, UM_THREADS, smem, stream>>>(a);
     KERNEL_CHECK();
     return ABCD_OK;
@@ -252,18 +253,26 @@ int launch_nch(const UmmaArgs& a, int splits, cudaStream_t stream) {
 
 }  // namespace
 
+// M: whole 128-row tiles, or a ragged last tile (rows past M are computed on zero-filled operands and dropped) when the
+// padding stays below ~50%
+bool umma_tn_shape_ok(int M, int N, int K) {
+    if (M % UM_BM != 0 && (M < 64 || M % UM_BM < 64)) return false;
+    if (N < 1 || N > UM_MAX_N) return false;
+    return K >= 256;                                            // below that not worth a tensor-memory round trip
+}
+
 bool umma_tn_eligible(const GemmArgs& g) {
     if (g.a_kmajor || g.b_kmajor) return false;                 // TN form only
-    if (g.M % UM_BM != 0 || g.N < 1 || g.N > UM_MAX_N) return false;
-    if (g.K < 256) return false;                                // not worth a tensor-memory round trip
+    if (!umma_tn_shape_ok(g.M, g.N, g.K)) return false;
     if (g.lda % 4 != 0 || (reinterpret_cast<uintptr_t>(g.A) & 15) != 0) return false;
+    if (((g.M + 3) & ~3) > g.lda) return false;                 // the last 16-byte piece of a ragged M tile stays inside the row
     if (!g.partials) return false;
     return true;
 }
 
 // Split count that gives every SM one CTA; the caller's partials buffer must hold splits*M*N floats.
 int umma_tn_pick_splits(int M, int K) {
-    int mtiles = M / UM_BM;
+    int mtiles = (M + UM_BM - 1) / UM_BM;
     int s = (148 + mtiles - 1) / mtiles;
     if (s * mtiles > 148) s = 148 / mtiles;                      // one wave
     int max_s = (K + 4 * UM_SLAB - 1) / (4 * UM_SLAB);          // at least 4 slabs per split

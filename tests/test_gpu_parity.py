@@ -353,9 +353,14 @@ def test_umma_tn_gemm_3xtf32(abcd):
 	L = abcd._lib
 	L.ensure_device(torch.device('cuda'))
 	torch.manual_seed(1)
-	for (M, N, K, ldb, gather) in ((1024, 256, 5000, 256, True), (1024, 65, 3001, 65, False), (256, 256, 777, 256, False),
-									(128, 17, 300, 20, True), (1024, 65, 14755, 68, True)):
-		A = torch.randn(K, M, device='cuda')
+	# (M, N, K, ldb, gather, lda, first column of A): the last two exercise a ragged last M tile inside a wider row
+	# (the emission head's weight gradient: M = F = 65 columns of the [sumT, 2 * 68] gradient buffer)
+	for (M, N, K, ldb, gather, lda, a_col) in ((1024, 256, 5000, 256, True, 1024, 0), (1024, 65, 3001, 65, False, 1024, 0),
+												(256, 256, 777, 256, False, 256, 0), (128, 17, 300, 20, True, 128, 0),
+												(1024, 65, 14755, 68, True, 1024, 0), (65, 256, 14755, 256, False, 136, 68),
+												(200, 130, 1000, 132, False, 200, 0)):
+		Afull = torch.randn(K, lda, device='cuda')
+		A = Afull[:, a_col:a_col + M]
 		Bfull = torch.randn(K + 7, ldb, device='cuda')
 		idx = torch.randint(-1, K + 7, (K,), device='cuda', dtype=torch.int32) if gather else None
 		rows = Bfull[:K] if idx is None else torch.where((idx >= 0)[:, None], Bfull[idx.clamp(min=0).long()], torch.zeros_like(Bfull[:K]))
@@ -368,7 +373,7 @@ def test_umma_tn_gemm_3xtf32(abcd):
 			lib = L.load()
 			# abcd_sgemm has no gather argument: exercise the gather through the encoder/decoder paths; here plain rows
 			if idx is None:
-				L.call('abcd_sgemm', M, N, K, L.ptr(A), M, 0, L.ptr(Bfull), ldb, 0, L.ptr(Cout), N, 2.0, None, 0, 1, nsplit, L.ptr(part), L.stream_ptr())
+				L.call('abcd_sgemm', M, N, K, L.ptr(Afull) + 4 * a_col, lda, 0, L.ptr(Bfull), ldb, 0, L.ptr(Cout), N, 2.0, None, 0, 1, nsplit, L.ptr(part), L.stream_ptr())
 				torch.cuda.synchronize()
 				got = Cout.double() - 0.5
 				err = float((got - 2.0 * want).abs().max() / (2.0 * want).abs().max())
