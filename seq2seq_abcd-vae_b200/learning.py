@@ -157,7 +157,7 @@ class Learner(object):
 		kl_loss = self.feature_sampler.kl_divergence(category_logits, num_strings)
 		emission_loss, end_prediction_loss, _, _, _ = self.decoder(
 			features, batch_sizes=packed_input.batch_sizes, speaker=speaker, ground_truth_out=packed_input.data,
-			ground_truth_offset=is_offset.data)
+			ground_truth_offset=is_offset.data, return_outputs=False)
 		return emission_loss, end_prediction_loss, kl_loss, category_logits
 
 	def train_step(self, packed_input, is_offset, speaker, num_strings, is_pretraining, global_batch_size=None):

@@ -406,11 +406,14 @@ class _SampleFn(torch.autograd.Function):
 		ctx.save_for_backward(y, codebook)
 		ctx.mode, ctx.tau = mode, float(tau)
 		ctx.mark_non_differentiable(y)
+		ctx.set_materialize_grads(False)
 		return feats, y
 
 	@staticmethod
 	def backward(ctx, dfeat, _dy):
 		y, codebook = ctx.saved_tensors
+		if dfeat is None:
+			return None, None, None, None, None
 		dfeat = _f32(dfeat)
 		B, K = y.shape
 		(gcb,), (gcb_ret,) = _grad_buffers((codebook,))
@@ -585,7 +588,7 @@ class _DecoderFn(torch.autograd.Function):
 	@staticmethod
 	def forward(ctx, feat_in, eps, gt, is_offset, desc, cell, dims, *params):
 		lib = L.ensure_device(feat_in.device)
-		F, H, M = dims
+		F, H, M, want_outputs = dims
 		feat_in, eps = _f32(feat_in), _f32(eps)
 		gt = _f32(gt) if gt is not None else None
 		is_offset = _f32(is_offset) if is_offset is not None else None
@@ -595,18 +598,23 @@ class _DecoderFn(torch.autograd.Function):
 		ws_bytes = lib.abcd_dec_workspace_bytes(cell, F, fin, desc.B, desc.sumT)
 		ws = _ws(ws_bytes, dev)
 		losses = torch.zeros(2, dtype=torch.float32, device=dev)
-		out_x = torch.empty(desc.sumT, F, dtype=torch.float32, device=dev)
-		out_mean = torch.empty_like(out_x)
-		out_lv = torch.empty_like(out_x)
-		out_off = torch.empty(desc.sumT, dtype=torch.float32, device=dev)
+		if want_outputs:
+			out_x = torch.empty(desc.sumT, F, dtype=torch.float32, device=dev)
+			out_mean = torch.empty_like(out_x)
+			out_lv = torch.empty_like(out_x)
+			out_off = torch.empty(desc.sumT, dtype=torch.float32, device=dev)
+		else:   # losses only (Learner.train_step): the kernels skip the unpadded copies
+			out_x = out_mean = out_lv = out_off = None
 		dp, _ = _dec_structs(cell, F, H, M, fin, params)
 		L.call('abcd_dec_fwd', C.byref(dp), desc.ref(), L.ptr(feat_in), L.ptr(eps), eps.shape[1],
 			L.ptr(gt), gt.shape[1] if gt is not None else 0, L.ptr(is_offset), L.ptr(losses),
 			L.ptr(out_x), L.ptr(out_mean), L.ptr(out_lv), L.ptr(out_off), L.ptr(ws), ws_bytes, L.stream_ptr())
-		ctx.desc, ctx.cell, ctx.dims, ctx.ws, ctx.ws_bytes = desc, cell, dims, ws, ws_bytes
+		ctx.desc, ctx.cell, ctx.dims, ctx.ws, ctx.ws_bytes = desc, cell, (F, H, M), ws, ws_bytes
 		ctx.has_targets = gt is not None and is_offset is not None
 		ctx.save_for_backward(feat_in, eps, gt if gt is not None else eps, is_offset if is_offset is not None else eps, *params)
-		ctx.mark_non_differentiable(out_x, out_mean, out_lv, out_off)
+		if want_outputs:
+			ctx.mark_non_differentiable(out_x, out_mean, out_lv, out_off)
+		ctx.set_materialize_grads(False)   # no zero-filled [sumT, F] gradients for the non-differentiable outputs
 		return losses[0], losses[1], out_x, out_mean, out_lv, out_off
 
 	@staticmethod
@@ -693,9 +701,11 @@ class RNN_Variational_Decoder(torch.nn.Module):
 	def _length_to_batch_sizes(self, lengths):
 		return [(lengths > t).sum() for t in range(int(lengths.max()))]
 
-	def forward(self, features, lengths=None, batch_sizes=None, speaker=None, ground_truth_out=None, ground_truth_offset=None):
+	def forward(self, features, lengths=None, batch_sizes=None, speaker=None, ground_truth_out=None, ground_truth_offset=None,
+				return_outputs=True):
 		"""Returns (emission_loss, offset_loss, flatten_out, (mean, log_variance), flatten_offset_weights); the
-		flattened tensors are in PackedSequence.data order."""
+		flattened tensors are in PackedSequence.data order.  return_outputs=False (not in the reference; used by
+		Learner, which only needs the losses) returns None for the flattened tensors and skips their copies."""
 		assert (lengths is not None) or (batch_sizes is not None), 'Either lengths or batch_sizes must be given.'
 		if lengths is not None:
 			batch_sizes = torch.stack(self._length_to_batch_sizes(lengths)).cpu()
@@ -709,7 +719,7 @@ class RNN_Variational_Decoder(torch.nn.Module):
 		if eps is None:
 			eps = noise_like(torch.empty(desc.sumT, F, device=features.device))
 		em, off, out_x, mean, lv, off_logit = _DecoderFn.apply(
-			features, eps, ground_truth_out, ground_truth_offset, desc, _cell_code(self.rnn_cell.mode), (F, H, M), *self._params())
+			features, eps, ground_truth_out, ground_truth_offset, desc, _cell_code(self.rnn_cell.mode), (F, H, M, bool(return_outputs)), *self._params())
 		if ground_truth_out is None:
 			em = None
 		if ground_truth_offset is None:
