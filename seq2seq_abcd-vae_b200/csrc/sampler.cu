@@ -154,9 +154,16 @@ __global__ void kl_shape_bwd_kernel(int K, int B, const float* __restrict__ s, c
     __shared__ double red[40];
     const int tid = threadIdx.x;
     for (int k = tid; k < K; k += blockDim.x) {   // block partials in a fixed order
-        float tot = 0.f;
-        for (int i = 0; i < nparts; ++i) tot += Qpart[(size_t)i * K + k];
-        Q[k] = tot;
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;   // four loads in flight; the order is still fixed
+        int i = 0;
+        for (; i + 3 < nparts; i += 4) {
+            t0 += Qpart[(size_t)i * K + k];
+            t1 += Qpart[(size_t)(i + 1) * K + k];
+            t2 += Qpart[(size_t)(i + 2) * K + k];
+            t3 += Qpart[(size_t)(i + 3) * K + k];
+        }
+        for (; i < nparts; ++i) t0 += Qpart[(size_t)i * K + k];
+        Q[k] = (t0 + t1) + (t2 + t3);
     }
     __syncthreads();
     double dot = 0.0;

@@ -359,24 +359,34 @@ __global__ void colsum_kernel(const float* __restrict__ A, long lda, int rows, i
         }
     }
 }
+// blockIdx.x: 32-column strip; warp w adds splits w, w+8, ... (four loads in flight), warp 0 adds the 8 warps: fixed order
 __global__ void colsum_finish_kernel(const float* __restrict__ scratch, int nsplit, int cols, float alpha,
                                      float* __restrict__ out, int accumulate, GateMap dst) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
     float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-    int y = 0;
-    for (; y + 3 < nsplit; y += 4) {
-        t0 += scratch[(long)y * cols + c];
-        t1 += scratch[(long)(y + 1) * cols + c];
-        t2 += scratch[(long)(y + 2) * cols + c];
-        t3 += scratch[(long)(y + 3) * cols + c];
+    if (c < cols) {
+        int y = w;
+        for (; y + 24 < nsplit; y += 32) {
+            t0 += scratch[(long)y * cols + c];
+            t1 += scratch[(long)(y + 8) * cols + c];
+            t2 += scratch[(long)(y + 16) * cols + c];
+            t3 += scratch[(long)(y + 24) * cols + c];
+        }
+        for (; y < nsplit; y += 8) t0 += scratch[(long)y * cols + c];
     }
-    for (; y < nsplit; ++y) t0 += scratch[(long)y * cols + c];
-    float t = (t0 + t1) + (t2 + t3);
-    int d = gate_src_row(dst, c);
-    if (d >= 0) {
-        t *= alpha;
-        out[d] = accumulate ? out[d] + t : t;
+    red[w][lane] = (t0 + t1) + (t2 + t3);
+    __syncthreads();
+    if (w == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][lane];
+        int d = gate_src_row(dst, c);
+        if (d >= 0) {
+            t *= alpha;
+            out[d] = accumulate ? out[d] + t : t;
+        }
     }
 }
 
@@ -515,7 +525,7 @@ int colsum_launch(const float* A, long lda, int rows, int cols, float alpha, flo
     colsum_kernel<<<dim3(strips, nsplit), 256, 0, stream>>>(A, lda, rows, cols, alpha, out, accumulate, dst, scratch);
     KERNEL_CHECK();
     if (nsplit > 1) {
-        colsum_finish_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(scratch, nsplit, cols, alpha, out, accumulate, dst);
+        colsum_finish_kernel<<<strips, 256, 0, stream>>>(scratch, nsplit, cols, alpha, out, accumulate, dst);
         KERNEL_CHECK();
     }
     return ABCD_OK;
