@@ -23,6 +23,7 @@ constexpr int RM_RAW_A = RM_BM * RM_PITCH * 4;     // bytes
 constexpr int RM_RAW_B = RM_BN * RM_PITCH * 4;     // bytes (k-major B; the n-major form needs 32*256*4, less)
 constexpr int RM_STAGE = RM_RAW_A + RM_RAW_B;
 constexpr int RM_STAGES = 2;
+constexpr int RM_EP_PITCH = 36;                     // epilogue bounce tile: [32 rows][36] floats per warp (8 x 4608 B in the staging area)
 constexpr size_t RM_SMEM = 2 * RM_A_TILE + 2 * RM_B_TILE + RM_STAGES * RM_STAGE + 1024;
 
 struct RmArgs {
@@ -161,33 +162,49 @@ __global__ void __launch_bounds__(RM_THREADS, 1) umma_rm_kernel(RmArgs g) {
         }
         issue_slab(s + RM_STAGES, slot);
     }
-    // ---- epilogue: tensor memory -> registers -> C ----
+    // ---- epilogue: tensor memory -> registers -> per-warp transpose in shared memory -> C ----
+    // A thread reads ROW lane of the accumulator; storing that directly would scatter 16-byte pieces over 32 rows per
+    // instruction.  Each warp bounces its 32 x 32 block through the (now free) staging area and writes 128-byte runs.
+    cp_async_wait<0>();
     if (nslab > 0) umma::mbar_wait(&mma_bar, (uint32_t)((nslab - 1) & 1));
     umma::fence_after_sync();
     const int lane_q = warp & 3;
-    const int m = m0 + lane_q * 32 + lane;
-    float* out = g.C + (long)m * g.ldc + n0;
+    float* tile = reinterpret_cast<float*>(stage) + warp * (32 * RM_EP_PITCH);
+    const int rq = lane >> 3, cq = lane & 7;          // read-back: rows rq, rq + 4, ...; column quad cq
 #pragma unroll 1
-    for (int c0 = (warp >> 2) * 16; c0 < n_pad; c0 += 32) {
-        uint32_t r[16];
-        if (nslab > 0) umma::tmem_ld16(tmem_d + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)c0, r);
-        else {
+    for (int c0 = (warp >> 2) * 32; c0 < n_pad; c0 += 64) {
+        uint32_t ra[16], rb[16];
+        if (nslab > 0) {
+            const uint32_t taddr = tmem_d + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)c0;
+            umma::tmem_ld16(taddr, ra);
+            umma::tmem_ld16(taddr + 16, rb);
+        } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = 0u;
+            for (int j = 0; j < 16; ++j) ra[j] = rb[j] = 0u;
         }
-        if (m < g.M) {
+        __syncwarp();                                 // the previous block has been read back
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int c = c0 + 4 * q;
-                if (c >= nloc) continue;
-                float4 v = make_float4(__uint_as_float(r[4 * q]) * g.alpha, __uint_as_float(r[4 * q + 1]) * g.alpha,
-                                       __uint_as_float(r[4 * q + 2]) * g.alpha, __uint_as_float(r[4 * q + 3]) * g.alpha);
-                if (g.bias) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + c));
-                    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        for (int q = 0; q < 4; ++q) {
+            *reinterpret_cast<float4*>(tile + lane * RM_EP_PITCH + 4 * q) =
+                make_float4(__uint_as_float(ra[4 * q]), __uint_as_float(ra[4 * q + 1]), __uint_as_float(ra[4 * q + 2]), __uint_as_float(ra[4 * q + 3]));
+            *reinterpret_cast<float4*>(tile + lane * RM_EP_PITCH + 16 + 4 * q) =
+                make_float4(__uint_as_float(rb[4 * q]), __uint_as_float(rb[4 * q + 1]), __uint_as_float(rb[4 * q + 2]), __uint_as_float(rb[4 * q + 3]));
+        }
+        __syncwarp();
+        const int c = c0 + 4 * cq;
+        if (c < nloc) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g.bias) b = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + c));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = rq + 4 * i;
+                const int m = m0 + lane_q * 32 + row;
+                if (m < g.M) {
+                    float4 v = *reinterpret_cast<const float4*>(tile + row * RM_EP_PITCH + 4 * cq);
+                    v.x = v.x * g.alpha + b.x; v.y = v.y * g.alpha + b.y; v.z = v.z * g.alpha + b.z; v.w = v.w * g.alpha + b.w;
+                    if (g.act == 1) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+                    *reinterpret_cast<float4*>(g.C + (long)m * g.ldc + n0 + c) = v;
                 }
-                if (g.act == 1) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
-                *reinterpret_cast<float4*>(out + c) = v;
             }
         }
     }
