@@ -190,39 +190,36 @@ __global__ void __launch_bounds__(UM_THREADS, 1) umma_tn_kernel(UmmaArgs g) {
         // every thread is past its reads of staging[slot]: refill it two slabs ahead
         issue_slab(s + UM_STAGES, slot);
     }
-    // ---- epilogue: TMEM -> registers -> partials ----
+    // ---- epilogue: TMEM -> registers -> per-warp transpose in shared memory -> partials ----
+    // A thread reads ROW lane of the accumulator; storing that directly scatters every store instruction over 32 rows.
+    // Each warp bounces its 32 x 32 block through the (now free) staging area and writes contiguous 128-byte runs.
+    cp_async_wait<0>();
     if (nslab > 0) mbar_wait(&mma_bar, (uint32_t)((nslab - 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const int lane_q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int m = m0 + lane_q * 32 + lane;
-    float* out = g.partials + ((long)blockIdx.z * g.M + m) * g.N;
-    const bool out_vec = (g.N % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.partials) & 15) == 0);
+    float* tile = reinterpret_cast<float*>(stage) + warp * (32 * 33);
+    float* out = g.partials + ((long)blockIdx.z * g.M + m0 + lane_q * 32) * g.N;
 #pragma unroll 1
-    for (int c0 = (warp >> 2) * 16; c0 < g.n_pad; c0 += 32) {
-        uint32_t r[16];
+    for (int c0 = (warp >> 2) * 32; c0 < g.n_pad; c0 += 64) {
+        uint32_t ra[16], rb[16];
         if (nslab > 0) {
             const uint32_t taddr = tmem_d + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                : "r"(taddr) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            umma::tmem_ld16(taddr, ra);
+            umma::tmem_ld16(taddr + 16, rb);
         } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = 0u;
+            for (int j = 0; j < 16; ++j) ra[j] = rb[j] = 0u;
         }
-        if (m < g.M) {
-            if (out_vec && c0 + 15 < g.N) {
+        __syncwarp();                                  // the previous block has been read back
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<float4*>(out + c0 + 4 * q) =
-                        make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c0 + j < g.N) out[c0 + j] = __uint_as_float(r[j]);
-            }
+        for (int j = 0; j < 16; ++j) {
+            tile[lane * 33 + j] = __uint_as_float(ra[j]);
+            tile[lane * 33 + 16 + j] = __uint_as_float(rb[j]);
+        }
+        __syncwarp();
+        if (c0 + lane < g.N) {
+            const int rows = min(32, g.M - (m0 + lane_q * 32));
+            for (int r = 0; r < rows; ++r) out[(long)r * g.N + c0 + lane] = tile[r * 33 + lane];
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
