@@ -199,7 +199,7 @@ def reference_arm(args):
 		'e2e': {'value': val, 'unit': 'segments/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
 		'gpu_launches': 0,
 	}
-	print(json.dumps(line), flush=True)
+	emit_json(line)
 
 
 def workload_config(args, lengths, world):
@@ -216,7 +216,22 @@ def workload_config(args, lengths, world):
 # ---------------------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def emit_json(line):
+	"""The one JSON line of the contract, on the process's ORIGINAL stdout."""
+	sys.stdout.flush()
+	os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + '\n').encode())
+
+
 def main():
+	global _JSON_FD
+	# stdout must carry exactly one JSON line, but native libraries print there too (NCCL's version banner when the
+	# environment sets NCCL_DEBUG): keep the original stdout for the JSON line and point fd 1 at stderr for everything else
+	sys.stdout.flush()
+	_JSON_FD = os.dup(1)
+	os.dup2(2, 1)
 	args = parse()
 	if args.impl == 'reference':
 		reference_arm(args)
@@ -417,7 +432,7 @@ def main():
 			'train_flops_per_step': flops_per_step(lengths, args.bins, rnn=args.rnn),
 			'achieved_tflops_whole_step': flops_per_step(lengths, args.bins, rnn=args.rnn) / (ms_per_step * 1e-3) / 1e12,
 		}
-		print(json.dumps(line), flush=True)
+		emit_json(line)
 	if world > 1:
 		torch.distributed.destroy_process_group()
 
