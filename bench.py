@@ -393,7 +393,7 @@ def main():
 		du = importlib.import_module('seq2seq_abcd-vae_b200.modules.data_utils')
 		n_fft, hop = 2 * (F - 1), F - 1
 		nsamp = torch.tensor([(int(l) - 1) * hop + hop // 2 for l in lengths], dtype=torch.int32)
-		onset = torch.cumsum(torch.cat([torch.zeros(1, dtype=torch.int64), nsamp[:-1].long()]), 0).to(torch.int32)
+		onset = torch.cumsum(torch.cat([torch.zeros(1, dtype=torch.int64), nsamp[:-1].long()]), 0)
 		wav = torch.from_numpy(np.random.RandomState(5).randint(-3000, 3000, size=int(nsamp.sum())).astype(np.int16)).to(dev)
 		desc = pkg.model.as_packed_desc(bs, dev)
 		win = torch.hann_window(n_fft).to(dev)

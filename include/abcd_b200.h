@@ -113,7 +113,7 @@ int abcd_profile_read(int id, float* total_ms, int* count);
 
 /* ---- front end: data_utils.STFT.__call__ + log_and_normalize (data_utils.py:131-139, learning.py:466) */
 int abcd_stft_logamp(const void* wav, int wav_is_int16, int64_t n_samples,
-                     const int32_t* seg_onset, const int32_t* seg_nsamp, /* [B] sample index / sample count, batch order */
+                     const int64_t* seg_onset, const int32_t* seg_nsamp, /* [B] first sample (int64: corpora past 2^31 samples) / sample count, batch order */
                      const abcd_packed_t* pk, int n_fft, int hop, int center, const float* window /*[n_fft]*/,
                      float eps, float normalizer, float* out /*[sumT, ld_out]*/, int64_t ld_out, void* stream);
 

@@ -79,7 +79,7 @@ SIGNATURES = {
 	'abcd_profile_name': (C.c_char_p, [C.c_int]),
 	'abcd_profile_enable': (None, [C.c_int]),
 	'abcd_profile_read': (C.c_int, [C.c_int, P(C.c_float), P(C.c_int)]),
-	'abcd_stft_logamp': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_i32p, c_i32p, P(PackedT), C.c_int, C.c_int, C.c_int,
+	'abcd_stft_logamp': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, c_i32p, P(PackedT), C.c_int, C.c_int, C.c_int,
 								c_f32p, C.c_float, C.c_float, c_f32p, C.c_int64, C.c_void_p]),
 	'abcd_enc_workspace_bytes': (C.c_size_t, [C.c_int] * 6),
 	'abcd_enc_fwd': (C.c_int, [P(EncParamsT), P(PackedT), c_f32p, C.c_int, c_f32p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),

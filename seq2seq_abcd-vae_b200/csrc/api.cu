@@ -152,11 +152,11 @@ int abcd_init(int device) {
     return ABCD_OK;
 }
 
-int abcd_stft_logamp(const void* wav, int wav_is_int16, int64_t n_samples, const int32_t* seg_onset,
+int abcd_stft_logamp(const void* wav, int wav_is_int16, int64_t n_samples, const int64_t* seg_onset,
                      const int32_t* seg_nsamp, const abcd_packed_t* pk, int n_fft, int hop, int center,
                      const float* window, float eps, float normalizer, float* out, int64_t ld_out, void* stream) {
     ARG_CHECK(pk, "stft: null packed descriptor");
-    return stft_logamp(wav, wav_is_int16, (long)n_samples, seg_onset, seg_nsamp, pk->B, pk->offsets, pk->T_max, pk->sumT,
+    return stft_logamp(wav, wav_is_int16, (long)n_samples, (const long long*)seg_onset, seg_nsamp, pk->B, pk->offsets, pk->T_max, pk->sumT,
                        n_fft, hop, center, window, eps, normalizer, out, (long)ld_out, S(stream));
 }
 

@@ -17,7 +17,7 @@ namespace {
 
 struct StftK {
     const void* wav; int is_i16; long n_samples;
-    const int* onset; const int* nsamp;   // [B] in batch (sorted) order
+    const long long* onset; const int* nsamp;   // [B] in batch (sorted) order
     const int* offsets; int T_max; int sumT; int B;
     int n_fft, hop, center, F;
     const float* window;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(ST_THREADS) stft_logamp_kernel(StftK p) {
 
 }  // namespace
 
-int stft_logamp(const void* wav, int is_i16, long n_samples, const int* onset, const int* nsamp, int B,
+int stft_logamp(const void* wav, int is_i16, long n_samples, const long long* onset, const int* nsamp, int B,
                 const int* offsets, int T_max, int sumT, int n_fft, int hop, int center, const float* window,
                 float eps, float normalizer, float* out, long ld_out, cudaStream_t stream) {
     ARG_CHECK(n_fft >= 2 && n_fft <= 2048 && hop >= 1, "stft: n_fft %d / hop %d unsupported", n_fft, hop);

@@ -1,6 +1,6 @@
 #pragma once
 #include "common.cuh"
-int stft_logamp(const void* wav, int is_i16, long n_samples, const int* onset, const int* nsamp, int B,
+int stft_logamp(const void* wav, int is_i16, long n_samples, const long long* onset, const int* nsamp, int B,
                 const int* offsets, int T_max, int sumT, int n_fft, int hop, int center, const float* window,
                 float eps, float normalizer, float* out, long ld_out, cudaStream_t stream);
 int gradnorm_clip_sgd(float* params, float* grads, float* momentum_buf, long n, float lr, float momentum,

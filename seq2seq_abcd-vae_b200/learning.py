@@ -15,7 +15,7 @@ import itertools
 import json
 import math
 import os
-from logging import DEBUG, FileHandler, Formatter, getLogger
+from logging import DEBUG, FileHandler, Formatter, NullHandler, getLogger
 
 import numpy as np
 import torch
@@ -26,12 +26,23 @@ from .modules import data_utils, model
 logger = getLogger(__name__)
 
 
-def update_log_handler(file_dir):
-	"""(Re)attach <file_dir>/history.log; an existing log means the job is being resumed."""
+def _dist_rank_world(group=None):
+	if torch.distributed.is_available() and torch.distributed.is_initialized():
+		return torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
+	return 0, 1
+
+
+def update_log_handler(file_dir, write=True):
+	"""(Re)attach <file_dir>/history.log; an existing log means the job is being resumed.  With write=False (ranks > 0 of
+	a data-parallel job) the decision is the same but nothing is written: rank 0 owns history.log."""
 	for h in list(logger.handlers):
 		logger.removeHandler(h)
 	log_file_path = os.path.join(file_dir, 'history.log')
 	retrieval = os.path.isfile(log_file_path)
+	if not write:
+		logger.addHandler(NullHandler())
+		logger.setLevel(DEBUG)
+		return retrieval, log_file_path
 	handler = FileHandler(filename=log_file_path)
 	handler.setLevel(DEBUG)
 	handler.setFormatter(Formatter('{asctime} - {levelname} - {message}', style='{'))
@@ -86,51 +97,92 @@ class FlatArena(object):
 
 
 class Learner(object):
+	"""ABCD-VAE learner (reference: ABCD-VAE/learning.py:36-347).  The latent-variable part is factored into four small
+	hooks (_build_sampler, _sampler_from_checkpoint, _latent, _log_batch) so that plain/learning.py can swap in the isotropic
+	Gaussian latent of the reference's plain/ variant and share everything else."""
+	has_pretraining = True
+
 	def __init__(self, input_size, encoder_rnn_hidden_size, decoder_rnn_hidden_size, mlp_hidden_size, num_feature_categories,
 				feature_dim, save_dir, encoder_rnn_type='LSTM', decoder_rnn_type='LSTM', encoder_rnn_layers=1,
 				bidirectional_encoder=True, bidirectional_decoder=False, right2left_decoder_weight=0.5,
 				encoder_hidden_dropout=0.0, decoder_input_dropout=0.0, device='cuda', seed=1111,
 				emission_distribution='isotropic_gaussian', decoder_self_feedback=True, esn_leak=1.0, num_speakers=None,
 				speaker_embed_dim=None, prior_concentration=1.0, process_group=None):
-		self.save_dir = save_dir
-		self.process_group = process_group
-		self.retrieval, self.log_file_path = update_log_handler(save_dir) if save_dir is not None else (False, None)
-		if not str(device).startswith('cuda'):
-			raise ValueError('the B200 hot path has no CPU fallback: pass -d cuda (got {!r})'.format(device))
-		self.device = torch.device(device)
-		logger.info('Device: {device}'.format(device=device))
+		self._init_common(save_dir, device, process_group)
 		if self.retrieval:
 			self.last_epoch = self.retrieve_model(device=device)
 			logger.info('Model retrieved.')
-		else:
-			torch.manual_seed(seed)
-			torch.cuda.manual_seed_all(seed)
-			model.manual_noise_seed(seed)
-			if encoder_hidden_dropout > 0.0 and encoder_rnn_layers == 1:
-				logger.warning('Non-zero dropout cannot be used for the single-layer encoder RNN (because there is no non-top hidden layers).')
-				encoder_hidden_dropout = 0.0
-			# creation order encoder -> sampler -> decoder fixes the seeded initial weights (reference learning.py:90-92)
-			self.encoder = model.RNN_Variational_Encoder(input_size, encoder_rnn_hidden_size, rnn_type=encoder_rnn_type,
-														rnn_layers=encoder_rnn_layers, hidden_dropout=encoder_hidden_dropout,
-														bidirectional=bidirectional_encoder, esn_leak=esn_leak)
-			self.feature_sampler = model.ABCDSampler(self.encoder.hidden_size_total, mlp_hidden_size, num_feature_categories,
-													feature_dim, prior_concentration=prior_concentration)
-			self.decoder = model.RNN_Variational_Decoder(input_size, decoder_rnn_hidden_size, mlp_hidden_size, feature_dim,
-														emission_distr_name=emission_distribution, rnn_type=decoder_rnn_type,
-														input_dropout=decoder_input_dropout, self_feedback=decoder_self_feedback,
-														esn_leak=esn_leak, bidirectional=bidirectional_decoder,
-														right2left_weight=right2left_decoder_weight, num_speakers=num_speakers,
-														speaker_embed_dim=speaker_embed_dim)
-			logger.info('Data are encoded into one of {num_cat} possible {feature_dim}-dim feature vectors.'.format(num_cat=num_feature_categories, feature_dim=feature_dim))
-			logger.info('Random seed: {seed}'.format(seed=seed))
-			logger.info('Type of RNN used for the encoder: {rnn_type}'.format(rnn_type=encoder_rnn_type))
-			logger.info('Type of RNN used for the decoder: {rnn_type}'.format(rnn_type=decoder_rnn_type))
-			logger.info("# of hidden units in the encoder RNNs: {hs}".format(hs=encoder_rnn_hidden_size))
-			logger.info("# of hidden units in the decoder RNNs: {hs}".format(hs=decoder_rnn_hidden_size))
-			logger.info("# of hidden units in the MLPs: {hs}".format(hs=mlp_hidden_size))
-			self._place_on_device()
+			return
+		self._seed_everything(seed)
+		if encoder_hidden_dropout > 0.0 and encoder_rnn_layers == 1:
+			logger.warning('Non-zero dropout cannot be used for the single-layer encoder RNN (because there is no non-top hidden layers).')
+			encoder_hidden_dropout = 0.0
+		# creation order encoder -> sampler -> decoder fixes the seeded initial weights (reference learning.py:90-92)
+		self.encoder = model.RNN_Variational_Encoder(input_size, encoder_rnn_hidden_size, rnn_type=encoder_rnn_type,
+													rnn_layers=encoder_rnn_layers, hidden_dropout=encoder_hidden_dropout,
+													bidirectional=bidirectional_encoder, esn_leak=esn_leak)
+		self.feature_sampler = self._build_sampler(self.encoder.hidden_size_total, mlp_hidden_size, num_feature_categories,
+													feature_dim, prior_concentration)
+		self.decoder = model.RNN_Variational_Decoder(input_size, decoder_rnn_hidden_size, mlp_hidden_size, feature_dim,
+													emission_distr_name=emission_distribution, rnn_type=decoder_rnn_type,
+													input_dropout=decoder_input_dropout, self_feedback=decoder_self_feedback,
+													esn_leak=esn_leak, bidirectional=bidirectional_decoder,
+													right2left_weight=right2left_decoder_weight, num_speakers=num_speakers,
+													speaker_embed_dim=speaker_embed_dim)
+		logger.info('Random seed: {seed}'.format(seed=seed))
+		logger.info('Type of RNN used for the encoder: {rnn_type}'.format(rnn_type=encoder_rnn_type))
+		logger.info('Type of RNN used for the decoder: {rnn_type}'.format(rnn_type=decoder_rnn_type))
+		logger.info("# of hidden units in the encoder RNNs: {hs}".format(hs=encoder_rnn_hidden_size))
+		logger.info("# of hidden units in the decoder RNNs: {hs}".format(hs=decoder_rnn_hidden_size))
+		logger.info("# of hidden units in the MLPs: {hs}".format(hs=mlp_hidden_size))
+		self._place_on_device()
+
+	# -- latent-variable hooks (overridden by plain/learning.py) ------------------------------------------
+	def _build_sampler(self, hidden_size_total, mlp_hidden_size, num_feature_categories, feature_dim, prior_concentration):
+		logger.info('Data are encoded into one of {num_cat} possible {feature_dim}-dim feature vectors.'.format(num_cat=num_feature_categories, feature_dim=feature_dim))
+		logger.info('Discrete categories are assumed to be distributed according to Categorical(pi), with Dirichlet({}) prior on pi.'.format(prior_concentration))
+		return model.ABCDSampler(hidden_size_total, mlp_hidden_size, num_feature_categories, feature_dim, prior_concentration=prior_concentration)
+
+	def _sampler_from_checkpoint(self, init_parameters):
+		return model.ABCDSampler(**init_parameters)
+
+	def _latent(self, last_hidden, num_strings, is_pretraining):
+		"""-> (decoder input features, KL summed over the batch, category logits)  (learning.py:150-152)"""
+		category_logits = self.feature_sampler(last_hidden)
+		features = self.feature_sampler.sample(category_logits, no_sample=is_pretraining)
+		kl_loss = self.feature_sampler.kl_divergence(category_logits, num_strings)
+		return features, kl_loss, category_logits
+
+	def _log_batch(self, batch_ix, num_batches, loss, logits):
+		"""One read-back per batch: the loss and the three perplexities of learning.py:171-186 (with world_size > 1 the
+		perplexities are those of rank 0's shard of the batch)."""
+		stats = torch.cat([loss.detach().reshape(1), self.feature_sampler.perplexities(logits)]).tolist()
+		logger.info('{batch_ix}/{num_batches} training batches complete. mean loss: {loss:5.4f}. Perplexity of the posterior clustering probs.: {cluster_perplex:5.4f}. Perplexity of the mean clustering probs. over minibatch: {batch_perplex:5.4f}. Perplexity of the posterior Dirichlet shape: {shape_perplex:5.4f}'.format(
+			batch_ix=batch_ix, num_batches=num_batches, loss=stats[0], cluster_perplex=stats[1], batch_perplex=stats[2], shape_perplex=stats[3]))
 
 	# -- set-up -----------------------------------------------------------------------------------------
+	def _init_common(self, save_dir, device, process_group):
+		self.save_dir = save_dir
+		self.process_group = process_group
+		self.rank, self.world_size = _dist_rank_world(process_group)
+		if not str(device).startswith('cuda'):
+			raise ValueError('the B200 hot path has no CPU fallback: pass -d cuda (got {!r})'.format(device))
+		self.device = torch.device(device)
+		self.retrieval, self.log_file_path = False, None
+		if save_dir is not None:
+			# every rank decides "resume or fresh start" on the same file-system state, THEN rank 0 creates history.log
+			self.retrieval = os.path.isfile(os.path.join(save_dir, 'history.log'))
+			if self.world_size > 1:
+				torch.distributed.barrier(group=process_group)
+			_, self.log_file_path = update_log_handler(save_dir, write=self.rank == 0)
+		logger.info('Device: {device}'.format(device=device))
+
+	def _seed_everything(self, seed):
+		torch.manual_seed(seed)
+		torch.cuda.manual_seed_all(seed)
+		# in-kernel Philox noise: ranks of a data-parallel job draw from disjoint streams (SURVEY 8e)
+		model.manual_noise_seed(seed, stream=self.rank)
+
 	def _modules(self):
 		return (self.encoder, self.feature_sampler, self.decoder)
 
@@ -140,21 +192,17 @@ class Learner(object):
 			m.to(self.device)
 		self.parameters = lambda: itertools.chain.from_iterable(m.parameters() for m in self._modules())
 		self.arena = FlatArena(self._modules(), self.device)
-		self.world_size = 1
-		if self.process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-			self.world_size = torch.distributed.get_world_size(self.process_group)
+		self._n_enc_params = len(list(self.encoder.parameters()))
 
 	# -- one fused optimisation step ----------------------------------------------------------------------
 	def forward_losses(self, packed_input, is_offset, speaker, num_strings, is_pretraining, hidden_grad_hook=None):
-		"""Encoder -> sampler -> decoder; returns the three summed losses and the category logits.
+		"""Encoder -> sampler -> decoder; returns the three summed losses and the category logits (None for plain/).
 		`hidden_grad_hook` (optional) is registered on the encoder output: autograd calls it once the sampler's and the
 		decoder's backward have been enqueued and before the encoder's backward starts."""
 		last_hidden = self.encoder(packed_input)
 		if hidden_grad_hook is not None and last_hidden.requires_grad:
 			last_hidden.register_hook(hidden_grad_hook)
-		category_logits = self.feature_sampler(last_hidden)
-		features = self.feature_sampler.sample(category_logits, no_sample=is_pretraining)
-		kl_loss = self.feature_sampler.kl_divergence(category_logits, num_strings)
+		features, kl_loss, category_logits = self._latent(last_hidden, num_strings, is_pretraining)
 		emission_loss, end_prediction_loss, _, _, _ = self.decoder(
 			features, batch_sizes=packed_input.batch_sizes, speaker=speaker, ground_truth_out=packed_input.data,
 			ground_truth_offset=is_offset.data, return_outputs=False)
@@ -163,14 +211,17 @@ class Learner(object):
 	def train_step(self, packed_input, is_offset, speaker, num_strings, is_pretraining, global_batch_size=None):
 		"""forward + backward + (all-reduce) + clip + SGD for one (local shard of a) batch, all on the device.
 		Gradients are SUMS over segments divided by the GLOBAL batch size, so shards add up exactly
-		(reference: loss / batch_sizes[0], learning.py:155-158)."""
+		(reference: loss / batch_sizes[0], learning.py:155-158).  With world_size > 1 the caller passes this rank's shard and
+		`global_batch_size` (Learner.train does; a full batch on every rank would be summed world_size times)."""
 		self.arena.rebind()
 		pending = []
 		hook = None
 		if self.world_size > 1:
+			if global_batch_size is None:
+				raise ValueError('train_step under a process group needs global_batch_size (the batch must be sharded over the ranks)')
 			# the arena is laid out [encoder | sampler | decoder]: the sampler/decoder part of the gradient is final before the
 			# encoder's backward starts, so its all-reduce (5.8 of the 6.9 MB) overlaps the encoder BPTT and weight-gradient GEMMs
-			tail = self.arena.grad[self.arena.offsets[len(list(self.encoder.parameters()))]:]
+			tail = self.arena.grad[self.arena.offsets[self._n_enc_params]:]
 
 			def hook(grad):
 				pending.append(torch.distributed.all_reduce(tail, op=torch.distributed.ReduceOp.SUM, group=self.process_group, async_op=True))
@@ -183,7 +234,7 @@ class Learner(object):
 			loss.backward()
 		if self.world_size > 1:
 			if pending:
-				head = self.arena.grad[:self.arena.offsets[len(list(self.encoder.parameters()))]]
+				head = self.arena.grad[:self.arena.offsets[self._n_enc_params]]
 				torch.distributed.all_reduce(head, op=torch.distributed.ReduceOp.SUM, group=self.process_group)
 				for w in pending:
 					w.wait()
@@ -192,7 +243,7 @@ class Learner(object):
 		lr = self.optimizer.param_groups[0]['lr']
 		momentum = self.optimizer.param_groups[0]['momentum']
 		self.arena.clip_and_step(lr, momentum, self.gradient_clip)
-		if not is_pretraining:
+		if self.has_pretraining and not is_pretraining:
 			self.feature_sampler.increment_iter_counts()
 		return loss, emission_loss, end_loss, kl_loss, logits
 
@@ -203,7 +254,14 @@ class Learner(object):
 		speaker = speaker.to(self.device) if self.decoder.embed_speaker is not None else None
 		return packed_input, is_offset, speaker
 
+	def _reduce_totals(self, totals):
+		if self.world_size > 1:
+			torch.distributed.all_reduce(totals, op=torch.distributed.ReduceOp.SUM, group=self.process_group)
+		return totals
+
 	def train(self, dataloader, is_pretraining=False):
+		"""One epoch.  Under a process group the DataLoader hands every rank its strided shard of each length-sorted batch
+		(data_utils.DataLoader(rank, world_size)); losses are divided by the global batch size and summed over ranks."""
 		for m in self._modules():
 			m.train()
 		num_batches = dataloader.get_num_batches()
@@ -211,12 +269,15 @@ class Learner(object):
 		totals = torch.zeros(3, dtype=torch.float64, device=self.device)
 		for batch_ix, (packed_input, is_offset, speaker, _) in enumerate(dataloader, 1):
 			packed_input, is_offset, speaker = self._move(packed_input, is_offset, speaker)
-			loss, em, end, kl, logits = self.train_step(packed_input, is_offset, speaker, num_strings, is_pretraining)
-			totals += torch.stack([em.detach(), end.detach(), kl.detach()]).double()
-			stats = torch.cat([loss.detach().reshape(1), self.feature_sampler.perplexities(logits)]).tolist()   # one read-back
-			logger.info('{batch_ix}/{num_batches} training batches complete. mean loss: {loss:5.4f}. Perplexity of the posterior clustering probs.: {cluster_perplex:5.4f}. Perplexity of the mean clustering probs. over minibatch: {batch_perplex:5.4f}. Perplexity of the posterior Dirichlet shape: {shape_perplex:5.4f}'.format(
-				batch_ix=batch_ix, num_batches=num_batches, loss=stats[0], cluster_perplex=stats[1], batch_perplex=stats[2], shape_perplex=stats[3]))
-		return self._log_epoch('training', totals, num_strings)
+			gb = dataloader.last_global_batch_size if self.world_size > 1 else None
+			loss, em, end, kl, logits = self.train_step(packed_input, is_offset, speaker, num_strings, is_pretraining, global_batch_size=gb)
+			part = torch.stack([em.detach(), end.detach(), kl.detach()]).double()
+			totals += part / self.world_size if getattr(dataloader, 'last_replicated', False) else part
+			if self.world_size > 1:
+				loss = loss.detach().clone()
+				torch.distributed.all_reduce(loss, op=torch.distributed.ReduceOp.SUM, group=self.process_group)
+			self._log_batch(batch_ix, num_batches, loss, logits)
+		return self._log_epoch('training', self._reduce_totals(totals), num_strings)
 
 	def _log_epoch(self, phase, totals, num_strings):
 		emission_loss, end_prediction_loss, kl_loss = (totals / num_strings).tolist()
@@ -225,7 +286,7 @@ class Learner(object):
 		logger.info('mean {} end-prediction loss (per string): {:5.4f}'.format(phase, end_prediction_loss))
 		logger.info('mean {} KL (per string): {:5.4f}'.format(phase, kl_loss))
 		logger.info('mean {} total loss (per string): {:5.4f}'.format(phase, mean_loss))
-		if phase == 'training':
+		if phase == 'training' and self.has_pretraining:
 			self.feature_sampler.update_epoch_init_iter_counts()
 		return mean_loss
 
@@ -240,9 +301,10 @@ class Learner(object):
 			for batch_ix, (packed_input, is_offset, speaker, _) in enumerate(dataloader, 1):
 				packed_input, is_offset, speaker = self._move(packed_input, is_offset, speaker)
 				em, end, kl, _ = self.forward_losses(packed_input, is_offset, speaker, num_strings, is_pretraining)
-				totals += torch.stack([em, end, kl]).double()
+				part = torch.stack([em, end, kl]).double()
+				totals += part / self.world_size if getattr(dataloader, 'last_replicated', False) else part
 				logger.info('{batch_ix}/{num_batches} validation batches complete.'.format(batch_ix=batch_ix, num_batches=num_batches))
-		return self._log_epoch('validation', totals, num_strings)
+		return self._log_epoch('validation', self._reduce_totals(totals), num_strings)
 
 	def setup_optimizer(self, learning_rate, momentum, gradient_clip=None, patience=0):
 		"""torch.optim.SGD / ReduceLROnPlateau are kept as host-side bookkeeping (lr, state_dict layout of the
@@ -252,17 +314,44 @@ class Learner(object):
 			self.optimizer.load_state_dict(self.checkpoint['optimizer'])
 			self.lr_scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(self.optimizer)
 			self.lr_scheduler.load_state_dict(self.checkpoint['lr_scheduler'])
-			mb = self.checkpoint.get('momentum_arena')
-			if mb is not None:
-				self.arena.momentum_buf = mb.to(self.device)
+			self._momentum_from_optimizer_state()
 		else:
 			self.lr_scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(self.optimizer, patience=patience)
 			self.gradient_clip = gradient_clip
 
+	def _momentum_from_optimizer_state(self):
+		"""Fill the flat momentum arena from torch.optim.SGD's per-parameter `momentum_buffer`s -- the form in which both the
+		reference's checkpoints and ours carry momentum (learning.py:306-307)."""
+		found = False
+		for p, o in zip(self.arena.params, self.arena.offsets):
+			buf = self.optimizer.state.get(p, {}).get('momentum_buffer')
+			if buf is None:
+				continue
+			if self.arena.momentum_buf is None:
+				self.arena.momentum_buf = torch.zeros_like(self.arena.flat)
+			self.arena.momentum_buf[o:o + p.numel()].copy_(buf.reshape(-1).to(self.device))
+			found = True
+		self.optimizer.state.clear()   # the arena is the live copy from here on
+		return found
+
+	def _momentum_to_optimizer_state(self):
+		"""Expose the momentum arena as per-parameter `momentum_buffer`s so that optimizer.state_dict() has the reference's
+		layout (a reference Learner can resume from our checkpoint and vice versa)."""
+		if self.arena.momentum_buf is None:
+			return
+		for p, o in zip(self.arena.params, self.arena.offsets):
+			self.optimizer.state[p]['momentum_buffer'] = self.arena.momentum_buf[o:o + p.numel()].view(p.shape).clone()
+
+	def _make_dataloaders(self, train_dataset, valid_dataset, batch_size_train, batch_size_valid):
+		train_dataloader = data_utils.DataLoader(train_dataset, batch_size=batch_size_train, shuffle=True, device=self.device,
+												rank=self.rank, world_size=self.world_size)
+		valid_dataloader = data_utils.DataLoader(valid_dataset, batch_size=batch_size_valid, device=self.device,
+												rank=self.rank, world_size=self.world_size)
+		return train_dataloader, valid_dataloader
+
 	def learn(self, train_dataset, valid_dataset, num_epochs, batch_size_train, batch_size_valid, pretrain_epochs=0,
 			learning_rate=0.1, momentum=0.9, gradient_clip=0.25, patience=0):
-		train_dataloader = data_utils.DataLoader(train_dataset, batch_size=batch_size_train, shuffle=True, device=self.device)
-		valid_dataloader = data_utils.DataLoader(valid_dataset, batch_size=batch_size_valid, device=self.device)
+		train_dataloader, valid_dataloader = self._make_dataloaders(train_dataset, valid_dataset, batch_size_train, batch_size_valid)
 		self.setup_optimizer(learning_rate, momentum, gradient_clip, patience)
 		if self.retrieval:
 			initial_epoch = self.last_epoch + 1
@@ -271,7 +360,8 @@ class Learner(object):
 			initial_epoch = 1
 			logger.info("START LEARNING.")
 			logger.info("max # of epochs: {ep}".format(ep=num_epochs))
-			logger.info("first {} epochs are for pretraining w/o gumbel-softmax sampling.".format(pretrain_epochs))
+			if self.has_pretraining:
+				logger.info("first {} epochs are for pretraining w/o gumbel-softmax sampling.".format(pretrain_epochs))
 			logger.info("batch size for training data: {size}".format(size=batch_size_train))
 			logger.info("batch size for validation data: {size}".format(size=batch_size_valid))
 			logger.info("initial learning rate: {lr}".format(lr=learning_rate))
@@ -280,7 +370,7 @@ class Learner(object):
 		for epoch in range(initial_epoch, num_epochs + 1):
 			logger.info('START OF EPOCH: {:3d}'.format(epoch))
 			logger.info('current learning rate: {lr}'.format(lr=self.optimizer.param_groups[0]['lr']))
-			is_pretrain = epoch <= pretrain_epochs
+			is_pretrain = self.has_pretraining and epoch <= pretrain_epochs
 			logger.info('start of TRAINING phase.')
 			self.train(train_dataloader, is_pretrain)
 			logger.info('end of TRAINING phase.')
@@ -288,7 +378,7 @@ class Learner(object):
 			mean_valid_loss = self.test_or_validate(valid_dataloader, is_pretrain)
 			logger.info('end of VALIDATION phase.')
 			self.lr_scheduler.step(mean_valid_loss)
-			if epoch == pretrain_epochs:
+			if self.has_pretraining and epoch == pretrain_epochs:
 				self.lr_scheduler.best = math.inf   # forget the pretraining optimum
 				logger.info('END OF PRETRAINING.')
 			self.save_model(epoch)
@@ -297,34 +387,40 @@ class Learner(object):
 
 	# -- checkpoints (same dict keys as the reference, learning.py:298-313) -------------------------------
 	def save_model(self, epoch):
-		checkpoint = {
-			'epoch': epoch,
-			'encoder': {k: v.detach().cpu().clone() for k, v in self.encoder.state_dict().items()},
-			'encoder_init_parameters': self.encoder.pack_init_parameters(),
-			'feature_sampler': {k: v.detach().cpu().clone() for k, v in self.feature_sampler.state_dict().items()},
-			'feature_sampler_init_parameters': self.feature_sampler.pack_init_parameters(),
-			'decoder': {k: v.detach().cpu().clone() for k, v in self.decoder.state_dict().items()},
-			'decoder_init_parameters': self.decoder.pack_init_parameters(),
-			'optimizer': self.optimizer.state_dict(),
-			'lr_scheduler': self.lr_scheduler.state_dict(),
-			'gradient_clip': self.gradient_clip,
-			'random_state': torch.get_rng_state(),
-			'random_state_cuda': torch.cuda.get_rng_state_all(),
-			'noise_state': dict(model._noise_state),
-		}
-		if self.arena.momentum_buf is not None:
-			checkpoint['momentum_arena'] = self.arena.momentum_buf.cpu()
-		torch.save(checkpoint, os.path.join(self.save_dir, 'checkpoint.pt'))
-		logger.info('Config successfully saved.')
+		"""checkpoint.pt with the reference's keys; momentum travels as optimizer.state[...]['momentum_buffer'] like torch's
+		own SGD.  Under a process group only rank 0 writes (parameters are replicated) and everybody waits for the file."""
+		if self.rank == 0:
+			self._momentum_to_optimizer_state()
+			checkpoint = {
+				'epoch': epoch,
+				'encoder': {k: v.detach().cpu().clone() for k, v in self.encoder.state_dict().items()},
+				'encoder_init_parameters': self.encoder.pack_init_parameters(),
+				'feature_sampler': {k: v.detach().cpu().clone() for k, v in self.feature_sampler.state_dict().items()},
+				'feature_sampler_init_parameters': self.feature_sampler.pack_init_parameters(),
+				'decoder': {k: v.detach().cpu().clone() for k, v in self.decoder.state_dict().items()},
+				'decoder_init_parameters': self.decoder.pack_init_parameters(),
+				'optimizer': self.optimizer.state_dict(),
+				'lr_scheduler': self.lr_scheduler.state_dict(),
+				'gradient_clip': self.gradient_clip,
+				'random_state': torch.get_rng_state(),
+				'random_state_cuda': torch.cuda.get_rng_state_all(),
+				'noise_state': dict(model._noise_state),   # in-kernel Philox stream (not in the reference; ignored by it)
+			}
+			torch.save(checkpoint, os.path.join(self.save_dir, 'checkpoint.pt'))
+			self.optimizer.state.clear()
+			logger.info('Config successfully saved.')
+		if self.world_size > 1:
+			torch.distributed.barrier(group=self.process_group)
 
 	def retrieve_model(self, checkpoint_path=None, device='cuda'):
+		"""Loads checkpoints written by this Learner or by the reference's (learning.py:315-347): same keys; a reference
+		checkpoint simply lacks 'noise_state'."""
 		if checkpoint_path is None:
 			checkpoint_path = os.path.join(self.save_dir, 'checkpoint.pt')
 		self.checkpoint = torch.load(checkpoint_path, map_location='cpu', weights_only=False)
-		dec_init = dict(self.checkpoint['decoder_init_parameters'])
 		self.encoder = model.RNN_Variational_Encoder(**self.checkpoint['encoder_init_parameters'])
-		self.feature_sampler = model.ABCDSampler(**self.checkpoint['feature_sampler_init_parameters'])
-		self.decoder = model.RNN_Variational_Decoder(**dec_init)
+		self.feature_sampler = self._sampler_from_checkpoint(dict(self.checkpoint['feature_sampler_init_parameters']))
+		self.decoder = model.RNN_Variational_Decoder(**dict(self.checkpoint['decoder_init_parameters']))
 		self.encoder.load_state_dict(self.checkpoint['encoder'], strict=False)
 		self.feature_sampler.load_state_dict(self.checkpoint['feature_sampler'])
 		self.decoder.load_state_dict(self.checkpoint['decoder'])
@@ -334,8 +430,12 @@ class Learner(object):
 			torch.set_rng_state(self.checkpoint['random_state'])
 		except RuntimeError:
 			logger.warning('Failed to retrieve random_state.')
+		cuda_states = self.checkpoint.get('random_state_cuda')
+		if cuda_states is not None and len(cuda_states) == torch.cuda.device_count():
+			torch.cuda.set_rng_state_all(cuda_states)   # (unused by the kernels: their noise is the Philox stream below)
 		if 'noise_state' in self.checkpoint:
 			model._noise_state.update(self.checkpoint['noise_state'])
+			model._noise_state['stream'] = getattr(self, 'rank', 0)
 		return self.checkpoint['epoch']
 
 

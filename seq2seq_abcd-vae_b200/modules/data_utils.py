@@ -66,6 +66,7 @@ class Dataset(torch.utils.data.Dataset):
 		self.device = torch.device(device) if device is not None else None
 		self._wav_host = {}
 		self._wav_dev = {}
+		self._corpus = {}   # device -> (one buffer holding every referenced wav back to back, {path: first sample})
 		self.get_discrete_bounds()
 
 	def _wav(self, input_path):
@@ -87,6 +88,29 @@ class Dataset(torch.utils.data.Dataset):
 				t = torch.from_numpy(data.astype(np.float32))
 			self._wav_dev[key] = t.to(device)
 		return self._wav_dev[key]
+
+	def corpus_on_device(self, device):
+		"""All wav files this dataset references, decoded once and stored back to back in ONE device buffer (int16 when every
+		file is int16, else float32), with the first-sample index of each file.  Batches that touch several files then need no
+		per-batch concatenation: segment onsets are rebased with int64 arithmetic and the STFT kernel reads the corpus directly.
+		Host copies are dropped once uploaded (the device buffer is the cache; 180 GB of HBM holds ~780 h of 16 kHz int16)."""
+		key = str(device)
+		if key not in self._corpus:
+			paths = list(dict.fromkeys(self.df_annotation['input_path'].tolist()))
+			arrays = [self._wav(p) for p in paths]
+			all_i16 = all(a.dtype == np.int16 for a in arrays)
+			base, off = {}, 0
+			for p, a in zip(paths, arrays):
+				base[p] = off
+				off += int(a.shape[0])
+			buf = torch.empty(off, dtype=torch.int16 if all_i16 else torch.float32, device=device)
+			for p, a in zip(paths, arrays):
+				t = torch.from_numpy(a if all_i16 else a.astype(np.float32))
+				buf[base[p]:base[p] + t.numel()].copy_(t)
+			self._corpus[key] = (buf, base)
+			self._file_len = {p: int(a.shape[0]) for p, a in zip(paths, arrays)}
+			self._wav_host.clear()
+		return self._corpus[key]
 
 	def get_discrete_bounds(self):
 		"""onset/offset in samples = round-half-even(seconds * fs); length = offset_ix - onset_ix (in samples)."""
@@ -143,7 +167,9 @@ class Transform(object):
 
 
 def _stft_launch(wav, onset, nsamp, desc, frame_length, step_size, centering, window, eps, normalizer, out):
+	"""onset: int64 [B] first sample of each segment in `wav`; nsamp: int32 [B] samples per segment (both on the device)."""
 	L.ensure_device(out.device)
+	assert onset.dtype == torch.int64 and nsamp.dtype == torch.int32
 	L.call('abcd_stft_logamp', L.ptr(wav), int(wav.dtype == torch.int16), wav.numel(), L.ptr(onset), L.ptr(nsamp), desc.ref(),
 		int(frame_length), int(step_size), int(bool(centering)), L.ptr(window), float(eps), float(normalizer),
 		L.ptr(out), out.shape[1], L.stream_ptr())
@@ -181,7 +207,7 @@ class STFT(object):
 		n = wav.numel()
 		T = self.num_frames(n)
 		desc = L.Packed(torch.ones(T, dtype=torch.int64), dev)
-		onset = torch.zeros(1, dtype=torch.int32, device=dev)
+		onset = torch.zeros(1, dtype=torch.int64, device=dev)
 		nsamp = torch.full((1,), n, dtype=torch.int32, device=dev)
 		out = torch.empty(T, self.frame_length // 2 + 1, dtype=torch.float32, device=dev)
 		# normalizer == 0 selects the plain-amplitude output of the kernel
@@ -229,9 +255,15 @@ class DataLoader(object):
 	"""Yields (packed log-STFT, packed is_offset, speakers, indices) per batch, like the reference's DataLoader
 	(data_utils.py:150-185): batches come from a BatchSampler (drop_last=False) and are consumed from the end."""
 
-	def __init__(self, dataset, batch_size=1, shuffle=False, device=None):
+	def __init__(self, dataset, batch_size=1, shuffle=False, device=None, rank=0, world_size=1):
+		"""rank / world_size (not in the reference): under data parallelism every rank draws the SAME batches (same torch
+		seed) and keeps the strided shard rank, rank + world_size, ... of each length-sorted batch (dist.shard_sorted_batch),
+		so only its own segments go through the STFT; `last_global_batch_size` is the divisor of the loss."""
 		self.dataset = dataset
 		self.shuffle = shuffle
+		self.rank, self.world_size = int(rank), int(world_size)
+		self.last_global_batch_size = None
+		self.last_replicated = False
 		if shuffle:
 			sampler = torch.utils.data.RandomSampler(self.dataset, replacement=False)
 		else:
@@ -252,6 +284,15 @@ class DataLoader(object):
 			raise StopIteration
 		ixs = self.batches.pop()
 		ixs = self.dataset.sort_indices_by_length(ixs)
+		self.last_global_batch_size = len(ixs)
+		self.last_replicated = False
+		if self.world_size > 1:
+			if len(ixs) >= self.world_size:
+				ixs = ixs[self.rank::self.world_size]
+			else:
+				# fewer segments than ranks (tail batch): every rank takes all of them and the divisor grows accordingly
+				self.last_global_batch_size = len(ixs) * self.world_size
+				self.last_replicated = True
 		fused = self._fused_transform()
 		if fused is not None:
 			batched_input, is_offset = self._next_fused(ixs, fused)
@@ -276,26 +317,16 @@ class DataLoader(object):
 		desc = L.Packed(batch_sizes, dev)
 		F = stft.frame_length // 2 + 1
 		out = torch.empty(desc.sumT, F, dtype=torch.float32, device=dev)
-		# one launch per distinct wav file (segments of other files are given zero frames by masking nsamp)
-		uniq = list(dict.fromkeys(paths))
-		if len(uniq) == 1:
-			wav = self.dataset.wav_on_device(uniq[0], dev)
-			meta = torch.from_numpy(np.stack([onset, nsamp]).astype(np.int32)).to(dev)
-			_stft_launch(wav, meta[0], meta[1], desc, stft.frame_length, stft.step_size, stft.centering, stft.window_on(dev),
-						fused.epsilon, fused.normalizer, out)
-		else:
-			# concatenate the needed files into one device buffer and rebase onsets
-			base, parts, off = {}, [], 0
-			for p in uniq:
-				w = self.dataset.wav_on_device(p, dev)
-				base[p] = off
-				parts.append(w if w.dtype == torch.float32 else w.float())
-				off += w.numel()
-			wav = torch.cat(parts)
-			onset = onset + np.array([base[p] for p in paths], dtype=np.int64)
-			meta = torch.from_numpy(np.stack([onset, nsamp]).astype(np.int32)).to(dev)
-			_stft_launch(wav, meta[0], meta[1], desc, stft.frame_length, stft.step_size, stft.centering, stft.window_on(dev),
-						fused.epsilon, fused.normalizer, out)
+		# every wav file of the dataset lives back to back in one device buffer: rebase the onsets (int64) and launch once
+		wav, base = self.dataset.corpus_on_device(dev)
+		file_len = np.array([self.dataset._file_len[p] for p in paths], dtype=np.int64)
+		if (onset < 0).any() or (onset + nsamp > file_len).any() or int(nsamp.max()) > np.iinfo(np.int32).max:
+			raise ValueError('annotation bounds lie outside the decoded audio of {}'.format(sorted(set(paths[(onset + nsamp > file_len) | (onset < 0)]))))
+		onset = onset + np.array([base[p] for p in paths], dtype=np.int64)
+		onset_d = torch.from_numpy(onset).to(dev)
+		nsamp_d = torch.from_numpy(nsamp.astype(np.int32)).to(dev)
+		_stft_launch(wav, onset_d, nsamp_d, desc, stft.frame_length, stft.step_size, stft.centering, stft.window_on(dev),
+					fused.epsilon, fused.normalizer, out)
 		# is_offset: 1.0 at each segment's last frame = packed index offsets[len-1] + b
 		is_off = torch.zeros(desc.sumT, dtype=torch.float32, device=dev)
 		last = desc.offsets_cpu[desc.lengths_cpu - 1] + torch.arange(desc.B)

@@ -111,13 +111,20 @@ def choose_distribution(distribution_name):
 	return (sample_from_isotropic_gaussian, log_pdf_isotropic_gaussian, kl_isotropic_to_standard_gaussian, 2)
 
 
-_noise_state = {'seed': 0x5EED, 'offset': 0}
+_noise_state = {'seed': 0x5EED, 'offset': 0, 'stream': 0}
 
 
-def manual_noise_seed(seed):
-	"""Seed of the in-kernel Philox stream used for Gumbel / emission noise."""
+def manual_noise_seed(seed, stream=0):
+	"""Seed of the in-kernel Philox stream used for Gumbel / emission noise.  `stream` selects one of 2^64 disjoint key
+	streams under the same seed: data-parallel ranks pass their rank, so different shards of a batch never see the same
+	draws (the reference has one process and one torch generator)."""
 	_noise_state['seed'] = int(seed) & 0xFFFFFFFFFFFFFFFF
 	_noise_state['offset'] = 0
+	_noise_state['stream'] = int(stream)
+
+
+def _noise_key():
+	return (_noise_state['seed'] ^ ((_noise_state.get('stream', 0) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF
 
 
 def noise_like(t, kind='normal'):
@@ -126,7 +133,7 @@ def noise_like(t, kind='normal'):
 	out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
 	n = out.numel()
 	fn = 'abcd_philox_normal' if kind == 'normal' else 'abcd_philox_gumbel'
-	L.call(fn, L.ptr(out), n, _noise_state['seed'], _noise_state['offset'], L.stream_ptr())
+	L.call(fn, L.ptr(out), n, _noise_key(), _noise_state['offset'], L.stream_ptr())
 	_noise_state['offset'] += (n + 3) // 4
 	return out
 
@@ -248,6 +255,17 @@ class Sampler(torch.nn.Module):
 
 	def kl_divergence(self, parameters):
 		return self._kl_divergence(*parameters)
+
+	def sample_and_kl(self, parameters):
+		"""sample() and kl_divergence() of the same parameters in ONE fused kernel (plain/learning.py:148-149 calls them back
+		to back): z = mean + exp(0.5 lv) eps and KL(N(mean, e^lv) || N(0, I)) summed over the batch.  `injected_noise`
+		(parity hook) supplies eps for the next call; otherwise it is drawn from the Philox stream."""
+		mean, log_variance = parameters
+		eps = getattr(self, 'injected_noise', None)
+		self.injected_noise = None
+		if eps is None:
+			eps = noise_like(mean)
+		return _GaussLatentFn.apply(mean, log_variance, _f32(eps))
 
 	def log_pdf(self, samples, parameters):
 		return self._log_pdf(samples, *parameters)

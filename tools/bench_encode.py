@@ -43,7 +43,7 @@ def main():
 	# audio for the front end
 	n_fft, hop = 2 * (F - 1), F - 1
 	nsamp = torch.tensor([(int(l) - 1) * hop + hop // 2 for l in lengths], dtype=torch.int32)
-	onset = torch.cumsum(torch.cat([torch.zeros(1, dtype=torch.int64), nsamp[:-1].long()]), 0).to(torch.int32).to(dev)
+	onset = torch.cumsum(torch.cat([torch.zeros(1, dtype=torch.int64), nsamp[:-1].long()]), 0).to(dev)
 	wav = torch.from_numpy(np.random.RandomState(5).randint(-3000, 3000, size=int(nsamp.sum())).astype(np.int16)).to(dev)
 	nsamp = nsamp.to(dev)
 	desc = pkg.model.as_packed_desc(bs, dev)
