@@ -95,9 +95,11 @@ int abcd_debug_enc_timing(unsigned long long* out10);
 /* same for the last dec_fwd launch: out16[0..9] = P1 setup, P1 gemm, P1 cell, barrier, P2 gemm, P2 store, barrier, P3 setup+gemm,
  * P3 sample, barrier; out16[10..14] = breakdown of the P1 gemm; out16[15] = steps */
 int abcd_debug_dec_timing(unsigned long long* out16);
-/* probe (tools/ts_probe.py): D[128,N] = A[128,K] B[K,N] with the A operand of tcgen05.mma read from tensor memory (TS form),
- * single-pass TF32; variant bit 0 selects the a_major bit of the instruction descriptor */
-int abcd_debug_ts_probe(const float* A, const float* B, float* D, int K, int N, int variant, void* stream);
+/* measurement (bench.py "latency_roofline"): nanoseconds per round of the publish -> cluster barrier -> consume exchange that
+ * every phase of the persistent recurrent kernels performs, on ONE cluster of `cluster_size` CTAs x 256 threads.
+ * mode 0: barrier only; 1: one token through L2 per round; 2: 16-way fan-in of a 128-byte row per CTA.
+ * out2[0] = ns per round (device float), scratch >= 16*32 floats. */
+int abcd_measure_cluster_exchange(int cluster_size, int iters, int mode, float* out2, float* scratch, void* stream);
 /* Recurrent contractions of the encoder forward / backward and the decoder backward (model.py:60-66, 165-196): on the tensor
  * cores (tcgen05 kind::tf32, weights resident in tensor memory, 3xTF32 split, fp32-grade; default) or on the FFMA path.  on = 1/0; -1 only queries.  Returns
  * the previous setting.  Initial value: env ABCD_RNN_TC (default 1). */
@@ -179,6 +181,16 @@ int abcd_gradnorm_clip_sgd(float* params, float* grads, float* momentum_buf /*or
 /* ---- noise --------------------------------------------------------------------------------------- */
 int abcd_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
 int abcd_philox_gumbel(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+
+/* ---- Encoder.encode_dataset (encode.py:38-55): host-side long-format CSV rows of one batch ------------- */
+/* Category-major like DataFrame.melt: for k < K, for b < B: "<h_data_ix[b]>,<k>,<h_vals[b*ld+k]><suffix b>\n", the value
+ * printed as pandas.to_csv prints a float32 (shortest round-trip digits; scientific outside [1e-4, 1e6)).  h_suffix /
+ * h_suffix_off ([B+1] byte offsets; both may be NULL) carry the pre-formatted annotation cells of each segment including
+ * their leading comma.  ALL pointers are HOST pointers.  Returns the number of bytes written to h_out, or a negative
+ * error code; h_out must hold B*K*abcd_csv_row_bound(longest suffix) bytes. */
+int64_t abcd_csv_row_bound(int64_t max_suffix_bytes);
+int64_t abcd_csv_format_long(const float* h_vals, int32_t B, int32_t K, int64_t ld, const int64_t* h_data_ix,
+                             const char* h_suffix, const int64_t* h_suffix_off, char* h_out, int64_t out_cap);
 
 /* ---- generic fp32 GEMM (exposed for tests): C[M,N] = alpha * A * B (+bias)(tanh) -------------------- */
 int abcd_sgemm(int M, int N, int K, const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor,

@@ -387,8 +387,10 @@ def clip_and_sgd(params, grads, lr, max_norm, momentum=0.0, bufs=None):
 # one full training step (learning.py:147-163)
 # ---------------------------------------------------------------------------------------------------
 def train_step(enc_P, smp_P, dec_P, seqs, eps, gumbel, entire_data_size, is_pretraining, tau=1.0, rnn_type='LSTM',
-				prior_concentration=1.0, speaker=None, global_batch=None, batched=False):
-	"""Forward + backward of one batch; returns dict(losses, logits, grads per module)."""
+				prior_concentration=1.0, speaker=None, global_batch=None, batched=False, latent='abcd'):
+	"""Forward + backward of one batch; returns dict(losses, logits, grads per module).
+	latent='gaussian' is the plain/ variant (plain/learning.py:147-149): smp_P holds the two MLPs of plain Sampler and
+	`gumbel` carries the N(0,1) draws [B, f] of the latent sample."""
 	leaves = {}
 	for name, P in (('encoder', enc_P), ('feature_sampler', smp_P), ('decoder', dec_P)):
 		leaves[name] = {k: v.clone().requires_grad_(v.dtype.is_floating_point and k != 'prior_concentration') for k, v in P.items()}
@@ -398,9 +400,13 @@ def train_step(enc_P, smp_P, dec_P, seqs, eps, gumbel, entire_data_size, is_pret
 		last_hidden = encoder_forward_batched(data, bs, enc_keys, rnn_type)
 	else:
 		last_hidden = encoder_forward(seqs, enc_keys, rnn_type)
-	logits = sampler_logits(last_hidden, leaves['feature_sampler'])
-	feats, y = sampler_sample(logits, leaves['feature_sampler'], is_pretraining, tau, gumbel)
-	kl = sampler_kl(logits, leaves['feature_sampler'], entire_data_size, prior_concentration)
+	if latent == 'gaussian':
+		feats, kl, z_mean, _ = gauss_latent(last_hidden, leaves['feature_sampler'], gumbel)
+		logits = z_mean
+	else:
+		logits = sampler_logits(last_hidden, leaves['feature_sampler'])
+		feats, y = sampler_sample(logits, leaves['feature_sampler'], is_pretraining, tau, gumbel)
+		kl = sampler_kl(logits, leaves['feature_sampler'], entire_data_size, prior_concentration)
 	is_off = is_offset_packed(bs).to(data.dtype)
 	em, off, x_all, mean, lv, off_logit = decoder_forward(feats, bs, leaves['decoder'], eps, data, is_off, rnn_type, speaker)
 	B = global_batch if global_batch is not None else bs[0]

@@ -25,6 +25,12 @@ EXTRA_CASES = {
 	'train_gru_f129_speaker': dict(rnn='GRU', F=129, K=32, f=64, lengths=[12, 12, 9, 4, 4, 4, 2, 1, 1], pretrain=False, tau=0.7, N_data=9, seed=8,
 								num_speakers=4, E=256),
 }
+# plain/ variant (Gaussian latent, BASELINE.json configs[1]); `f` is the latent size (plain/learning.py -f, default 16)
+PLAIN_CASES = {
+	'train_plain_lstm': dict(rnn='LSTM', F=65, f=16, lengths=[12, 9, 9, 5, 2, 1], seed=11, latent='gaussian', pretrain=False, tau=1.0, N_data=6, K=16),
+	'train_plain_gru_speaker': dict(rnn='GRU', F=65, f=16, lengths=[10, 7, 7, 3], seed=12, latent='gaussian', pretrain=False, tau=1.0, N_data=4, K=16,
+									num_speakers=3, E=256),
+}
 SAMPLE_STRIDE = 101
 
 
@@ -57,7 +63,10 @@ def build_modules(model_module, cfg):
 	"""Instantiate encoder / ABCD sampler / decoder from `model_module` (the reference's model.py or the B200
 	package's) for a case."""
 	enc = model_module.RNN_Variational_Encoder(cfg['F'], 256, rnn_type=cfg['rnn'])
-	smp = model_module.ABCDSampler(enc.hidden_size_total, 256, cfg['K'], cfg['f'])
+	if cfg.get('latent') == 'gaussian':
+		smp = model_module.Sampler(enc.hidden_size_total, 256, cfg['f'])
+	else:
+		smp = model_module.ABCDSampler(enc.hidden_size_total, 256, cfg['K'], cfg['f'])
 	dec = model_module.RNN_Variational_Decoder(cfg['F'], 256, 256, cfg['f'], rnn_type=cfg['rnn'],
 												num_speakers=cfg.get('num_speakers'), speaker_embed_dim=cfg.get('E'))
 	return enc, smp, dec
@@ -70,7 +79,10 @@ def build_case(cfg, modules):
 	seqs = make_inputs(cfg['lengths'], cfg['F'], s)
 	sumT = sum(cfg['lengths'])
 	eps = O.det_tensor((sumT, cfg['F']), s * 7 + 5, 'normal', 1.0)
-	gumbel = O.det_tensor((len(cfg['lengths']), cfg['K']), s * 7 + 6, 'gumbel', 1.0)
+	if cfg.get('latent') == 'gaussian':   # N(0,1) draws of the latent sample take the place of the Gumbel noise
+		gumbel = O.det_tensor((len(cfg['lengths']), cfg['f']), s * 7 + 6, 'normal', 1.0)
+	else:
+		gumbel = O.det_tensor((len(cfg['lengths']), cfg['K']), s * 7 + 6, 'gumbel', 1.0)
 	speaker = None
 	if cfg.get('num_speakers'):
 		speaker = torch.tensor([(i * 2 + 1) % cfg['num_speakers'] for i in range(len(cfg['lengths']))])

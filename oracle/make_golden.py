@@ -38,14 +38,17 @@ def load_reference_model(package='ABCD-VAE'):
 
 
 def run_reference_step(ref, cfg, enc_sd, smp_sd, dec_sd, seqs, eps, gumbel, speaker):
+	gaussian = cfg.get('latent') == 'gaussian'
 	enc = ref.RNN_Variational_Encoder(cfg['F'], 256, rnn_type=cfg['rnn'])
-	smp = ref.ABCDSampler(enc.hidden_size_total, 256, cfg['K'], cfg['f'])
+	smp = ref.Sampler(enc.hidden_size_total, 256, cfg['f']) if gaussian else ref.ABCDSampler(enc.hidden_size_total, 256, cfg['K'], cfg['f'])
 	dec = ref.RNN_Variational_Decoder(cfg['F'], 256, 256, cfg['f'], rnn_type=cfg['rnn'],
 										num_speakers=cfg.get('num_speakers'), speaker_embed_dim=cfg.get('E'))
 	if dec.embed_speaker is not None:
 		dec.embed_speaker = torch.nn.Embedding(cfg['num_speakers'], cfg['E'], sparse=False)
 	enc.load_state_dict(enc_sd); smp.load_state_dict(smp_sd); dec.load_state_dict(dec_sd)
 	smp.temperature = cfg['tau']
+	if gaussian:
+		smp._sampler = lambda mean, log_variance: mean + (0.5 * log_variance).exp() * gumbel
 	packed = torch.nn.utils.rnn.pack_sequence(seqs)
 	is_off = torch.nn.utils.rnn.pack_sequence([torch.tensor([0.0] * (s.size(0) - 1) + [1.0]) for s in seqs])
 	cursor = {'i': 0}
@@ -63,9 +66,15 @@ def run_reference_step(ref, cfg, enc_sd, smp_sd, dec_sd, seqs, eps, gumbel, spea
 	torch.nn.functional.gumbel_softmax = recorded_gumbel
 	try:
 		last_hidden = enc(packed)
-		logits = smp(last_hidden)
-		feats = smp.sample(logits, no_sample=cfg['pretrain'])
-		kl = smp.kl_divergence(logits, cfg['N_data'])
+		if gaussian:   # plain/learning.py:147-149
+			params = smp(last_hidden)
+			feats = smp.sample(params)
+			kl = smp.kl_divergence(params)
+			logits = params[0]
+		else:
+			logits = smp(last_hidden)
+			feats = smp.sample(logits, no_sample=cfg['pretrain'])
+			kl = smp.kl_divergence(logits, cfg['N_data'])
 		em, off, x_all, (mean, lv), off_logit = dec(feats, batch_sizes=packed.batch_sizes, speaker=speaker,
 													ground_truth_out=packed.data, ground_truth_offset=is_off.data)
 		loss = (em + off + kl) / packed.batch_sizes[0]
@@ -89,15 +98,15 @@ def max_rel(a, b):
 	return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
-def gen_train_cases(ref):
-	for name, cfg in TRAIN_CASES.items():
+def gen_train_cases(ref, cases=None):
+	for name, cfg in (cases if cases is not None else TRAIN_CASES).items():
 		enc_sd, smp_sd, dec_sd, seqs, eps, gumbel, speaker = build_case(cfg, ref)
 		r, _ = run_reference_step(ref, cfg, enc_sd, smp_sd, dec_sd, seqs, eps, gumbel, speaker)
 		dev = {}
 		for dt in (torch.float32, torch.float64):
 			cast = lambda d: {k: (v.to(dt) if v.dtype.is_floating_point else v) for k, v in d.items()}
 			o = O.train_step(cast(enc_sd), cast(smp_sd), cast(dec_sd), [s.to(dt) for s in seqs], eps.to(dt), gumbel.to(dt),
-							cfg['N_data'], cfg['pretrain'], cfg['tau'], cfg['rnn'], 1.0, speaker)
+							cfg['N_data'], cfg['pretrain'], cfg['tau'], cfg['rnn'], 1.0, speaker, latent=cfg.get('latent', 'abcd'))
 			tag = 'f32' if dt == torch.float32 else 'f64'
 			for k in ('emission', 'offset', 'kl', 'loss', 'logits', 'last_hidden', 'flatten_out', 'mean', 'logvar', 'offset_logit'):
 				dev['{}_{}'.format(k, tag)] = max_rel(o[k], r[k])
@@ -200,6 +209,8 @@ if __name__ == '__main__':
 	ref = load_reference_model('ABCD-VAE')
 	gen_train_cases(ref)
 	gen_stft(REF)
-	gen_plain(load_reference_model('plain'))
+	ref_plain = load_reference_model('plain')
+	gen_plain(ref_plain)
+	gen_train_cases(ref_plain, CS.PLAIN_CASES)
 	gen_optim()
 	print('golden vectors written to', GOLD)

@@ -73,7 +73,7 @@ SIGNATURES = {
 	'abcd_debug_enc_timing': (C.c_int, [P(C.c_ulonglong)]),
 	'abcd_set_rnn_tensorcore': (C.c_int, [C.c_int]),
 	'abcd_debug_dec_timing': (C.c_int, [P(C.c_ulonglong)]),
-	'abcd_debug_ts_probe': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+	'abcd_measure_cluster_exchange': (C.c_int, [C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, C.c_void_p]),
 	'abcd_launch_count': (C.c_longlong, []),
 	'abcd_profile_groups': (C.c_int, []),
 	'abcd_profile_name': (C.c_char_p, [C.c_int]),
@@ -107,6 +107,8 @@ SIGNATURES = {
 									c_f32p, c_f32p, C.c_void_p]),
 	'abcd_philox_normal': (C.c_int, [c_f32p, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p]),
 	'abcd_philox_gumbel': (C.c_int, [c_f32p, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p]),
+	'abcd_csv_row_bound': (C.c_int64, [C.c_int64]),
+	'abcd_csv_format_long': (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
 	'abcd_sgemm': (C.c_int, [C.c_int, C.c_int, C.c_int, c_f32p, C.c_int64, C.c_int, c_f32p, C.c_int64, C.c_int,
 							c_f32p, C.c_int64, C.c_float, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),
 }

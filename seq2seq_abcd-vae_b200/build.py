@@ -10,7 +10,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libabcd_b200.so')
-SOURCES = ['api.cu', 'sgemm.cu', 'umma_gemm.cu', 'umma_rm_gemm.cu', 'umma_probe.cu', 'enc.cu', 'dec.cu', 'sampler.cu', 'stft.cu', 'optim.cu']
+SOURCES = ['api.cu', 'sgemm.cu', 'umma_gemm.cu', 'umma_rm_gemm.cu', 'latency_probe.cu', 'enc.cu', 'dec.cu', 'sampler.cu', 'stft.cu', 'optim.cu', 'csv.cu']
+# layout probes used by tools/ (not product code): a separate test library, built on demand by build_probe()
+PROBE_LIB_PATH = os.path.join(HERE, 'libabcd_b200_probe.so')
+PROBE_SOURCES = ['umma_probe.cu', 'probe_api.cu']
 NVCC_FLAGS = [
 	'-gencode', 'arch=compute_100a,code=sm_100a',
 	'-O3', '-std=c++17', '-lineinfo',
@@ -77,5 +80,16 @@ def build(force=False, verbose=False):
 	return LIB_PATH
 
 
+def build_probe():
+	"""libabcd_b200_probe.so: the tcgen05 TS-form layout probe of tools/ts_probe.py (kept out of the product library)."""
+	nvcc = _nvcc()
+	cmd = [nvcc] + NVCC_FLAGS + ['-shared', '-cudart', 'static', '-o', PROBE_LIB_PATH] + [os.path.join(CSRC, s) for s in PROBE_SOURCES]
+	subprocess.check_call(cmd)
+	return PROBE_LIB_PATH
+
+
 if __name__ == '__main__':
+	if '--probe' in sys.argv:
+		print(build_probe())
+		sys.exit(0)
 	print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

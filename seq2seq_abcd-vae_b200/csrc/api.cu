@@ -11,7 +11,7 @@ int enc_max_clusters(int which, int* out);
 int enc_read_timing(unsigned long long* out5);
 int rnn_set_tc(int on);
 int dec_read_timing(unsigned long long* out16);
-int umma_ts_probe(const float* A, const float* B, float* D, int K, int N, int variant, cudaStream_t stream);
+int measure_cluster_exchange(int cluster_size, int iters, int mode, float* d_out2, float* d_scratch, cudaStream_t stream);
 int dec_max_clusters(int which, int F, int* out);
 
 static thread_local char g_err[1024] = "";
@@ -115,8 +115,8 @@ long long abcd_launch_count(void) { return g_launches.load(); }
 int abcd_debug_enc_timing(unsigned long long* out10) { return enc_read_timing(out10); }
 int abcd_set_rnn_tensorcore(int on) { return rnn_set_tc(on); }
 int abcd_debug_dec_timing(unsigned long long* out16) { return dec_read_timing(out16); }
-int abcd_debug_ts_probe(const float* A, const float* B, float* D, int K, int N, int variant, void* stream) {
-    return umma_ts_probe(A, B, D, K, N, variant, (cudaStream_t)stream);
+int abcd_measure_cluster_exchange(int cluster_size, int iters, int mode, float* out2, float* scratch, void* stream) {
+    return measure_cluster_exchange(cluster_size, iters, mode, out2, scratch, (cudaStream_t)stream);
 }
 int abcd_profile_groups(void) { return PROF_COUNT; }
 const char* abcd_profile_name(int id) { return (id >= 0 && id < PROF_COUNT) ? g_prof_names[id] : ""; }

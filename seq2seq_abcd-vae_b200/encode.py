@@ -7,6 +7,7 @@ B200 path: batched GPU STFT -> persistent encoder kernel (inference variant, no 
 (data_ix, category_ix, prob [+ annotation columns]) with numpy instead of per-batch pandas melt/merge."""
 import argparse
 import os
+import sys
 
 import numpy as np
 import torch
@@ -64,34 +65,72 @@ class Encoder(learning.Learner):
 			out = (p.data.cpu().numpy() for p in out)
 		return out
 
-	def encode_dataset(self, dataset, save_path, to_numpy=True, batch_size=1, output='prob'):
+	def encode_dataset(self, dataset, save_path, to_numpy=True, batch_size=1, output='prob', writer_threads=4):
+		"""Long-format CSV of the reference (encode.py:38-55): per batch, rows `data_ix, category_ix, prob [+ annotation
+		columns]`, category-major like DataFrame.melt, values printed as pandas prints a float32 column.  The GPU encodes batch
+		i+1 while host threads format batch i with the native row formatter (abcd_csv_format_long); the file is written in
+		batch order.  Returns the number of rows written."""
+		import collections
+		import concurrent.futures
 		dataloader = data_utils.DataLoader(dataset, batch_size=batch_size, device=self.device)
 		rename_existing_file(save_path)
 		var_name, value_name = OUTPUT_KINDS[output]
-		if 'label' in dataset.df_annotation.columns:
-			df_ann = dataset.df_annotation.drop(columns=['onset_ix', 'offset_ix', 'length'])
-		else:
-			df_ann = None
-		header = ['data_ix', var_name, value_name] + (list(df_ann.columns) if df_ann is not None else [])
-		with open(save_path, 'w') as f:
-			f.write(','.join(header) + '\n')
+		suffix_of, ann_cols = annotation_suffixes(dataset.df_annotation)
+		header = ['data_ix', var_name, value_name] + ann_cols
+		rows = 0
+
+		def format_batch(vals, ixs):
+			return format_long_rows(vals, ixs, suffix_of)
+
+		pending = collections.deque()
+		with open(save_path, 'wb') as f, concurrent.futures.ThreadPoolExecutor(max(1, writer_threads)) as pool:
+			f.write((','.join(_csv_cell(c) for c in header) + '\n').encode())
 			for data, _, _, ix_in_list in dataloader:
-				vals = self.encode(data, is_packed=True, to_numpy=False, output=output).cpu().numpy()
-				B, K = vals.shape
-				ixs = np.asarray(ix_in_list)
-				# long format, category-major like DataFrame.melt: all rows of category 0, then category 1, ...
-				ann_rows = None
-				if df_ann is not None:
-					ann_rows = [','.join(_csv_cell(v) for v in df_ann.loc[ix].tolist()) for ix in ixs]
-				lines = []
-				for k in range(K):
-					col = vals[:, k]
-					for b in range(B):
-						line = '{},{},{}'.format(ixs[b], k, repr(float(col[b])))
-						if ann_rows is not None:
-							line += ',' + ann_rows[b]
-						lines.append(line)
-				f.write('\n'.join(lines) + '\n')
+				vals = self.encode(data, is_packed=True, to_numpy=False, output=output)
+				vals = np.ascontiguousarray(vals.cpu().numpy(), dtype=np.float32)
+				ixs = np.ascontiguousarray(np.asarray(ix_in_list), dtype=np.int64)
+				rows += vals.size
+				pending.append(pool.submit(format_batch, vals, ixs))
+				while len(pending) > 2 * writer_threads:
+					f.write(memoryview(pending.popleft().result()))
+			while pending:
+				f.write(memoryview(pending.popleft().result()))
+		return rows
+
+
+def format_long_rows(vals, ixs, suffix_of=None):
+	"""Rows of one batch as a uint8 array: for k, for b: `ixs[b],k,vals[b,k]<suffix_of[ixs[b]]>\\n` (host-only native call)."""
+	lib = L.load()
+	vals = np.ascontiguousarray(vals, dtype=np.float32)
+	ixs = np.ascontiguousarray(ixs, dtype=np.int64)
+	B, K = vals.shape
+	blob, off = None, None
+	if suffix_of is not None:
+		parts = [suffix_of[ix] for ix in ixs.tolist()]
+		off = np.zeros(B + 1, dtype=np.int64)
+		np.cumsum([len(p) for p in parts], out=off[1:])
+		blob = b''.join(parts)
+	cap = B * K * lib.abcd_csv_row_bound(int(np.diff(off).max()) if off is not None and B else 0)
+	out = np.empty(max(cap, 1), dtype=np.uint8)
+	n = lib.abcd_csv_format_long(vals.ctypes.data, B, K, K, ixs.ctypes.data, blob, off.ctypes.data if off is not None else None,
+								out.ctypes.data, cap)
+	if n < 0:
+		raise L.AbcdError('abcd_csv_format_long failed ({}): {}'.format(n, lib.abcd_last_error().decode()))
+	return out[:n]
+
+
+def annotation_suffixes(df_annotation):
+	"""The annotation cells the reference appends to every row of a segment (encode.py:41-44, 50-51: left merge on data_ix
+	when the annotation has a `label` column), formatted ONCE per segment by pandas itself: {data_ix: b',cell,cell,...'}."""
+	if 'label' not in df_annotation.columns:
+		return None, []
+	df_ann = df_annotation.drop(columns=['onset_ix', 'offset_ix', 'length'])
+	lines = df_ann.to_csv(header=False, index=False).split('\n')
+	if lines and lines[-1] == '':
+		lines.pop()
+	if len(lines) != len(df_ann):   # a cell contains a line break: fall back to per-row formatting
+		lines = [df_ann.iloc[[i]].to_csv(header=False, index=False).rstrip('\n') for i in range(len(df_ann))]
+	return {ix: (',' + line).encode() for ix, line in zip(df_ann.index.tolist(), lines)}, list(df_ann.columns)
 
 
 def _csv_cell(v):
@@ -130,6 +169,8 @@ def get_parameters(argv=None):
 
 
 def main(argv=None, output=None):
+	"""encode.py / encode_logit.py / encode_features.py of the reference share everything but the encoded quantity:
+	`output` is fixed by the entry-point module (encode_logit.py -> 'logit', encode_features.py -> 'feature')."""
 	a = get_parameters(argv)
 	save_path = a.save_path or os.path.join(a.input_root, 'autoencoded.csv')
 	os.makedirs(os.path.dirname(os.path.abspath(save_path)), exist_ok=True)

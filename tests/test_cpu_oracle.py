@@ -23,12 +23,12 @@ def _run_oracle(abcd, cfg, dtype):
 	enc_sd, smp_sd, dec_sd, seqs, eps, gumbel, speaker = CS.build_case(cfg, mods)
 	cast = lambda d: {k: (v.to(dtype) if v.dtype.is_floating_point else v) for k, v in d.items()}
 	return O.train_step(cast(enc_sd), cast(smp_sd), cast(dec_sd), [s.to(dtype) for s in seqs], eps.to(dtype), gumbel.to(dtype),
-						cfg['N_data'], cfg['pretrain'], cfg['tau'], cfg['rnn'], 1.0, speaker)
+						cfg['N_data'], cfg['pretrain'], cfg['tau'], cfg['rnn'], 1.0, speaker, latent=cfg.get('latent', 'abcd'))
 
 
-@pytest.mark.parametrize('name', sorted(CS.TRAIN_CASES))
+@pytest.mark.parametrize('name', sorted(CS.TRAIN_CASES) + sorted(CS.PLAIN_CASES))
 def test_oracle_reproduces_reference_golden(abcd, golden_dir, name):
-	cfg = CS.TRAIN_CASES[name]
+	cfg = CS.TRAIN_CASES[name] if name in CS.TRAIN_CASES else CS.PLAIN_CASES[name]
 	g = np.load(os.path.join(golden_dir, name + '.npz'))
 	o = _run_oracle(abcd, cfg, torch.float64)
 	for k in ('emission', 'offset', 'loss'):
