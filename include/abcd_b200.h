@@ -172,6 +172,16 @@ int abcd_dec_bwd(const abcd_dec_params_t* p, const abcd_dec_grads_t* g, const ab
                  const float* g_losses /*[2] upstream gradients of the two losses*/, float* d_feat_in /*[B,fin] or NULL*/,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* abcd_dec_bwd in two halves, so that the caller can put the weight-gradient reductions on a second stream where they
+ * overlap the rest of the backward pass (sampler backward, encoder BPTT): _data = loss-head gradients + BPTT + d_feat_in
+ * (the critical path), _weights = every parameter gradient, reading what _data left in the workspace.  The caller orders
+ * _weights after _data (event) and joins the second stream before using the gradients. */
+int abcd_dec_bwd_data(const abcd_dec_params_t* p, const abcd_packed_t* pk, const float* feat_in,
+                      const float* eps, int ld_eps, const float* gt, int ld_gt, const float* is_offset, const float* g_losses,
+                      float* d_feat_in, void* workspace, size_t workspace_bytes, void* stream);
+int abcd_dec_bwd_weights(const abcd_dec_params_t* p, const abcd_dec_grads_t* g, const abcd_packed_t* pk, const float* feat_in,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- clip_grad_norm_ + SGD.step over a flat arena (learning.py:161-163) ---------------------------- */
 int abcd_optim_partial_count(void);
 int abcd_gradnorm_clip_sgd(float* params, float* grads, float* momentum_buf /*or NULL*/, int64_t n, float lr,
@@ -181,6 +191,11 @@ int abcd_gradnorm_clip_sgd(float* params, float* grads, float* momentum_buf /*or
 /* ---- noise --------------------------------------------------------------------------------------- */
 int abcd_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
 int abcd_philox_gumbel(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+/* the same generators with a DEVICE-resident stream position: draw i uses Philox counter offset + *d_base + i/4 (d_base may be
+ * NULL).  A training step recorded in a CUDA graph bakes `offset` (its position inside the step) and ends with
+ * abcd_counter_add(d_base, draws of the step), so that every replay continues the stream (model.py:19, 604: fresh noise per step). */
+int abcd_philox_fill(float* out, int64_t n, int kind /*0 normal, 1 Gumbel*/, uint64_t seed, uint64_t offset, const uint64_t* d_base, void* stream);
+int abcd_counter_add(uint64_t* d_counter, uint64_t delta, void* stream);
 
 /* ---- Encoder.encode_dataset (encode.py:38-55): host-side long-format CSV rows of one batch ------------- */
 /* Category-major like DataFrame.melt: for k < K, for b < B: "<h_data_ix[b]>,<k>,<h_vals[b*ld+k]><suffix b>\n", the value

@@ -102,11 +102,16 @@ SIGNATURES = {
 							c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
 	'abcd_dec_bwd': (C.c_int, [P(DecParamsT), P(DecGradsT), P(PackedT), c_f32p, c_f32p, C.c_int, c_f32p, C.c_int, c_f32p,
 							c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+	'abcd_dec_bwd_data': (C.c_int, [P(DecParamsT), P(PackedT), c_f32p, c_f32p, C.c_int, c_f32p, C.c_int, c_f32p,
+							c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+	'abcd_dec_bwd_weights': (C.c_int, [P(DecParamsT), P(DecGradsT), P(PackedT), c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
 	'abcd_optim_partial_count': (C.c_int, []),
 	'abcd_gradnorm_clip_sgd': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int,
 									c_f32p, c_f32p, C.c_void_p]),
 	'abcd_philox_normal': (C.c_int, [c_f32p, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p]),
 	'abcd_philox_gumbel': (C.c_int, [c_f32p, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p]),
+	'abcd_philox_fill': (C.c_int, [c_f32p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
+	'abcd_counter_add': (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
 	'abcd_csv_row_bound': (C.c_int64, [C.c_int64]),
 	'abcd_csv_format_long': (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
 	'abcd_sgemm': (C.c_int, [C.c_int, C.c_int, C.c_int, c_f32p, C.c_int64, C.c_int, c_f32p, C.c_int64, C.c_int,

@@ -237,6 +237,22 @@ int abcd_dec_bwd(const abcd_dec_params_t* p, const abcd_dec_grads_t* g, const ab
                         ws, ws_bytes, S(stream));
 }
 
+int abcd_dec_bwd_data(const abcd_dec_params_t* p, const abcd_packed_t* pk, const float* feat_in,
+                      const float* eps, int ld_eps, const float* gt, int ld_gt, const float* is_offset, const float* g_losses,
+                      float* d_feat_in, void* ws, size_t ws_bytes, void* stream) {
+    ARG_CHECK(p && pk && feat_in && ws, "dec_bwd_data: null argument");
+    DecGrads none;
+    memset(&none, 0, sizeof(none));
+    return dec_backward(to_dp(p), none, to_meta(pk), feat_in, eps, ld_eps, gt, ld_gt, is_offset, g_losses, d_feat_in,
+                        ws, ws_bytes, S(stream), 1);
+}
+int abcd_dec_bwd_weights(const abcd_dec_params_t* p, const abcd_dec_grads_t* g, const abcd_packed_t* pk, const float* feat_in,
+                         void* ws, size_t ws_bytes, void* stream) {
+    ARG_CHECK(p && g && pk && feat_in && ws, "dec_bwd_weights: null argument");
+    return dec_backward(to_dp(p), to_dg(g), to_meta(pk), feat_in, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr,
+                        ws, ws_bytes, S(stream), 2);
+}
+
 int abcd_optim_partial_count(void) { return optim_partial_count(); }
 int abcd_gradnorm_clip_sgd(float* params, float* grads, float* momentum_buf, int64_t n, float lr, float momentum,
                            float max_norm, int zero_grads, float* norm_out, float* partial, void* stream) {
@@ -248,6 +264,13 @@ int abcd_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, vo
 }
 int abcd_philox_gumbel(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
     return philox_fill(out, (long)n, seed, offset, 1, S(stream));
+}
+int abcd_philox_fill(float* out, int64_t n, int kind, uint64_t seed, uint64_t offset, const uint64_t* d_base, void* stream) {
+    ARG_CHECK(kind == 0 || kind == 1, "philox_fill: kind must be 0 (normal) or 1 (Gumbel)");
+    return philox_fill(out, (long)n, seed, offset, kind, S(stream), (const unsigned long long*)d_base);
+}
+int abcd_counter_add(uint64_t* d_counter, uint64_t delta, void* stream) {
+    return counter_add((unsigned long long*)d_counter, delta, S(stream));
 }
 
 int abcd_sgemm(int M, int N, int K, const float* A, int64_t lda, int a_kmajor, const float* B, int64_t ldb, int b_kmajor,

@@ -1307,7 +1307,7 @@ DecWs dec_carve(void* base, size_t cap, int cell, int F, int fin, int B, int sum
     memset(&w, 0, sizeof(w));
     const int H = ABCD_H, M = ABCD_M, Fp = pad4(F);
     const int hc = cell == 0 ? 2 * H : H;
-    const int n_tiles = (B + ROWS - 1) / ROWS;
+    const int n_tiles = num_tiles(B);
     w.hc0 = a.take<float>((size_t)B * hc);
     w.Hall = a.take<float>((size_t)(B + sumT) * H);
     w.Call = a.take<float>((size_t)(B + sumT) * H);
@@ -1354,7 +1354,7 @@ DecK make_k(const DecParams& P, const PackedMeta& pk, const DecWs& w) {
     DecK k;
     memset(&k, 0, sizeof(k));
     k.cell = P.cell; k.F = P.F; k.Fp = pad4(P.F);
-    k.n_tiles = (pk.B + ROWS - 1) / ROWS; k.B = pk.B; k.T_max = pk.T_max;
+    k.n_tiles = num_tiles(pk.B); k.B = pk.B; k.T_max = pk.T_max;
     k.batch_sizes = pk.batch_sizes; k.offsets = pk.offsets; k.lengths = pk.lengths;
     k.w_ih = P.w_ih; k.w_hh = P.w_hh; k.b_ih = P.b_ih; k.b_hh = P.b_hh;
     for (int i = 0; i < 2; ++i) { k.em_w1[i] = P.em_w1[i]; k.em_b1[i] = P.em_b1[i]; k.em_w2[i] = P.em_w2[i]; k.em_b2[i] = P.em_b2[i]; }
@@ -1426,7 +1426,7 @@ int dec_forward(const DecParams& P, const PackedMeta& pk, const float* feat_in, 
     const int hc = P.cell == 0 ? 2 * H : H;
     DecWs w = dec_carve(ws, ws_bytes, P.cell, P.F, P.fin, pk.B, pk.sumT);
     if (w.bytes > ws_bytes) { abcd_set_error("decoder: workspace too small (%zu < %zu)", ws_bytes, w.bytes); return ABCD_ERR_WORKSPACE; }
-    const int n_tiles = (pk.B + ROWS - 1) / ROWS;
+    const int n_tiles = num_tiles(pk.B);
 
     // feature2hidden (model.py:169-170): hc0 = feat_in W^T + b
     GemmArgs g = gemm_args_zero();
@@ -1487,26 +1487,31 @@ int dec_forward(const DecParams& P, const PackedMeta& pk, const float* feat_in, 
     return ABCD_OK;
 }
 
+// parts: bit 0 = data path (loss-head gradients, BPTT, gradient of the features), bit 1 = weight gradients (reductions over all
+// packed frames of the buffers the data path left in the workspace; may run on another stream once the data path is done)
 int dec_backward(const DecParams& P, const DecGrads& G, const PackedMeta& pk, const float* feat_in, const float* eps,
                  int ld_eps, const float* gt, int ld_gt, const float* is_offset, const float* g_losses,
-                 float* d_feat_in, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                 float* d_feat_in, void* ws, size_t ws_bytes, cudaStream_t stream, int parts) {
     TRY(check_dec(P));
-    ARG_CHECK(gt && is_offset && g_losses && eps, "decoder bwd: ground truth, offsets, noise and loss gradients are required");
+    const bool do_data = parts & 1, do_wgrad = parts & 2;
+    ARG_CHECK(!do_data || (gt && is_offset && g_losses && eps), "decoder bwd: ground truth, offsets, noise and loss gradients are required");
     const int H = ABCD_H, M = ABCD_M, F = P.F, Fp = pad4(P.F);
     const int hc = P.cell == 0 ? 2 * H : H;
     DecWs w = dec_carve(ws, ws_bytes, P.cell, P.F, P.fin, pk.B, pk.sumT);
     if (w.bytes > ws_bytes) { abcd_set_error("decoder bwd: workspace too small"); return ABCD_ERR_WORKSPACE; }
     ColsumScratch colsum_scratch(w.partials, w.partial_floats);
-    const int n_tiles = (pk.B + ROWS - 1) / ROWS;
+    const int n_tiles = num_tiles(pk.B);
     const int sumT = pk.sumT;
     const float* Hfr = w.Hall + (size_t)pk.B * H;   // h of frame n
 
+    GemmArgs g = gemm_args_zero();
+    if (do_data) {
     // ---- loss-head gradients over all frames ----
     nll_grad_kernel<<<592, 256, 0, stream>>>(sumT, F, Fp, w.Mean, w.Lv, gt, ld_gt, g_losses, w.dML);
     KERNEL_CHECK();
     offset_head_bwd_kernel<<<592, 256, 0, stream>>>(sumT, w.HidOff, P.off_w2, w.OffLogit, is_offset, g_losses, w.dLogit, w.dHidOffPre);
     KERNEL_CHECK();
-    GemmArgs g = gemm_args_zero();   // dHoff = dHidOffPre * off_w1
+    // dHoff = dHidOffPre * off_w1
     g.M = sumT; g.N = H; g.K = M;
     g.A = w.dHidOffPre; g.lda = M; g.a_kmajor = 1;
     g.B = P.off_w1; g.ldb = H; g.b_kmajor = 0;
@@ -1543,6 +1548,17 @@ int dec_backward(const DecParams& P, const DecGrads& G, const PackedMeta& pk, co
         }
     }
 
+    if (d_feat_in) {   // gradient of the decoder input features (feature2hidden data gradient): on the critical path
+        g = gemm_args_zero();
+        g.M = pk.B; g.N = P.fin; g.K = hc;
+        g.A = w.dHC0; g.lda = hc; g.a_kmajor = 1;
+        g.B = P.w_f2h; g.ldb = P.fin; g.b_kmajor = 0;
+        g.C = d_feat_in; g.ldc = P.fin;
+        TRY(sgemm_launch(g, stream));
+    }
+    }   // do_data
+    if (!do_wgrad) return ABCD_OK;
+
     // ---- weight gradients: reductions over all packed frames ----
     dec_prev_index_kernel<<<min(pk.T_max, 592), 128, 0, stream>>>(pk.T_max, pk.B, pk.batch_sizes, pk.offsets, w.prev);
     KERNEL_CHECK();
@@ -1562,12 +1578,12 @@ int dec_backward(const DecParams& P, const DecGrads& G, const PackedMeta& pk, co
     TRY(tn(4 * H, F, w.dG, 4 * H, w.Xall, Fp, w.prev, map_ih, G.w_ih, F, sumT));
     TRY(tn(4 * H, H, w.dG, 4 * H, w.Hall, H, w.prev, map_hh, G.w_hh, H, sumT));
     // the BPTT kernel already reduced dG over the frames of every tile
-    TRY(colsum_launch(w.dbias, 4 * H, (pk.B + ROWS - 1) / ROWS, 4 * H, 1.f, G.b_ih, 1, map_ih, stream));
-    TRY(colsum_launch(w.dbias, 4 * H, (pk.B + ROWS - 1) / ROWS, 4 * H, 1.f, G.b_hh, 1, map_hh, stream));
+    TRY(colsum_launch(w.dbias, 4 * H, num_tiles(pk.B), 4 * H, 1.f, G.b_ih, 1, map_ih, stream));
+    TRY(colsum_launch(w.dbias, 4 * H, num_tiles(pk.B), 4 * H, 1.f, G.b_hh, 1, map_hh, stream));
     for (int i = 0; i < 2; ++i) {
         TRY(tn(M, H, w.dHidPre + i * M, 2 * M, Hfr, H, nullptr, gate_map_none(), G.em_w1[i], H, sumT));
         // the BPTT kernel already reduced dHidPre over the frames of every tile
-        TRY(colsum_launch(w.dbias1 + i * M, 2 * M, (pk.B + ROWS - 1) / ROWS, M, 1.f, G.em_b1[i], 1, gate_map_none(), stream));
+        TRY(colsum_launch(w.dbias1 + i * M, 2 * M, num_tiles(pk.B), M, 1.f, G.em_b1[i], 1, gate_map_none(), stream));
         TRY(tn(F, M, w.dML + i * Fp, 2 * Fp, w.Hid + i * M, 2 * M, nullptr, gate_map_none(), G.em_w2[i], M, sumT));
         TRY(colsum_launch(w.dML + i * Fp, 2 * Fp, sumT, F, 1.f, G.em_b2[i], 1, gate_map_none(), stream));
     }
@@ -1578,13 +1594,5 @@ int dec_backward(const DecParams& P, const DecGrads& G, const PackedMeta& pk, co
     // feature2hidden
     TRY(tn(hc, P.fin, w.dHC0, hc, feat_in, P.fin, nullptr, gate_map_none(), G.w_f2h, P.fin, pk.B));
     TRY(colsum_launch(w.dHC0, hc, pk.B, hc, 1.f, G.b_f2h, 1, gate_map_none(), stream));
-    if (d_feat_in) {
-        g = gemm_args_zero();
-        g.M = pk.B; g.N = P.fin; g.K = hc;
-        g.A = w.dHC0; g.lda = hc; g.a_kmajor = 1;
-        g.B = P.w_f2h; g.ldb = P.fin; g.b_kmajor = 0;
-        g.C = d_feat_in; g.ldc = P.fin;
-        TRY(sgemm_launch(g, stream));
-    }
     return ABCD_OK;
 }

@@ -842,7 +842,7 @@ static EncWs enc_carve(void* base, size_t cap, int cell, int F, int B, int sumT,
     for (int d = 0; d < ndirs; ++d) {
         w.bias_comb[d] = a.take<float>(4 * H);
         w.wih_pad[d] = a.take<float>((size_t)4 * H * ((F + 3) & ~3));
-        w.himg[d] = reinterpret_cast<char*>(a.take<float>((size_t)((B + ROWS - 1) / ROWS) * 2 * ts_image_bytes(H) / sizeof(float)));
+        w.himg[d] = reinterpret_cast<char*>(a.take<float>((size_t)num_tiles(B) * 2 * ts_image_bytes(H) / sizeof(float)));
         w.xproj[d] = a.take<float>((size_t)sumT * 4 * H);
         w.hs[d] = a.take<float>(save ? (size_t)sumT * H : (size_t)2 * B * H);
         if (save) {
@@ -854,8 +854,8 @@ static EncWs enc_carve(void* base, size_t cap, int cell, int F, int B, int sumT,
     if (save) {
         // dG aliases xproj (dead after the forward recurrence) -- both [sumT][4H] per direction
         for (int d = 0; d < ndirs; ++d) w.dg[d] = w.xproj[d];
-        for (int d = 0; d < ndirs; ++d) w.dbias[d] = a.take<float>((size_t)((B + ROWS - 1) / ROWS) * 4 * H);
-        w.pbuf = a.take<float>((size_t)2 * ndirs * ((B + ROWS - 1) / ROWS) * ENC_CL * ROWS * H);
+        for (int d = 0; d < ndirs; ++d) w.dbias[d] = a.take<float>((size_t)num_tiles(B) * 4 * H);
+        w.pbuf = a.take<float>((size_t)2 * ndirs * num_tiles(B) * ENC_CL * ROWS * H);
         w.prev_fwd = a.take<int>(sumT);
         w.prev_bwd = a.take<int>(sumT);
         int s1 = sgemm_pick_splits(4 * H, H, sumT), s2 = sgemm_pick_splits(4 * H, F, sumT);
@@ -879,7 +879,7 @@ int enc_forward(const EncParams& P, const PackedMeta& pk, const float* x, int ld
     const int H = ABCD_H;
     EncWs w = enc_carve(ws, ws_bytes, P.cell, P.F, pk.B, pk.sumT, ndirs, save);
     if (w.bytes > ws_bytes) { abcd_set_error("encoder: workspace too small (%zu < %zu)", ws_bytes, w.bytes); return ABCD_ERR_WORKSPACE; }
-    const int n_tiles = (pk.B + ROWS - 1) / ROWS;
+    const int n_tiles = num_tiles(pk.B);
     const int ngates = P.cell == 0 ? 4 : 3;
 
     EncFwdK k;
@@ -933,7 +933,7 @@ int enc_backward(const EncParams& P, const EncGrads& G, const PackedMeta& pk, co
     EncWs w = enc_carve(ws, ws_bytes, P.cell, P.F, pk.B, pk.sumT, ndirs, 1);
     if (w.bytes > ws_bytes) { abcd_set_error("encoder bwd: workspace too small"); return ABCD_ERR_WORKSPACE; }
     ColsumScratch colsum_scratch(w.partials, w.partial_floats);
-    const int n_tiles = (pk.B + ROWS - 1) / ROWS;
+    const int n_tiles = num_tiles(pk.B);
 
     EncBwdK k;
     memset(&k, 0, sizeof(k));

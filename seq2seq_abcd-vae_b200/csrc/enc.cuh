@@ -51,4 +51,4 @@ int dec_forward(const DecParams& P, const PackedMeta& pk, const float* feat_in, 
                 void* ws, size_t ws_bytes, cudaStream_t stream);
 int dec_backward(const DecParams& P, const DecGrads& G, const PackedMeta& pk, const float* feat_in,
                  const float* eps, int ld_eps, const float* gt, int ld_gt, const float* is_offset, const float* g_losses /*[2] device*/,
-                 float* d_feat_in, void* ws, size_t ws_bytes, cudaStream_t stream);
+                 float* d_feat_in, void* ws, size_t ws_bytes, cudaStream_t stream, int parts = 3);

@@ -92,7 +92,11 @@ __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5
 
 // kind 0: standard normal (Box-Muller); kind 1: standard Gumbel  -log(-log U)  (= -log of an Exp(1) draw,
 // torch.nn.functional.gumbel_softmax's noise, model.py:604)
-__global__ void philox_kernel(float* __restrict__ out, long n, uint64_t seed, uint64_t offset, int kind) {
+__global__ void philox_kernel(float* __restrict__ out, long n, uint64_t seed, uint64_t offset, int kind,
+                              const unsigned long long* __restrict__ d_base) {
+    // d_base (optional): a device-resident stream position added to the launch-time offset, so that a launch recorded in a
+    // CUDA graph draws fresh numbers on every replay (the graph advances the counter with counter_add_kernel)
+    if (d_base) offset += (uint64_t)__ldg(d_base);
     const long n4 = (n + 3) >> 2;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         uint32_t r[4];
@@ -115,7 +119,16 @@ __global__ void philox_kernel(float* __restrict__ out, long n, uint64_t seed, ui
     }
 }
 
+__global__ void counter_add_kernel(unsigned long long* ctr, unsigned long long delta) { *ctr += delta; }
+
 }  // namespace
+
+int counter_add(unsigned long long* d_ctr, unsigned long long delta, cudaStream_t stream) {
+    ARG_CHECK(d_ctr, "counter_add: null counter");
+    counter_add_kernel<<<1, 1, 0, stream>>>(d_ctr, delta);
+    KERNEL_CHECK();
+    return ABCD_OK;
+}
 
 int optim_partial_count() { return OPT_BLOCKS; }
 
@@ -135,13 +148,14 @@ int gradnorm_clip_sgd(float* params, float* grads, float* momentum_buf, long n, 
     return ABCD_OK;
 }
 
-int philox_fill(float* out, long n, unsigned long long seed, unsigned long long offset, int kind, cudaStream_t stream) {
+int philox_fill(float* out, long n, unsigned long long seed, unsigned long long offset, int kind, cudaStream_t stream,
+                const unsigned long long* d_base) {
     if (n <= 0) return ABCD_OK;
     ProfScope ps(PROF_NOISE, stream);
     long n4 = (n + 3) >> 2;
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    philox_kernel<<<blocks, 256, 0, stream>>>(out, n, (uint64_t)seed, (uint64_t)offset, kind);
+    philox_kernel<<<blocks, 256, 0, stream>>>(out, n, (uint64_t)seed, (uint64_t)offset, kind, d_base);
     KERNEL_CHECK();
     return ABCD_OK;
 }

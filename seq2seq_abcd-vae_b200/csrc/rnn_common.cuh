@@ -29,6 +29,19 @@ constexpr int RG = NRG;            // thread of row group rg owns the interleave
 constexpr int ROWS = RT * NRG;     // rows (segments) per tile
 constexpr int NTHREADS = 256;
 
+// Row tiles of a batch of B segments.  At least ceil(B / ROWS) so that a tile fits the per-thread register tile; for small
+// batches (a rank's shard of the publication batch under strong scaling: 64 segments) MORE, smaller tiles -- up to the 7 clusters
+// of 16 CTAs (or 2 x 7 clusters of 8) the GPU keeps co-resident -- because the per-step cost of a tile shrinks with its rows while
+// an idle SM buys nothing: 64 segments run as 7 tiles of 9-10 rows instead of one tile of 64.
+constexpr int MAX_CORESIDENT_TILES = 7;
+constexpr int MIN_TILE_ROWS = 8;
+__host__ __device__ inline int num_tiles(int B) {
+    const int need = (B + ROWS - 1) / ROWS;
+    int spread = (B + MIN_TILE_ROWS - 1) / MIN_TILE_ROWS;
+    if (spread > MAX_CORESIDENT_TILES) spread = MAX_CORESIDENT_TILES;
+    return need > spread ? need : spread;
+}
+
 struct ThreadMap {
     int cg, rg, ks;   // column group (4 columns), row group, K-split index
     bool active;

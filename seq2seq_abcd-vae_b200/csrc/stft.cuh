@@ -7,4 +7,6 @@ int gradnorm_clip_sgd(float* params, float* grads, float* momentum_buf, long n, 
                       float max_norm, int zero_grads, float* norm_out, float* partial, int n_partial,
                       cudaStream_t stream);
 int optim_partial_count();
-int philox_fill(float* out, long n, unsigned long long seed, unsigned long long offset, int kind, cudaStream_t stream);
+int philox_fill(float* out, long n, unsigned long long seed, unsigned long long offset, int kind, cudaStream_t stream,
+                const unsigned long long* d_base = nullptr);
+int counter_add(unsigned long long* d_ctr, unsigned long long delta, cudaStream_t stream);

@@ -193,6 +193,13 @@ class Learner(object):
 		self.parameters = lambda: itertools.chain.from_iterable(m.parameters() for m in self._modules())
 		self.arena = FlatArena(self._modules(), self.device)
 		self._n_enc_params = len(list(self.encoder.parameters()))
+		import collections
+		self.use_cuda_graph = getattr(self, 'use_cuda_graph', False)   # opt-in: Learner.use_cuda_graph = True (bench.py, -G)
+		self.max_cuda_graphs = 8
+		self._side_stream = torch.cuda.Stream(device=self.device)
+		self._graphs = collections.OrderedDict()
+		self._graph_seen = {}
+		self._replayed_launches = 0
 
 	# -- one fused optimisation step ----------------------------------------------------------------------
 	def forward_losses(self, packed_input, is_offset, speaker, num_strings, is_pretraining, hidden_grad_hook=None):
@@ -212,40 +219,116 @@ class Learner(object):
 		"""forward + backward + (all-reduce) + clip + SGD for one (local shard of a) batch, all on the device.
 		Gradients are SUMS over segments divided by the GLOBAL batch size, so shards add up exactly
 		(reference: loss / batch_sizes[0], learning.py:155-158).  With world_size > 1 the caller passes this rank's shard and
-		`global_batch_size` (Learner.train does; a full batch on every rank would be summed world_size times)."""
+		`global_batch_size` (Learner.train does; a full batch on every rank would be summed world_size times).
+
+		With `use_cuda_graph` the ~60 kernel launches of a step are recorded once per (input buffers, batch shape,
+		hyper-parameters) into a CUDA graph -- the second time that combination is seen -- and replayed afterwards: one
+		cudaGraphLaunch per step, kernels back to back, the weight-gradient branch running beside the encoder BPTT.  The noise
+		stream position lives on the device (model.noise_like), so replays draw fresh noise exactly like eager steps."""
+		if self.world_size > 1 and global_batch_size is None:
+			raise ValueError('train_step under a process group needs global_batch_size (the batch must be sharded over the ranks)')
+		args = (packed_input, is_offset, speaker, num_strings, is_pretraining, global_batch_size)
+		key = self._graph_key(*args) if self.use_cuda_graph else None
+		if key is None:
+			out = self._train_step_body(*args)
+		else:
+			entry = self._graphs.get(key)
+			if entry is None and self._graph_seen.get(key, 0) == 0:
+				self._graph_seen[key] = 1
+				if len(self._graph_seen) > 64:
+					self._graph_seen.clear()
+				out = self._train_step_body(*args)      # first sight: a host-launched step (also fills descriptor caches)
+			else:
+				if entry is None:
+					entry = self._capture(key, args)
+				else:
+					self._graphs.move_to_end(key)
+					self._replayed_launches += entry['launches']
+					model._noise_state['offset'] += entry['noise']
+				entry['graph'].replay()
+				out = entry['out']
+		if self.has_pretraining and not is_pretraining:
+			self.feature_sampler.increment_iter_counts()
+		return out
+
+	def _train_step_body(self, packed_input, is_offset, speaker, num_strings, is_pretraining, global_batch_size):
 		self.arena.rebind()
 		pending = []
 		hook = None
+		side = self._side_stream
 		if self.world_size > 1:
-			if global_batch_size is None:
-				raise ValueError('train_step under a process group needs global_batch_size (the batch must be sharded over the ranks)')
 			# the arena is laid out [encoder | sampler | decoder]: the sampler/decoder part of the gradient is final before the
 			# encoder's backward starts, so its all-reduce (5.8 of the 6.9 MB) overlaps the encoder BPTT and weight-gradient GEMMs
 			tail = self.arena.grad[self.arena.offsets[self._n_enc_params]:]
 
 			def hook(grad):
-				pending.append(torch.distributed.all_reduce(tail, op=torch.distributed.ReduceOp.SUM, group=self.process_group, async_op=True))
+				# sampler gradients are enqueued on this stream, decoder weight gradients on the side stream: reduce after both
+				side.wait_stream(torch.cuda.current_stream())
+				with torch.cuda.stream(side):
+					pending.append(torch.distributed.all_reduce(tail, op=torch.distributed.ReduceOp.SUM, group=self.process_group, async_op=True))
 				return grad
 		emission_loss, end_loss, kl_loss, logits = self.forward_losses(packed_input, is_offset, speaker, num_strings, is_pretraining,
 																		hidden_grad_hook=hook)
 		batch_size = int(packed_input.batch_sizes[0]) if global_batch_size is None else global_batch_size
 		loss = (emission_loss + end_loss + kl_loss) / batch_size
-		with model.accumulate_into_grad():   # kernels add straight into the flat gradient arena
+		# kernels add straight into the flat gradient arena; the decoder's weight-gradient GEMMs run on a second stream beside
+		# the sampler backward and the encoder BPTT (which leaves 36 of the 148 SMs idle)
+		with model.accumulate_into_grad(), model.weight_gradient_stream(side):
 			loss.backward()
+		torch.cuda.current_stream().wait_stream(side)
 		if self.world_size > 1:
 			if pending:
 				head = self.arena.grad[:self.arena.offsets[self._n_enc_params]]
 				torch.distributed.all_reduce(head, op=torch.distributed.ReduceOp.SUM, group=self.process_group)
-				for w in pending:
-					w.wait()
+				with torch.cuda.stream(side):
+					for w in pending:
+						w.wait()
+				torch.cuda.current_stream().wait_stream(side)
 			else:   # the hook did not fire (encoder frozen): one all-reduce over everything
 				torch.distributed.all_reduce(self.arena.grad, op=torch.distributed.ReduceOp.SUM, group=self.process_group)
 		lr = self.optimizer.param_groups[0]['lr']
 		momentum = self.optimizer.param_groups[0]['momentum']
 		self.arena.clip_and_step(lr, momentum, self.gradient_clip)
-		if self.has_pretraining and not is_pretraining:
-			self.feature_sampler.increment_iter_counts()
+		model.noise_commit(self.device)
 		return loss, emission_loss, end_loss, kl_loss, logits
+
+	# -- CUDA-graph replay of a recorded step ---------------------------------------------------------------
+	def _graph_key(self, packed_input, is_offset, speaker, num_strings, is_pretraining, global_batch_size):
+		"""Everything a recorded step bakes in: buffer addresses, the batch layout, and every scalar passed by value."""
+		smp, dec = self.feature_sampler, self.decoder
+		if getattr(smp, 'injected_gumbel_noise', None) is not None or getattr(smp, 'injected_noise', None) is not None \
+				or dec.injected_emission_noise is not None or not torch.is_grad_enabled():
+			return None   # parity hooks hand in fresh tensors every step: host-launched
+		bs = packed_input.batch_sizes
+		g = self.optimizer.param_groups[0]
+		return (packed_input.data.data_ptr(), is_offset.data.data_ptr(), speaker.data_ptr() if speaker is not None else 0,
+				bs.numel(), bs.numpy().tobytes(), float(num_strings), bool(is_pretraining), global_batch_size,
+				float(g['lr']), float(g['momentum']), float(self.gradient_clip), float(getattr(smp, 'temperature', 0.0)),
+				model._noise_key(), self.arena.momentum_buf is None)
+
+	def _capture(self, key, args):
+		lib = L.load()
+		torch.cuda.synchronize(self.device)
+		if self.arena.momentum_buf is None and self.optimizer.param_groups[0]['momentum'] != 0.0:
+			self.arena.momentum_buf = torch.zeros_like(self.arena.flat)
+		noise0 = model._noise_state['offset']
+		launches0 = lib.abcd_launch_count()
+		graph = torch.cuda.CUDAGraph()
+		with torch.cuda.graph(graph):
+			out = self._train_step_body(*args)
+		entry = {'graph': graph, 'out': out, 'launches': int(lib.abcd_launch_count() - launches0),
+				'noise': model._noise_state['offset'] - noise0}
+		self._graphs[key] = entry
+		while len(self._graphs) > self.max_cuda_graphs:
+			self._graphs.popitem(last=False)
+		return entry
+
+	def kernel_launches(self):
+		"""Kernels of this library enqueued so far, including those replayed from recorded graphs."""
+		return int(L.load().abcd_launch_count()) + self._replayed_launches
+
+	def launch_mode(self):
+		return 'cuda-graph replay ({} recorded step(s))'.format(len(self._graphs)) if self.use_cuda_graph and self._graphs else 'host-launched kernels'
 
 	# -- epochs -----------------------------------------------------------------------------------------
 	def _move(self, packed_input, is_offset, speaker):
@@ -301,6 +384,7 @@ class Learner(object):
 			for batch_ix, (packed_input, is_offset, speaker, _) in enumerate(dataloader, 1):
 				packed_input, is_offset, speaker = self._move(packed_input, is_offset, speaker)
 				em, end, kl, _ = self.forward_losses(packed_input, is_offset, speaker, num_strings, is_pretraining)
+				model.noise_commit(self.device)
 				part = torch.stack([em, end, kl]).double()
 				totals += part / self.world_size if getattr(dataloader, 'last_replicated', False) else part
 				logger.info('{batch_ix}/{num_batches} validation batches complete.'.format(batch_ix=batch_ix, num_batches=num_batches))
@@ -434,8 +518,10 @@ class Learner(object):
 		if cuda_states is not None and len(cuda_states) == torch.cuda.device_count():
 			torch.cuda.set_rng_state_all(cuda_states)   # (unused by the kernels: their noise is the Philox stream below)
 		if 'noise_state' in self.checkpoint:
-			model._noise_state.update(self.checkpoint['noise_state'])
+			ns = self.checkpoint['noise_state']
+			model._noise_state['seed'] = ns['seed']
 			model._noise_state['stream'] = getattr(self, 'rank', 0)
+			model.set_noise_offset(ns['offset'])
 		return self.checkpoint['epoch']
 
 

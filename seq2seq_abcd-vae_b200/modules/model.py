@@ -44,6 +44,28 @@ class accumulate_into_grad(object):
 		return False
 
 
+# Optional second stream for the decoder's weight-gradient reductions (Learner.train_step): inside
+# `weight_gradient_stream(side)` _DecoderFn.backward enqueues the data path (BPTT, d_features) on the current stream and the
+# parameter gradients on `side`, ordered by an event; the caller joins `side` before it reads the gradients.
+_WGRAD_STREAM = None
+
+
+class weight_gradient_stream(object):
+	def __init__(self, stream):
+		self.stream = stream
+
+	def __enter__(self):
+		global _WGRAD_STREAM
+		self.prev = _WGRAD_STREAM
+		_WGRAD_STREAM = self.stream
+		return self
+
+	def __exit__(self, *exc):
+		global _WGRAD_STREAM
+		_WGRAD_STREAM = self.prev
+		return False
+
+
 def _grad_buffers(tensors):
 	"""-> (buffers handed to the kernel, values returned to autograd) for parameter-like inputs."""
 	bufs, rets = [], []
@@ -111,7 +133,13 @@ def choose_distribution(distribution_name):
 	return (sample_from_isotropic_gaussian, log_pdf_isotropic_gaussian, kl_isotropic_to_standard_gaussian, 2)
 
 
+# In-kernel Philox noise.  The stream position lives ON THE DEVICE (one uint64 per device): a launch draws at
+# *counter + `_noise_rel`, where `_noise_rel` counts the draws already issued since the last commit, and noise_commit()
+# advances the device counter by that amount with a one-thread kernel.  Eager steps and CUDA-graph replays of a recorded
+# step therefore consume the same stream ('offset' is the host mirror of the committed position, kept for checkpoints).
 _noise_state = {'seed': 0x5EED, 'offset': 0, 'stream': 0}
+_noise_rel = 0
+_noise_ctr = {}
 
 
 def manual_noise_seed(seed, stream=0):
@@ -119,23 +147,59 @@ def manual_noise_seed(seed, stream=0):
 	streams under the same seed: data-parallel ranks pass their rank, so different shards of a batch never see the same
 	draws (the reference has one process and one torch generator)."""
 	_noise_state['seed'] = int(seed) & 0xFFFFFFFFFFFFFFFF
-	_noise_state['offset'] = 0
 	_noise_state['stream'] = int(stream)
+	set_noise_offset(0)
+
+
+def set_noise_offset(offset):
+	"""Move the stream position (checkpoint restore)."""
+	global _noise_rel
+	_noise_state['offset'] = int(offset)
+	_noise_rel = 0
+	for t in _noise_ctr.values():
+		t.fill_(int(offset))
 
 
 def _noise_key():
 	return (_noise_state['seed'] ^ ((_noise_state.get('stream', 0) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF
 
 
+def _noise_counter(device):
+	key = str(device)
+	if key not in _noise_ctr:
+		_noise_ctr[key] = torch.tensor([_noise_state['offset']], dtype=torch.int64, device=device)
+	return _noise_ctr[key]
+
+
 def noise_like(t, kind='normal'):
 	"""Philox draws with the shape of `t` (N(0,1) or standard Gumbel)."""
+	global _noise_rel
 	L.ensure_device(t.device)
 	out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
 	n = out.numel()
-	fn = 'abcd_philox_normal' if kind == 'normal' else 'abcd_philox_gumbel'
-	L.call(fn, L.ptr(out), n, _noise_key(), _noise_state['offset'], L.stream_ptr())
-	_noise_state['offset'] += (n + 3) // 4
+	L.call('abcd_philox_fill', L.ptr(out), n, 0 if kind == 'normal' else 1, _noise_key(), _noise_rel, L.ptr(_noise_counter(t.device)), L.stream_ptr())
+	_noise_rel += (n + 3) // 4
 	return out
+
+
+def noise_pending():
+	"""Draw groups issued since the last commit."""
+	return _noise_rel
+
+
+def noise_commit(device, host_only=False):
+	"""Advance the device-resident stream position past the draws issued since the last commit (enqueued on the current
+	stream, after the kernels that consumed them).  host_only=True only updates the host mirror: used after replaying a
+	CUDA graph that already contains the device-side increment."""
+	global _noise_rel
+	if _noise_rel == 0:
+		return 0
+	n = _noise_rel
+	if not host_only:
+		L.call('abcd_counter_add', L.ptr(_noise_counter(device)), n, L.stream_ptr())
+	_noise_state['offset'] += n
+	_noise_rel = 0
+	return n
 
 
 class _GaussLatentFn(torch.autograd.Function):
@@ -653,8 +717,19 @@ class _DecoderFn(torch.autograd.Function):
 		grads, rets = _grad_buffers(params)
 		d_feat = torch.empty_like(feat_in)
 		dp, dg = _dec_structs(ctx.cell, F, H, M, feat_in.shape[1], params, grads)
-		L.call('abcd_dec_bwd', C.byref(dp), C.byref(dg), ctx.desc.ref(), L.ptr(feat_in), L.ptr(eps), eps.shape[1],
-			L.ptr(gt), gt.shape[1], L.ptr(is_offset), L.ptr(g), L.ptr(d_feat), L.ptr(ctx.ws), ctx.ws_bytes, L.stream_ptr())
+		side = _WGRAD_STREAM
+		if side is None or any(r is not None for r in rets):
+			L.call('abcd_dec_bwd', C.byref(dp), C.byref(dg), ctx.desc.ref(), L.ptr(feat_in), L.ptr(eps), eps.shape[1],
+				L.ptr(gt), gt.shape[1], L.ptr(is_offset), L.ptr(g), L.ptr(d_feat), L.ptr(ctx.ws), ctx.ws_bytes, L.stream_ptr())
+		else:
+			# data path here; weight gradients (accumulated straight into the parameters' .grad) on the side stream
+			L.call('abcd_dec_bwd_data', C.byref(dp), ctx.desc.ref(), L.ptr(feat_in), L.ptr(eps), eps.shape[1],
+				L.ptr(gt), gt.shape[1], L.ptr(is_offset), L.ptr(g), L.ptr(d_feat), L.ptr(ctx.ws), ctx.ws_bytes, L.stream_ptr())
+			side.wait_stream(torch.cuda.current_stream())
+			with torch.cuda.stream(side):
+				L.call('abcd_dec_bwd_weights', C.byref(dp), C.byref(dg), ctx.desc.ref(), L.ptr(feat_in), L.ptr(ctx.ws), ctx.ws_bytes, L.stream_ptr())
+			for t in (ctx.ws, feat_in):
+				t.record_stream(side)
 		return (d_feat, None, None, None, None, None, None) + tuple(rets)
 
 

@@ -222,3 +222,40 @@ def test_learner_20_step_drift_vs_oracle(abcd):
 		print('  step %2d  %.1e  %.1e  %.1e' % ((s,) + c))
 	for s, (lr_, nr, pr) in enumerate(curve):
 		assert lr_ < 5e-5 and nr < TOL and pr < TOL, (s, lr_, nr, pr)
+
+
+@pytest.mark.parametrize('B', [64, 200])
+def test_cuda_graph_replay_equals_host_launched_steps(abcd, B):
+	"""Learner.use_cuda_graph: a step recorded into a CUDA graph and replayed (with the decoder weight gradients on the side
+	stream and the Philox position on the device) must leave bit-identical parameters to the same steps launched from the
+	host -- same kernels, same order of floating-point operations, same noise stream."""
+	learning = importlib.import_module('seq2seq_abcd-vae_b200.learning')
+	S = importlib.import_module('seq2seq_abcd-vae_b200.synthetic')
+	lengths = S.synthetic_lengths(B, 77)
+	bs = S.batch_sizes_of(lengths)
+	x = S.synthetic_frames(int(lengths.sum()), 65, 3).cuda()
+	off = S.is_offset_of(lengths, bs).cuda()
+	p_in = torch.nn.utils.rnn.PackedSequence(x, bs)
+	p_off = torch.nn.utils.rnn.PackedSequence(off, bs)
+	results = []
+	for use_graph in (False, True):
+		learner = learning.Learner(65, 256, 256, 256, 128, 256, None, device='cuda', seed=5)
+		for i, m in enumerate(learner._modules()):
+			m.load_state_dict({k: v.cuda() for k, v in S.deterministic_state(m, 900 + i).items()})
+		abcd.model.manual_noise_seed(1234)
+		learner.setup_optimizer(0.5, 0.9, gradient_clip=1.0, patience=0)
+		learner.feature_sampler.train()
+		learner.use_cuda_graph = use_graph
+		losses = []
+		for step in range(6):
+			losses.append(learner.train_step(p_in, p_off, None, 5000, False)[0].detach().clone())
+		torch.cuda.synchronize()
+		results.append((torch.stack(losses).cpu(), learner.arena.flat.detach().cpu().clone(), learner.arena.momentum_buf.cpu().clone(),
+						dict(abcd.model._noise_state), learner.launch_mode(), learner.kernel_launches()))
+	(l0, p0, m0, n0, mode0, k0), (l1, p1, m1, n1, mode1, k1) = results
+	print('graph parity B=%d: losses' % B, l0.tolist(), l1.tolist(), mode0, '|', mode1, 'launches', k0, k1)
+	assert 'graph' in mode1 and 'graph' not in mode0
+	assert n0['offset'] == n1['offset'] > 0
+	assert len(set(l0.tolist())) == 6              # fresh noise every step (also under replay)
+	assert torch.equal(l0, l1)
+	assert torch.equal(p0, p1) and torch.equal(m0, m1)

@@ -83,8 +83,26 @@ def main():
 	torch.distributed.broadcast(flat, 0)
 	same = bool(torch.equal(flat, ln.arena.flat))
 	print('rank {} parameters identical to rank 0: {}'.format(rank, same))
+
+	# in-kernel (Philox) noise, one stream per rank; the same 5 sharded steps host-launched and as CUDA-graph replays (NCCL
+	# all-reduces recorded inside the graph, decoder weight gradients on the side stream) must give bit-identical parameters
+	finals = []
+	for use_graph in (False, True):
+		l2 = make_learner()
+		pkg.model.manual_noise_seed(77, stream=rank)
+		l2.use_cuda_graph = use_graph
+		for _ in range(5):
+			l2.train_step(p_in, p_off, None, cfg['N_data'], False, global_batch_size=B)
+		torch.cuda.synchronize()
+		finals.append((l2.arena.flat.clone(), l2.launch_mode()))
+	graph_same = bool(torch.equal(finals[0][0], finals[1][0]))
+	bc = finals[1][0].clone()
+	torch.distributed.broadcast(bc, 0)
+	graph_ranks_same = bool(torch.equal(bc, finals[1][0]))
+	print('rank {} graph replay == host-launched: {} ({}); ranks identical: {}'.format(rank, graph_same, finals[1][1], graph_ranks_same))
+	torch.distributed.barrier()
 	torch.distributed.destroy_process_group()
-	sys.exit(0 if (ok and same) else 1)
+	sys.exit(0 if (ok and same and graph_same and graph_ranks_same) else 1)
 
 
 if __name__ == '__main__':
