@@ -22,6 +22,7 @@ namespace {
 constexpr int DEC_N1P = 392;   // backward: pitch of the resident [W_hh | W_ih] rows (H + pad4(F) <= 388 for F <= 129)
 constexpr size_t SMEM_MAX = 232448;   // 227 KB of dynamic shared memory per CTA on sm_100
 constexpr float LOG_2PI = 1.8378770664093453f;
+constexpr int DEC_MAX_F = 129;
 
 __host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
 __host__ __device__ inline int xcols_per_cta(int F) { return (F + CL - 1) / CL; }
@@ -359,6 +360,292 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_kernel(DecK p) {
     float tot = block_sum(nll, red);
     if (tid == 0) p.nll_partial[blockIdx.x] = tot;
     if (TC) ts_fini(ts, tid);
+}
+
+// -------------------------------------------------------------------------------------------------
+// forward, pair variant (default for output_size <= 128): the gate contraction P1 runs on tcgen05 with full-rate M = 128
+// instructions -- the two CTAs of a pair share the 128 gate columns of 32 units and split K = [h | x] between them, hi AND lo
+// parts of the weights resident in tensor memory (rnn_ts.cuh, "pair variant").  P2 / P3 are those of dec_fwd_kernel.
+// Shared memory: [activation ring (also the P2 staging buffers, the hidden-layer slice and the accumulator bounce) | W1 | W2s | scratch]
+// -------------------------------------------------------------------------------------------------
+constexpr int DFP_KC = 64;   // staged K-chunk of P2 (its two staging buffers alias the activation ring)
+static_assert((size_t)2 * ROWS * (DFP_KC + 4) * sizeof(float) <= (size_t)TSP_STAGES * TS_STAGE_BYTES, "P2 staging must fit in the activation ring");
+
+template <int CELL>
+__global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_pair_kernel(DecK p) {
+    extern __shared__ __align__(1024) float smem_pair[];
+    float* const smem = smem_pair;
+    const int H = ABCD_H, M = ABCD_M;
+    const int F = p.F, Fp = p.Fp;
+    const int XC = xcols_per_cta(F);
+    constexpr int KC = DFP_KC;
+    constexpr int HSP = 2 * U + 4;            // pitch of the CTA's own hidden-layer slice kept in shared memory
+    const int ts_nslx = (Fp + TS_SLAB - 1) / TS_SLAB;                  // slabs of the x image
+    const int nsl_total = H / TS_SLAB + ts_nslx;
+    float* W1 = reinterpret_cast<float*>(reinterpret_cast<char*>(smem) + (size_t)TSP_STAGES * TS_STAGE_BYTES);   // [H][2U]
+    float* W2s = W1 + H * (2 * U);            // [U][2Fp]: rows of the output layers that multiply this CTA's hidden units
+    float* red = W2s + U * 2 * Fp;            // 40 floats
+    const Stage st = make_stage(smem, KC);
+    float* Hs = st.buf0;                      // [ROWS][HSP] (the staging buffers are idle between phases)
+    __shared__ uint64_t tsp_bars[TSP_STAGES + 1];
+    __shared__ uint32_t tsp_tmem_slot;
+    TsPairCtx tsp;
+
+    const int tid = threadIdx.x;
+    const int rank = (int)cluster_ctarank();
+    const int tile = blockIdx.x / CL;
+    const int u0 = rank * U;                  // the 16 units this CTA finalises (cell update, MLP slices)
+    const int pair_u0 = (rank >> 1) * 2 * U;  // the 32 units whose gate columns the pair contracts
+    const int xc0 = rank * XC;
+    const int xc1 = min(F, xc0 + XC);
+
+    // ---- resident weights ----
+    if ((umma::smem_u32(smem) & 1023u) != 0) __trap();
+    {
+        auto wval = [&](int col, int k) -> float {
+            const int u = pair_u0 + (col >> 2), s = col & 3;
+            if (k < H) {
+                const int gate = CELL == 0 ? s : (s == 0 ? 0 : s == 1 ? 1 : s == 3 ? 2 : -1);
+                return gate >= 0 ? __ldg(p.w_hh + (long)(gate * H + u) * H + k) : 0.f;
+            }
+            const int gate = CELL == 0 ? s : (s == 3 ? -1 : s);
+            return (gate >= 0 && k - H < F) ? __ldg(p.w_ih + (long)(gate * H + u) * F + (k - H)) : 0.f;
+        };
+        ts_pair_init(tsp, reinterpret_cast<char*>(smem), tsp_bars, &tsp_tmem_slot, rank & 1, nsl_total, wval, tid);
+    }
+    char* himg[2]; char* ximg[2];
+    himg[0] = p.himg + (size_t)(tile * 2) * ts_image_bytes(ABCD_H); himg[1] = himg[0] + ts_image_bytes(ABCD_H);
+    ximg[0] = p.ximg + (size_t)(tile * 2) * ts_nslx * TS_STAGE_BYTES; ximg[1] = ximg[0] + (size_t)ts_nslx * TS_STAGE_BYTES;
+    // clear the images once (padding k >= F of the x image must be zero; stale rows must at least be finite)
+    {
+        float4* z = reinterpret_cast<float4*>(himg[0]);
+        const size_t n16 = 2 * ts_image_bytes(ABCD_H) / 16;
+        for (size_t i = (size_t)rank * NTHREADS + tid; i < n16; i += (size_t)CL * NTHREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4* zx = reinterpret_cast<float4*>(ximg[0]);
+        const size_t nx16 = (size_t)2 * ts_nslx * TS_STAGE_BYTES / 16;
+        for (size_t i = (size_t)rank * NTHREADS + tid; i < nx16; i += (size_t)CL * NTHREADS) zx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    ts_image_publish();
+    cluster_sync_all();
+    for (int idx = tid; idx < H * 2 * U; idx += NTHREADS) {
+        int col = idx % (2 * U), k = idx / (2 * U);
+        int which = col / U, u = col % U;
+        W1[idx] = p.em_w1[which][(long)(u0 + u) * H + k];
+    }
+    for (int idx = tid; idx < U * 2 * Fp; idx += NTHREADS) {
+        int c = idx % (2 * Fp), kk = idx / (2 * Fp);
+        int which = c >= Fp, cc = which ? c - Fp : c;     // mean columns [0,Fp), log-variance columns [Fp,2Fp)
+        W2s[idx] = cc < F ? p.em_w2[which][(long)cc * M + u0 + kk] : 0.f;
+    }
+
+    // ---- per-thread constants for the three phases ----
+    const ThreadMap tm1 = make_map(tid, U, 1);      // cell update: warps 0..3, (unit, 8 row groups)
+    const int unit = u0 + tm1.cg;
+    float bias1[4];
+    if (CELL == 0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) bias1[g] = p.b_ih[g * H + unit] + p.b_hh[g * H + unit];
+    } else {
+        bias1[0] = p.b_ih[unit] + p.b_hh[unit];
+        bias1[1] = p.b_ih[H + unit] + p.b_hh[H + unit];
+        bias1[2] = p.b_ih[2 * H + unit];
+        bias1[3] = p.b_hh[2 * H + unit];
+    }
+    const int KS2 = pick_ks_fit(2 * U / 4, 2 * U, KC);
+    const ThreadMap tm2 = make_map(tid, 2 * U / 4, KS2);
+    float bias2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int col = tm2.cg * 4 + j;
+        bias2[j] = p.em_b1[col / U][u0 + col % U];
+    }
+    const int ncg3 = 2 * Fp / 4;                                      // column groups of the local emission GEMM
+    float* Pmine = p.Pbuf + (long)blockIdx.x * ROWS * (2 * Fp);       // this CTA's partial emission parameters
+    const float* Ptile = p.Pbuf + (long)tile * CL * ROWS * (2 * Fp);  // partials of all CTAs of the cluster
+    // pair exchange of the gate partial sums (the backward pass's partial buffer is idle during the forward pass)
+    float* pair_send = p.Pb2 + (size_t)(blockIdx.x ^ 1) * ROWS * H;
+    const float* pair_recv = p.Pb2 + (size_t)blockIdx.x * ROWS * H;
+
+    // recurrent state of (row, unit) pairs owned by this thread
+    float creg[RT], hreg[RT];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+        int b = tile + p.n_tiles * (tm1.rg + i * RG);
+        creg[i] = 0.f; hreg[i] = 0.f;
+        if (b < p.B && tm1.active) {
+            hreg[i] = p.Hall[(long)b * H + unit];
+            if (CELL == 0) creg[i] = p.Call[(long)b * H + unit];
+        }
+    }
+    const int Tt = p.lengths[tile];
+    float nll = 0.f;
+    const int n_tiles = p.n_tiles, B = p.B;
+    const float* Hall = p.Hall; const float* Xall = p.Xall;
+    // images of the initial state (read by step 0 with parity (0 - 1) & 1 = 1)
+    if (tm1.active) {
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            const int r = tm1.rg + i * RG;
+            if (tile + p.n_tiles * r < p.B) ts_image_store(himg[1], unit, r, hreg[i]);
+        }
+    }
+    for (int o = tid; o < ROWS * XC; o += NTHREADS) {
+        const int r = o / XC, c = xc0 + o % XC;
+        const long b = tile + (long)n_tiles * r;
+        if (c < xc1 && b < B) ts_image_store(ximg[1], c, r, Xall[b * Fp + c]);
+    }
+    ts_image_publish();
+    cluster_sync_all();
+    __syncthreads();
+    const bool timing = p.timing == 1 && blockIdx.x == 0 && tid == 64;
+    unsigned long long tacc[16];
+    for (int i = 0; i < 16; ++i) tacc[i] = 0;
+#define DEC_TICK(slot) if (timing) { long long now_ = clock64(); tacc[slot] += now_ - tick_; tick_ = now_; }
+
+    for (int t = 0; t < Tt; ++t) {
+        long long tick_ = timing ? clock64() : 0;
+        const int na = active_rows(p.batch_sizes[t], tile, n_tiles);
+        const long off_t = p.offsets[t];
+
+        // ---- P1: gates + cell ----
+        {
+            float acc[RT][4];
+            zero_acc(acc);
+            DEC_TICK(0)
+            // h_{t-1} has been visible since the first barrier of the previous step; x_t only after the barrier whose
+            // arrive ended that step: the h slabs of the contraction overlap that barrier
+            phase_gemm_ts_pair(acc, tsp, himg[(t - 1) & 1], ximg[(t - 1) & 1], pair_send, pair_recv, na, tm1, tid, t > 0);
+            DEC_TICK(1)
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+                int r = tm1.rg + i * RG;
+                if (r >= na || !tm1.active) continue;
+                long frame = off_t + tile + (long)n_tiles * r;
+                float h;
+                if (CELL == 0) {
+                    float ig = sigmoid_acc(acc[i][0] + bias1[0]);
+                    float fg = sigmoid_acc(acc[i][1] + bias1[1]);
+                    float gg = tanhf(acc[i][2] + bias1[2]);
+                    float og = sigmoid_acc(acc[i][3] + bias1[3]);
+                    float c = fg * creg[i] + ig * gg;
+                    h = og * tanhf(c);
+                    creg[i] = c;
+                    *reinterpret_cast<float4*>(p.Gs + frame * (4 * H) + unit * 4) = make_float4(ig, fg, gg, og);
+                    p.Call[((long)B + frame) * H + unit] = c;
+                } else {
+                    float rg_ = sigmoid_acc(acc[i][0] + bias1[0]);
+                    float zg = sigmoid_acc(acc[i][1] + bias1[1]);
+                    float hn = acc[i][3] + bias1[3];
+                    float ng = tanhf(acc[i][2] + bias1[2] + rg_ * hn);
+                    h = (1.f - zg) * ng + zg * hreg[i];
+                    *reinterpret_cast<float4*>(p.Gs + frame * (4 * H) + unit * 4) = make_float4(rg_, zg, ng, hn);
+                }
+                hreg[i] = h;
+                p.Hall[((long)B + frame) * H + unit] = h;
+                ts_image_store(himg[t & 1], unit, r, h);
+            }
+        }
+        ts_image_publish();
+        DEC_TICK(2)
+        cluster_sync_all();
+        DEC_TICK(3)
+
+        // ---- P2: hidden layers of the two emission MLPs ----
+        {
+            float acc[RT][4];
+            zero_acc(acc);
+            auto rph = [=](int r) -> const float* { return Hall + ((long)B + off_t + tile + (long)n_tiles * r) * ABCD_H; };
+            phase_gemm<NTHREADS, KC, 2 * U>(acc, st, H, rph, 0, NullRow(), na, W1, tm2, KS2, tid);
+            DEC_TICK(4)
+            if (tm2.active && tm2.ks == 0) {
+#pragma unroll
+                for (int i = 0; i < RT; ++i) {
+                    int r = tm2.rg + i * RG;
+                    if (r >= na) continue;
+                    long frame = off_t + tile + (long)n_tiles * r;
+                    int col = tm2.cg * 4;
+                    int which = col / U, uu = col % U;
+                    float4 v = make_float4(tanhf(acc[i][0] + bias2[0]), tanhf(acc[i][1] + bias2[1]),
+                                           tanhf(acc[i][2] + bias2[2]), tanhf(acc[i][3] + bias2[3]));
+                    *reinterpret_cast<float4*>(p.Hid + frame * (2 * M) + which * M + u0 + uu) = v;
+                    *reinterpret_cast<float4*>(Hs + r * HSP + col) = v;
+                }
+            }
+            __syncthreads();
+            // ---- P3a: this CTA's share of the emission parameters (K-split over the hidden units, see dec_fwd_kernel) ----
+            for (int item = tid; item < ncg3 * 16; item += NTHREADS) {
+                const int cg = item % ncg3, r0 = item / ncg3;   // rows r0 + 16 i
+                if (r0 >= na) continue;
+                const float* a = Hs + r0 * HSP + ((cg * 4 < Fp) ? 0 : U);
+                const float* w = W2s + cg * 4;
+                float o[5][4];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+#pragma unroll
+                for (int kq = 0; kq < U / 4; ++kq) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(w + (kq * 4 + 0) * (2 * Fp));
+                    const float4 w1 = *reinterpret_cast<const float4*>(w + (kq * 4 + 1) * (2 * Fp));
+                    const float4 w2 = *reinterpret_cast<const float4*>(w + (kq * 4 + 2) * (2 * Fp));
+                    const float4 w3 = *reinterpret_cast<const float4*>(w + (kq * 4 + 3) * (2 * Fp));
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        const float4 av = *reinterpret_cast<const float4*>(a + i * 16 * HSP + kq * 4);
+                        o[i][0] = fmaf(av.x, w0.x, o[i][0]); o[i][1] = fmaf(av.x, w0.y, o[i][1]); o[i][2] = fmaf(av.x, w0.z, o[i][2]); o[i][3] = fmaf(av.x, w0.w, o[i][3]);
+                        o[i][0] = fmaf(av.y, w1.x, o[i][0]); o[i][1] = fmaf(av.y, w1.y, o[i][1]); o[i][2] = fmaf(av.y, w1.z, o[i][2]); o[i][3] = fmaf(av.y, w1.w, o[i][3]);
+                        o[i][0] = fmaf(av.z, w2.x, o[i][0]); o[i][1] = fmaf(av.z, w2.y, o[i][1]); o[i][2] = fmaf(av.z, w2.z, o[i][2]); o[i][3] = fmaf(av.z, w2.w, o[i][3]);
+                        o[i][0] = fmaf(av.w, w3.x, o[i][0]); o[i][1] = fmaf(av.w, w3.y, o[i][1]); o[i][2] = fmaf(av.w, w3.z, o[i][2]); o[i][3] = fmaf(av.w, w3.w, o[i][3]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    const int r = r0 + 16 * i;
+                    if (r < na) *reinterpret_cast<float4*>(Pmine + (long)r * (2 * Fp) + cg * 4) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+                }
+            }
+        }
+        DEC_TICK(5)
+        cluster_sync_all();
+        DEC_TICK(6)
+
+        // ---- P3b: sum the partials of this CTA's x columns, reparameterised sample, NLL ----
+        for (int o = tid; o < na * XC; o += NTHREADS) {
+            const int r = o / XC, c = xc0 + o % XC;
+            if (c >= xc1) continue;
+            const long frame = off_t + tile + (long)n_tiles * r;
+            const float e = __ldg(p.eps + frame * p.ld_eps + c);
+            const float g = p.gt ? __ldg(p.gt + frame * p.ld_gt + c) : 0.f;
+            float pm[CL], pv[CL];
+#pragma unroll
+            for (int src = 0; src < CL; ++src) {
+                const float* q = Ptile + ((long)src * ROWS + r) * (2 * Fp) + c;
+                pm[src] = ld_cg(q);
+                pv[src] = ld_cg(q + Fp);
+            }
+            float mean = __ldg(p.em_b2[0] + c), lv = __ldg(p.em_b2[1] + c);
+#pragma unroll
+            for (int src = 0; src < CL; ++src) { mean += pm[src]; lv += pv[src]; }
+            const float x = mean + expf(0.5f * lv) * e;
+            p.Mean[frame * Fp + c] = mean;
+            p.Lv[frame * Fp + c] = lv;
+            p.Xall[((long)B + frame) * Fp + c] = x;
+            ts_image_store(ximg[t & 1], c, r, x);
+            if (p.gt) {
+                const float d = g - mean;
+                nll += 0.5f * (LOG_2PI + lv + d * expf(-lv) * d);
+            }
+        }
+        DEC_TICK(7)
+        ts_image_publish();
+        DEC_TICK(8)
+        cluster_arrive_release();   // matched by the wait inside the next step's P1 (or the one after the loop)
+        DEC_TICK(9)
+    }
+#undef DEC_TICK
+    if (Tt > 0) cluster_wait_acquire();
+    if (timing) { tacc[15] = Tt; for (int i = 0; i < 16; ++i) g_dec_timing[i] = tacc[i]; }
+    float tot = block_sum(nll, red);
+    if (tid == 0) p.nll_partial[blockIdx.x] = tot;
+    ts_pair_fini(tsp, tid);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1247,11 +1534,34 @@ int dec_fwd_kc(int F) { return pick_kc(dec_fwd_fixed_floats(F), SMEM_MAX - 1024)
 int dec_bwd_kc(int F) { return pick_kc(dec_bwd_fixed_floats(F)); }
 size_t dec_fwd_smem(int F) { return (dec_fwd_fixed_floats(F) + stage_floats(dec_fwd_kc(F))) * sizeof(float); }
 size_t dec_bwd_smem(int F) { return (dec_bwd_fixed_floats(F) + stage_floats(dec_bwd_kc(F))) * sizeof(float); }
-constexpr int DEC_MAX_F = 129;
 // tensor-core forward: [tiles + raw ring | W_lo | W1 | W2s | scratch]
 size_t dec_fwd_ts_smem(int F) {
     const int Fp = pad4(F);
     return (size_t)TSI_STAGES * TS_STAGE_BYTES + ts_wlo_bytes_m<U * 4>(ABCD_H + Fp) + (size_t)(ABCD_H * 2 * U + U * 2 * Fp + 64) * sizeof(float);
+}
+// pair variant (default): [activation ring | W1 | W2s | scratch]
+size_t dec_fwd_pair_smem(int F) {
+    const int Fp = pad4(F);
+    return (size_t)TSP_STAGES * TS_STAGE_BYTES + (size_t)(ABCD_H * 2 * U + U * 2 * Fp + 64) * sizeof(float);
+}
+// ABCD_DEC_FWD=pair (default) | ffma | tc64.  The pair variant pays one more exchange per step than the FFMA kernel and wins once a
+// tile has enough rows for the tensor-core contraction to matter (measured: 1.41 vs 1.52 ms at 73 rows per tile, 1.20 vs 1.18 at 37, 1.03 vs 0.94 ms at
+// 10); below DEC_PAIR_MIN_ROWS rows per tile (small shards under strong scaling) the FFMA kernel runs.
+constexpr int DEC_PAIR_MIN_ROWS = 48;
+int dec_fwd_mode(int F, int B = 1 << 30) {
+    static int opt = -1;
+    if (opt < 0) {
+        const char* e = getenv("ABCD_DEC_FWD");
+        opt = (e && !strcmp(e, "ffma")) ? 0 : (e && !strcmp(e, "tc64")) ? 1 : 2;
+        const char* e2 = getenv("ABCD_DEC_FWD_TC");
+        if (e2 && e2[0] == '1') opt = 1;
+    }
+    const int nsl = ABCD_H / TS_SLAB + (pad4(F) + TS_SLAB - 1) / TS_SLAB;
+    static int force = -1;
+    if (force < 0) { const char* e = getenv("ABCD_DEC_FWD"); force = (e && !strcmp(e, "pair")) ? 1 : 0; }
+    const bool rows_ok = force || (B + num_tiles(B) - 1) / num_tiles(B) >= DEC_PAIR_MIN_ROWS;
+    if (opt == 2 && rows_ok && rnn_use_tc() && (nsl + 1) / 2 <= TSP_MAX_SLABS && dec_fwd_pair_smem(F) <= SMEM_MAX - 1024) return 2;
+    return opt == 2 ? 0 : opt;
 }
 // The M = 64 tensor-core gate contraction of the forward kernel is parity-green but not yet faster than the FFMA phase
 // (1.68 vs 1.52 ms: eleven serial split -> barrier -> issue rounds per step): opt-in with ABCD_DEC_FWD_TC=1.
@@ -1259,7 +1569,8 @@ bool dec_fwd_use_ts(int F) {
     static int opt = -1;
     if (opt < 0) { const char* e = getenv("ABCD_DEC_FWD_TC"); opt = (e && e[0] == '1') ? 1 : 0; }
     const int nsl = (ABCD_H + pad4(F) + TS_SLAB - 1) / TS_SLAB;
-    return opt == 1 && rnn_use_tc() && TS_D_COLS_M + nsl * TS_SLAB <= 512 && dec_fwd_ts_smem(F) <= SMEM_MAX - 1024;
+    (void)opt;
+    return dec_fwd_mode(F) == 1 && rnn_use_tc() && TS_D_COLS_M + nsl * TS_SLAB <= 512 && dec_fwd_ts_smem(F) <= SMEM_MAX - 1024;
 }
 // tensor-core backward: [operand tiles | W_lo tiles | WB3 | dh/dc carries | B3 staging (also the dHidPre / dG slices)]
 size_t dec_bwd_ts_fixed_bytes(int F) {
@@ -1384,6 +1695,8 @@ int dec_max_clusters(int which, int F, int* out) {
     if (which == 1 && dec_bwd_use_ts(F))   // the tensor-memory backward
         return rnn_max_active_clusters(dec_bwd_ts_kc(F) == 64 ? (const void*)dec_bwd_ts_kernel<0, 64> : (const void*)dec_bwd_ts_kernel<0, 32>,
                                        dec_bwd_ts_smem(F), CL, NTHREADS, out);
+    if (which == 0 && dec_fwd_mode(F) == 2)
+        return rnn_max_active_clusters((const void*)dec_fwd_pair_kernel<0>, dec_fwd_pair_smem(F), CL, NTHREADS, out);
     const int kc = which == 0 ? dec_fwd_kc(F) : dec_bwd_kc(F);
     const void* fn = which == 0 ? (kc == 128 ? (const void*)dec_fwd_kernel<0, 128> : kc == 64 ? (const void*)dec_fwd_kernel<0, 64> : (const void*)dec_fwd_kernel<0, 32>)
                                 : (kc == 128 ? (const void*)dec_bwd_kernel<0, 128> : kc == 64 ? (const void*)dec_bwd_kernel<0, 64> : (const void*)dec_bwd_kernel<0, 32>);
@@ -1395,6 +1708,8 @@ int dec_init() {
     TRY(rnn_prepare_kernel((const void*)dec_bwd_ts_kernel<1, 64>, SMEM_MAX - 1024));   // the kernel also has static shared memory
     TRY(rnn_prepare_kernel((const void*)dec_bwd_ts_kernel<0, 32>, SMEM_MAX - 1024));   // the kernel also has static shared memory
     TRY(rnn_prepare_kernel((const void*)dec_bwd_ts_kernel<1, 32>, SMEM_MAX - 1024));   // the kernel also has static shared memory
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_pair_kernel<0>, SMEM_MAX - 1024));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_pair_kernel<1>, SMEM_MAX - 1024));
     TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0, 64, true>, SMEM_MAX - 1024));
     TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<1, 64, true>, SMEM_MAX - 1024));
     TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0, 128>, SMEM_MAX - 1024));
@@ -1446,7 +1761,11 @@ int dec_forward(const DecParams& P, const PackedMeta& pk, const float* feat_in, 
     {
         ProfScope ps(PROF_DEC_FWD, stream);
         const size_t sm = dec_fwd_smem(P.F);
-        if (dec_fwd_use_ts(P.F)) {
+        if (dec_fwd_mode(P.F, pk.B) == 2) {
+            k.kc = DFP_KC;
+            if (P.cell == 0) TRY(launch_cluster_dec(dec_fwd_pair_kernel<0>, n_tiles, dec_fwd_pair_smem(P.F), stream, k));
+            else TRY(launch_cluster_dec(dec_fwd_pair_kernel<1>, n_tiles, dec_fwd_pair_smem(P.F), stream, k));
+        } else if (dec_fwd_use_ts(P.F)) {
             k.kc = 64;
             if (P.cell == 0) TRY(launch_cluster_dec(dec_fwd_kernel<0, 64, true>, n_tiles, dec_fwd_ts_smem(P.F), stream, k));
             else TRY(launch_cluster_dec(dec_fwd_kernel<1, 64, true>, n_tiles, dec_fwd_ts_smem(P.F), stream, k));

@@ -290,6 +290,22 @@ __device__ __forceinline__ void local_gemm_store(const float* A, const float* W,
     }
 }
 
+// Partial-sum reductions over the CL = 16 CTAs of a cluster read 16 values per output from L2.  To keep every load of a
+// step in flight at once (one L2 round trip instead of one per item), FOUR lanes share an output: lane `sub` (= tid & 3)
+// loads and adds sources 4 sub .. 4 sub + 3 in order, then quad_sum() combines the four sub-sums with two butterfly
+// exchanges -- ((s0..s3) + (s4..s7)) + ((s8..s11) + (s12..s15)), the same bits in all four lanes: a fixed order, so results
+// stay reproducible run to run.  Must be executed by all 32 lanes of a warp.
+__device__ __forceinline__ float quad_sum(float a) {
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    return a;
+}
+__device__ __forceinline__ float4 quad_sum4(float4 a) {
+    a.x = quad_sum(a.x); a.y = quad_sum(a.y); a.z = quad_sum(a.z); a.w = quad_sum(a.w);
+    return a;
+}
+__device__ __forceinline__ float pick4(const float4& a, int i) { return i == 0 ? a.x : i == 1 ? a.y : i == 2 ? a.z : a.w; }
+
 struct NullRow {
     __device__ __forceinline__ const float* operator()(int) const { return nullptr; }
 };

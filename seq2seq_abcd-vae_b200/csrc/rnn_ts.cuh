@@ -411,4 +411,209 @@ __device__ __forceinline__ void ts_init_m(TsCtx& c, char* tiles, char* wlo, floa
     umma::fence_after_sync();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Pair variant (decoder forward, default): full-rate M = 128 instructions inside a 16-CTA cluster.
+//
+// A 16-way column split leaves 64 gate columns per CTA, and M = 64 instructions run at half rate.  Instead, the two CTAs
+// of a PAIR (cluster ranks 2c, 2c+1) share the 128 gate columns of 32 hidden units and split the REDUCTION dimension
+// [h_{t-1} | x_t] (K = H + Fp, in 32-row slabs) between them: rank 2c takes the first ceil(NS/2) slabs (all of them rows of
+// h), rank 2c+1 the rest (the last h slabs and every x slab).  Each CTA keeps BOTH the hi and the lo part of its
+// [128 columns x K/2] weight block in tensor memory (2 x 192 of the 512 columns), so every one of the three products of the
+// 3xTF32 split is a TS-form instruction and no weight byte is read from shared memory in the time loop:
+//     D^T[128, rows] (+)= W_hi x a_hi,  W_hi x a_lo,  W_lo x a_hi          (accumulator: columns [0, 96))
+// The partial sums of the two CTAs are exchanged through L2: each CTA finalises the 16 units (64 accumulator lanes) it
+// owns -- lanes [64 r', 64 r' + 64) for pair rank r' -- so it publishes the OTHER 64 lanes to its partner's receive
+// buffer, a cluster barrier follows, and the owner adds the partner's partial to its own lanes while bouncing them
+// (transposed to [row][gate column]) through shared memory into the per-thread tile of the cell update.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TSP_STAGES = 6;                              // one ring stage per slab of a CTA (<= 6 slabs): no reuse inside a phase
+constexpr int TSP_MAX_SLABS = 6;
+constexpr int TSP_A_HI = TS_D_COLS_M;                      // tensor-memory columns: accumulator [0, 96), W_hi, W_lo
+constexpr int TSP_A_LO = TSP_A_HI + TSP_MAX_SLABS * TS_SLAB;
+constexpr int TSP_BOUNCE_PITCH = 64 + 4;
+static_assert(TSP_A_LO + TSP_MAX_SLABS * TS_SLAB <= 512, "tensor-memory budget of the pair variant");
+static_assert(ROWS * TSP_BOUNCE_PITCH * 4 <= TSP_STAGES * TS_STAGE_BYTES, "accumulator bounce must fit in the activation ring");
+
+struct TsPairCtx {
+    char* tiles;          // TSP_STAGES stages of [a_hi | a_lo] (1024-byte aligned)
+    uint64_t* full;       // [TSP_STAGES] bytes landed
+    uint64_t* done;       // MMAs of the phase complete
+    uint32_t tmem;
+    uint32_t n_phase;     // phases completed (uniform): parity of every barrier
+    int kh, nsl, slab0;   // pair rank, number of slabs of this CTA, first global slab
+};
+
+// Tensor memory allocation + resident weights (hi and lo) of this CTA's K half.  wval(col, k): weight of gate column col
+// (< 128, of the pair) at reduction index k of [h | x] (zero beyond the real K).  Ends with a CTA barrier.
+template <class WVal>
+__device__ __forceinline__ void ts_pair_init(TsPairCtx& c, char* tiles, uint64_t* bars, uint32_t* tmem_slot, int kh, int nsl_total,
+                                             WVal wval, int tid) {
+    c.tiles = tiles; c.full = bars; c.done = bars + TSP_STAGES; c.n_phase = 0;
+    const int ns0 = (nsl_total + 1) / 2;
+    c.kh = kh; c.slab0 = kh ? ns0 : 0; c.nsl = kh ? nsl_total - ns0 : ns0;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) umma::tmem_alloc<512>(tmem_slot);
+    if (tid == 0) {
+        for (int i = 0; i <= TSP_STAGES; ++i) umma::mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    c.tmem = *tmem_slot;
+    if (warp < 4) {
+        const int col = warp * 32 + lane;      // M = 128: gate column m lives in lane m
+        const int kbase = c.slab0 * TS_SLAB;
+        for (int k0 = 0; k0 < c.nsl * TS_SLAB; k0 += 16) {
+            uint32_t rh[16], rl[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const float w = wval(col, kbase + k0 + q);
+                rh[q] = __float_as_uint(w);
+                rl[q] = __float_as_uint(w - __uint_as_float(__float_as_uint(w) & 0xFFFFE000u));
+            }
+            const uint32_t lane_base = c.tmem + ((uint32_t)(warp * 32) << 16);
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+                ::"r"(lane_base + (uint32_t)(TSP_A_HI + k0)), "r"(rh[0]), "r"(rh[1]), "r"(rh[2]), "r"(rh[3]), "r"(rh[4]), "r"(rh[5]), "r"(rh[6]), "r"(rh[7]),
+                  "r"(rh[8]), "r"(rh[9]), "r"(rh[10]), "r"(rh[11]), "r"(rh[12]), "r"(rh[13]), "r"(rh[14]), "r"(rh[15]) : "memory");
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+                ::"r"(lane_base + (uint32_t)(TSP_A_LO + k0)), "r"(rl[0]), "r"(rl[1]), "r"(rl[2]), "r"(rl[3]), "r"(rl[4]), "r"(rl[5]), "r"(rl[6]), "r"(rl[7]),
+                  "r"(rl[8]), "r"(rl[9]), "r"(rl[10]), "r"(rl[11]), "r"(rl[12]), "r"(rl[13]), "r"(rl[14]), "r"(rl[15]) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+}
+__device__ __forceinline__ void ts_pair_fini(TsPairCtx& c, int tid) {
+    umma::fence_before_sync();
+    __syncthreads();
+    if ((tid >> 5) == 0) umma::tmem_dealloc<512>(c.tmem);
+}
+
+// acc += ([h | x][rows, K] * W[K, pair's 128 gate columns]) restricted to the 16 units (64 columns) this CTA owns, as the
+// per-thread tile of make_map(tid, 16, .) (threads with tm.ks == 0).  himage / ximage: operand-tile images of h_{t-1} (8 slabs)
+// and x_t; send / recv: receive buffer of the partner / of this CTA ([64 lanes][ROWS] floats in global memory).
+// wait_cluster: a cluster arrive is pending; the x image is only valid after the matching wait, which every thread executes
+// here (the copy and MMA threads after the h slabs are in flight, so that the h part of the contraction overlaps it).
+__device__ __forceinline__ void phase_gemm_ts_pair(float (&acc)[RT][4], TsPairCtx& c, const char* himage, const char* ximage,
+                                                   float* send, const float* recv, int nrows, const ThreadMap& tm, int tid,
+                                                   bool wait_cluster) {
+    constexpr int NSL_H = ABCD_H / TS_SLAB;
+    const int warp = tid >> 5, lane = tid & 31;
+    // the ring may have been used through the generic proxy since the last call (P2 staging and the bounce alias it)
+    umma::fence_proxy_async();
+    __syncthreads();
+    const int n_mma = (nrows + 15) & ~15;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t cbytes = (uint32_t)((n_mma + 31) / 32) * TS_CHUNK;
+    const uint32_t par = c.n_phase & 1;
+    // slabs of h come first in this CTA's list; the wait (if any) goes between the last h slab and the first x slab
+    const int n_h = max(0, min(c.nsl, NSL_H - c.slab0));
+    if (tid == 32) {
+        for (int s = 0; s < c.nsl; ++s) {
+            if (s == n_h && wait_cluster) cluster_wait_acquire_divergent();
+            const int gs = c.slab0 + s;
+            const uint32_t bar = umma::smem_u32(&c.full[s]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(2u * cbytes) : "memory");
+            const uint32_t dst = umma::smem_u32(c.tiles + (size_t)s * TS_STAGE_BYTES);
+            const char* src = gs < NSL_H ? himage + (size_t)gs * TS_STAGE_BYTES : ximage + (size_t)(gs - NSL_H) * TS_STAGE_BYTES;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                         ::"r"(dst), "l"(src), "r"(cbytes), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                         ::"r"(dst + (uint32_t)TS_B_BYTES), "l"(src + TS_B_BYTES), "r"(cbytes), "r"(bar) : "memory");
+        }
+        if (n_h == c.nsl && wait_cluster) cluster_wait_acquire_divergent();
+    } else if (tid == 0) {
+        const uint64_t d_b0 = umma::make_desc(umma::smem_u32(c.tiles), TS_CHUNK, 512);
+        for (int s = 0; s < c.nsl; ++s) {
+            if (s == n_h && wait_cluster) cluster_wait_acquire_divergent();
+            umma::mbar_wait(&c.full[s], par);
+            umma::fence_after_sync();
+            const uint64_t sb = d_b0 + (uint64_t)((s * TS_STAGE_BYTES) >> 4);
+#pragma unroll
+            for (int kg = 0; kg < TS_SLAB / 8; ++kg) {
+                const uint64_t dbh = sb + (uint64_t)((kg * 1024) >> 4);
+                const uint64_t dbl = dbh + (uint64_t)(TS_B_BYTES >> 4);
+                const uint32_t ta_hi = c.tmem + (uint32_t)(TSP_A_HI + s * TS_SLAB + kg * 8);
+                const uint32_t ta_lo = c.tmem + (uint32_t)(TSP_A_LO + s * TS_SLAB + kg * 8);
+                mma_tf32_ts(c.tmem, ta_hi, dbh, idesc, (s > 0 || kg > 0) ? 1u : 0u);
+                mma_tf32_ts(c.tmem, ta_hi, dbl, idesc, 1u);
+                mma_tf32_ts(c.tmem, ta_lo, dbh, idesc, 1u);
+            }
+        }
+        umma::commit(c.done);
+        if (n_h == c.nsl && wait_cluster) cluster_wait_acquire_divergent();
+    } else if (wait_cluster) {
+        cluster_wait_acquire_divergent();
+    }
+    __syncwarp();
+    umma::mbar_wait(c.done, par);
+    c.n_phase += 1;
+    umma::fence_after_sync();
+
+    // accumulator lanes: quadrants 2 kh, 2 kh + 1 are this CTA's own units, the other two go to the partner.
+    // Warps w and w + 4 share lane quadrant w & 3 and split the 16-row blocks: warp < 4 takes blocks 0..2, warp >= 4 blocks 3..4.
+    const int lq = warp & 3;
+    const bool own = (lq >> 1) == c.kh;
+    const int col64 = (lq & 1) * 32 + lane;                // lane within the 64-lane half
+    const int rb0 = warp < 4 ? 0 : 3, rb1 = warp < 4 ? 3 : 5;
+    uint32_t keep[3][16];
+#pragma unroll
+    for (int bi = 0; bi < 3; ++bi) {
+        const int rb = rb0 + bi;
+        if (rb < rb1 && rb * 16 < n_mma) {
+            umma::tmem_ld16(c.tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(rb * 16), keep[bi]);
+            if (!own) {
+                float4* dst = reinterpret_cast<float4*>(send + (size_t)col64 * ROWS + rb * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    dst[q] = make_float4(__uint_as_float(keep[bi][4 * q]), __uint_as_float(keep[bi][4 * q + 1]),
+                                         __uint_as_float(keep[bi][4 * q + 2]), __uint_as_float(keep[bi][4 * q + 3]));
+            }
+        }
+    }
+    umma::fence_before_sync();
+    cluster_sync_all();           // partner partials published / visible
+    float* bounce = reinterpret_cast<float*>(c.tiles);
+    if (own) {
+#pragma unroll
+        for (int bi = 0; bi < 3; ++bi) {
+            const int rb = rb0 + bi;
+            if (rb < rb1 && rb * 16 < n_mma) {
+                const float* src = recv + (size_t)col64 * ROWS + rb * 16;
+                float4 pv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pv[q] = ld_cg4(src + 4 * q);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float a[4] = {pv[q].x, pv[q].y, pv[q].z, pv[q].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = rb * 16 + 4 * q + j;
+                        if (r < nrows) bounce[r * TSP_BOUNCE_PITCH + col64] = __uint_as_float(keep[bi][4 * q + j]) + a[j];
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tm.active && tm.ks == 0) {
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            const int r = tm.rg + i * RG;
+            if (r < nrows) {
+                const float4 v = *reinterpret_cast<const float4*>(bounce + r * TSP_BOUNCE_PITCH + tm.cg * 4);
+                acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
+            }
+        }
+    }
+    // the bounce aliases the ring: later bulk copies (async proxy) must not overtake these generic accesses
+    umma::fence_proxy_async();
+    __syncthreads();
+}
+
 }  // namespace rnn
