@@ -551,6 +551,8 @@ def main():
 	if line is not None:
 		emit_json(line)
 	if world > 1:
+		learner.release_graphs()   # recorded steps hold NCCL kernels: drop them before tearing the communicator down
+		torch.distributed.barrier()
 		torch.distributed.destroy_process_group()
 
 

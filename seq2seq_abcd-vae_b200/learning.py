@@ -323,6 +323,16 @@ class Learner(object):
 			self._graphs.popitem(last=False)
 		return entry
 
+	def release_graphs(self):
+		"""Drop the recorded steps.  Call before torch.distributed.destroy_process_group(): a live CUDA graph that contains
+		NCCL kernels keeps the communicator busy and the tear-down blocks."""
+		torch.cuda.synchronize(self.device)
+		self._graphs.clear()
+		self._graph_seen.clear()
+		import gc
+		gc.collect()
+		torch.cuda.synchronize(self.device)
+
 	def kernel_launches(self):
 		"""Kernels of this library enqueued so far, including those replayed from recorded graphs."""
 		return int(L.load().abcd_launch_count()) + self._replayed_launches
