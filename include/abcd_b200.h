@@ -144,6 +144,23 @@ int abcd_sampler_kl_fwd(const abcd_sampler_params_t* p, int B, const float* logi
                         float* kl_out /*scalar*/, float* kl_ws, void* stream);
 int abcd_sampler_kl_bwd(const abcd_sampler_params_t* p, const abcd_sampler_grads_t* g, int B, const float* logits,
                         float entire_data_size, const float* g_kl /*scalar*/, float* d_logits, float* kl_ws, void* stream);
+/* The three calls above (after the to_code_like MLP) as ONE forward and ONE backward kernel -- BASELINE.json north star item 3:
+ * logits = xc codebook / sqrt(f); y = softmax(logits) (mode 0) or softmax((logits + G) / tau) (mode 1); features = y codebook^T;
+ * KL as abcd_sampler_kl_fwd.  G: gumbel_noise [B,K], or NULL to draw it in the kernel from the Philox stream
+ * (element e of the [B,K] tensor = component e & 3 of block offset + *d_base + (e >> 2): the same draws abcd_philox_fill makes).
+ * The codebook lives in shared memory: needs abcd_sampler_fused_supported(f, K) (f <= 512, K <= 256, f*K*4 <= ~200 KB).
+ * ws: abcd_sampler_fused_ws_floats(K) floats (256-byte aligned), no state carried between calls.
+ * bwd: d_features [B,f] and the scalar g_kl are the upstream gradients; d_xc [B,f] is written, the codebook and
+ * posterior_shape_logits gradients are accumulated into g; scratch: B*K floats. */
+int abcd_sampler_fused_supported(int f, int K);
+size_t abcd_sampler_fused_ws_floats(int K);
+int abcd_sampler_fused_fwd(const abcd_sampler_params_t* p, int B, const float* xc /*[B,f]*/, int mode, float tau, const float* gumbel_noise,
+                           uint64_t seed, uint64_t offset, const uint64_t* d_base, float entire_data_size,
+                           float* logits /*[B,K]*/, float* y /*[B,K] saved*/, float* features /*[B,f]*/, float* kl_out /*scalar*/,
+                           float* ws, void* stream);
+int abcd_sampler_fused_bwd(const abcd_sampler_params_t* p, const abcd_sampler_grads_t* g, int B, const float* xc,
+                           const float* logits, const float* y, int mode, float tau, float entire_data_size,
+                           const float* d_features, const float* g_kl, float* d_xc, float* scratch, float* ws, void* stream);
 /* per-batch perplexities of Learner.train (learning.py:171-178): out3 = cluster, batch-mean, Dirichlet-shape */
 int abcd_sampler_stats(int B, int K, const float* logits, const float* shape_logits, float* scratch_K, float* out3, void* stream);
 /* Encoder.encode (encode.py:28-32): probs = softmax(logits) and the row arg-max category */

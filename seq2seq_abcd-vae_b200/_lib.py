@@ -91,6 +91,12 @@ SIGNATURES = {
 	'abcd_sampler_kl_ws_floats': (C.c_size_t, [C.c_int]),
 	'abcd_sampler_kl_fwd': (C.c_int, [P(SamplerParamsT), C.c_int, c_f32p, C.c_float, c_f32p, c_f32p, C.c_void_p]),
 	'abcd_sampler_kl_bwd': (C.c_int, [P(SamplerParamsT), P(SamplerGradsT), C.c_int, c_f32p, C.c_float, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+	'abcd_sampler_fused_supported': (C.c_int, [C.c_int, C.c_int]),
+	'abcd_sampler_fused_ws_floats': (C.c_size_t, [C.c_int]),
+	'abcd_sampler_fused_fwd': (C.c_int, [P(SamplerParamsT), C.c_int, c_f32p, C.c_int, C.c_float, c_f32p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_float,
+									c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+	'abcd_sampler_fused_bwd': (C.c_int, [P(SamplerParamsT), P(SamplerGradsT), C.c_int, c_f32p, c_f32p, c_f32p, C.c_int, C.c_float, C.c_float,
+									c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
 	'abcd_sampler_stats': (C.c_int, [C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
 	'abcd_softmax_argmax': (C.c_int, [C.c_int, C.c_int, c_f32p, c_f32p, c_i32p, C.c_void_p]),
 	'abcd_mlp_fwd': (C.c_int, [P(MlpParamsT), C.c_int, c_f32p, c_f32p, c_f32p, C.c_void_p]),

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libabcd_b200.so')
-SOURCES = ['api.cu', 'sgemm.cu', 'umma_gemm.cu', 'umma_rm_gemm.cu', 'latency_probe.cu', 'enc.cu', 'dec.cu', 'sampler.cu', 'stft.cu', 'optim.cu', 'csv.cu']
+SOURCES = ['api.cu', 'sgemm.cu', 'umma_gemm.cu', 'umma_rm_gemm.cu', 'latency_probe.cu', 'enc.cu', 'dec.cu', 'sampler.cu', 'sampler_fused.cu', 'stft.cu', 'optim.cu', 'csv.cu']
 # layout probes used by tools/ (not product code): a separate test library, built on demand by build_probe()
 PROBE_LIB_PATH = os.path.join(HERE, 'libabcd_b200_probe.so')
 PROBE_SOURCES = ['umma_probe.cu', 'probe_api.cu']

@@ -199,6 +199,22 @@ int abcd_sampler_kl_bwd(const abcd_sampler_params_t* p, const abcd_sampler_grads
                         float n_data, const float* g_kl, float* d_logits, float* ws, void* stream) {
     return sampler_kl_backward(to_sp(p), to_sg(g), B, logits, n_data, g_kl, d_logits, ws, S(stream));
 }
+int abcd_sampler_fused_supported(int f, int K) { return sampler_fused_supported(f, K); }
+size_t abcd_sampler_fused_ws_floats(int K) { return sampler_fused_ws_floats(K); }
+int abcd_sampler_fused_fwd(const abcd_sampler_params_t* p, int B, const float* xc, int mode, float tau, const float* gumbel_noise,
+                           uint64_t seed, uint64_t offset, const uint64_t* d_base, float entire_data_size,
+                           float* logits, float* y, float* features, float* kl_out, float* ws, void* stream) {
+    ARG_CHECK(p, "sampler_fused_fwd: null argument");
+    return sampler_fused_forward(to_sp(p), B, xc, mode, tau, gumbel_noise, seed, offset, (const unsigned long long*)d_base,
+                                 entire_data_size, logits, y, features, kl_out, ws, S(stream));
+}
+int abcd_sampler_fused_bwd(const abcd_sampler_params_t* p, const abcd_sampler_grads_t* g, int B, const float* xc,
+                           const float* logits, const float* y, int mode, float tau, float entire_data_size,
+                           const float* d_features, const float* g_kl, float* d_xc, float* scratch, float* ws, void* stream) {
+    ARG_CHECK(p && g, "sampler_fused_bwd: null argument");
+    return sampler_fused_backward(to_sp(p), to_sg(g), B, xc, logits, y, mode, tau, entire_data_size, d_features, g_kl, d_xc,
+                                  scratch, ws, S(stream));
+}
 int abcd_sampler_stats(int B, int K, const float* logits, const float* shape_logits, float* scratch_K, float* out3, void* stream) {
     return sampler_stats(B, K, logits, shape_logits, scratch_K, out3, S(stream));
 }

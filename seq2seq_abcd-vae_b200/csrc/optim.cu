@@ -8,6 +8,7 @@
 // traffic 16 B/parameter (4 read for the norm, 8 read + 4 written for the step), +8 with momentum.
 #include "common.cuh"
 #include "stft.cuh"
+#include "philox.cuh"
 
 namespace {
 
@@ -71,24 +72,6 @@ __global__ void __launch_bounds__(OPT_THREADS) clip_sgd_kernel(float* __restrict
             g[i] = zero_grads ? 0.f : gv;
         }
 }
-
-// ---- Philox4x32-10 counter-based generator -------------------------------------------------------
-__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2]) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-    uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
-    uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
-    uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
-    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-    k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
-}
-__device__ __forceinline__ void philox4(uint64_t seed, uint64_t ctr, uint32_t (&out)[4]) {
-    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
-    uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-#pragma unroll
-    for (int r = 0; r < 10; ++r) philox_round(c, k);
-    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
-}
-__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0,1)
 
 // kind 0: standard normal (Box-Muller); kind 1: standard Gumbel  -log(-log U)  (= -log of an Exp(1) draw,
 // torch.nn.functional.gumbel_softmax's noise, model.py:604)

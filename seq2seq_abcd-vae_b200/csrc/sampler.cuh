@@ -32,3 +32,13 @@ int softmax_argmax(int B, int K, const float* logits, float* probs, int* argmax,
 int gauss_latent_forward(long n, const float* mean, const float* lv, const float* eps, float* z, float* kl_out, float* partial, cudaStream_t stream);
 int gauss_latent_backward(long n, const float* mean, const float* lv, const float* eps, const float* dz, const float* g_kl,
                           float* dmean, float* dlv, cudaStream_t stream);
+
+// fused ABCD sampler (sampler_fused.cu)
+int sampler_fused_supported(int f, int K);
+size_t sampler_fused_ws_floats(int K);
+int sampler_fused_forward(const SamplerParams& P, int B, const float* xc, int mode, float tau, const float* gumbel,
+                          unsigned long long seed, unsigned long long offset, const unsigned long long* d_base, float n_data,
+                          float* logits, float* y, float* feats, float* kl_out, float* ws, cudaStream_t stream);
+int sampler_fused_backward(const SamplerParams& P, const SamplerGrads& G, int B, const float* xc, const float* logits,
+                           const float* y, int mode, float tau, float n_data, const float* d_feats, const float* g_kl,
+                           float* d_xc, float* scratch, float* ws, cudaStream_t stream);

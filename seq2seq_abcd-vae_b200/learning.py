@@ -148,6 +148,8 @@ class Learner(object):
 
 	def _latent(self, last_hidden, num_strings, is_pretraining):
 		"""-> (decoder input features, KL summed over the batch, category logits)  (learning.py:150-152)"""
+		if self.feature_sampler.fused_supported():   # one fused kernel after the to_code_like MLP (codebook fits in shared memory)
+			return self.feature_sampler.forward_sample_kl(last_hidden, num_strings, no_sample=is_pretraining)
 		category_logits = self.feature_sampler(last_hidden)
 		features = self.feature_sampler.sample(category_logits, no_sample=is_pretraining)
 		kl_loss = self.feature_sampler.kl_divergence(category_logits, num_strings)

@@ -539,6 +539,59 @@ class _KlFn(torch.autograd.Function):
 		return dlogits, dshape_ret, None, None
 
 
+class _SamplerFusedFn(torch.autograd.Function):
+	"""logits / sample / features / KL of the ABCD sampler in one kernel each way (abcd_sampler_fused_fwd / _bwd)."""
+
+	@staticmethod
+	def forward(ctx, xc, codebook, shape_logits, mode, tau, gumbel, prior_c, n_data):
+		global _noise_rel
+		lib = L.ensure_device(xc.device)
+		xc = _f32(xc)
+		B, f = xc.shape
+		K = codebook.shape[1]
+		dev = xc.device
+		logits = torch.empty(B, K, dtype=torch.float32, device=dev)
+		y = torch.empty_like(logits)
+		feats = torch.empty(B, f, dtype=torch.float32, device=dev)
+		kl = torch.empty((), dtype=torch.float32, device=dev)
+		ws = torch.empty(lib.abcd_sampler_fused_ws_floats(K) + 64, dtype=torch.float32, device=dev)
+		sp = L.SamplerParamsT()
+		sp.f, sp.K, sp.codebook, sp.shape_logits, sp.prior_c = f, K, L.ptr(codebook), L.ptr(shape_logits), float(prior_c)
+		key, rel, ctr = 0, 0, None
+		if mode and gumbel is None:   # in-kernel Philox draws: the same stream positions noise_like() would use for a [B, K] tensor
+			key, rel, ctr = _noise_key(), _noise_rel, L.ptr(_noise_counter(dev))
+			_noise_rel += (B * K + 3) // 4
+		L.call('abcd_sampler_fused_fwd', C.byref(sp), B, L.ptr(xc), int(mode), float(tau), L.ptr(gumbel), key, rel, ctr, float(n_data),
+			L.ptr(logits), L.ptr(y), L.ptr(feats), L.ptr(kl), L.ptr(ws), L.stream_ptr())
+		ctx.save_for_backward(xc, logits, y, codebook, shape_logits)
+		ctx.cfg = (int(mode), float(tau), float(prior_c), float(n_data))
+		ctx.mark_non_differentiable(logits, y)
+		ctx.set_materialize_grads(False)
+		return feats, kl, logits, y
+
+	@staticmethod
+	def backward(ctx, d_feats, g_kl, _dl, _dy):
+		xc, logits, y, codebook, shape_logits = ctx.saved_tensors
+		mode, tau, prior_c, n_data = ctx.cfg
+		lib = L.load()
+		B, f = xc.shape
+		K = codebook.shape[1]
+		dev = xc.device
+		d_feats = _f32(d_feats) if d_feats is not None else torch.zeros(B, f, dtype=torch.float32, device=dev)
+		g_kl = _f32(g_kl) if g_kl is not None else torch.zeros((), dtype=torch.float32, device=dev)
+		(gcb, gsl), (gcb_ret, gsl_ret) = _grad_buffers((codebook, shape_logits))
+		d_xc = torch.empty_like(xc)
+		scratch = torch.empty(B * K, dtype=torch.float32, device=dev)
+		ws = torch.empty(lib.abcd_sampler_fused_ws_floats(K) + 64, dtype=torch.float32, device=dev)
+		sp = L.SamplerParamsT()
+		sp.f, sp.K, sp.codebook, sp.shape_logits, sp.prior_c = f, K, L.ptr(codebook), L.ptr(shape_logits), prior_c
+		sg = L.SamplerGradsT()
+		sg.codebook, sg.shape_logits = L.ptr(gcb), L.ptr(gsl)
+		L.call('abcd_sampler_fused_bwd', C.byref(sp), C.byref(sg), B, L.ptr(xc), L.ptr(logits), L.ptr(y), mode, tau, n_data,
+			L.ptr(d_feats), L.ptr(g_kl), L.ptr(d_xc), L.ptr(scratch), L.ptr(ws), L.stream_ptr())
+		return d_xc, gcb_ret, gsl_ret, None, None, None, None, None
+
+
 class ABCDSampler(torch.nn.Module):
 	""" "A"ttention-"B"ased "C"ategorical sampler with the "D"irichlet prior."""
 
@@ -581,6 +634,25 @@ class ABCDSampler(torch.nn.Module):
 		feats, y = _SampleFn.apply(logits, self.codebook, mode, self.temperature, noise)
 		self.last_sample_probs = y
 		return feats
+
+	def fused_supported(self):
+		return bool(L.load().abcd_sampler_fused_supported(self.codebook.shape[0], self.codebook.shape[1]))
+
+	def forward_sample_kl(self, x, entire_data_size, no_sample=False):
+		"""forward() + sample() + kl_divergence() of the reference (learning.py:150-152) with ONE kernel after the to_code_like
+		MLP (and one for its backward): returns (features, KL summed over the batch, category logits).  The logits come back
+		detached (they only feed the perplexity log line and the arg-max)."""
+		xc = self.to_code_like(x)
+		noise = None
+		if not no_sample:
+			noise = self.injected_gumbel_noise
+			self.injected_gumbel_noise = None
+			if noise is not None:
+				noise = _f32(noise)
+		feats, kl, logits, y = _SamplerFusedFn.apply(xc, self.codebook, self.posterior_shape_logits, 0 if no_sample else 1,
+													self.temperature, noise, float(self._prior_c), float(entire_data_size))
+		self.last_sample_probs = y
+		return feats, kl, logits
 
 	def kl_divergence(self, logits, entire_data_size):
 		"""KL(q(pi) q(z|x) || p(pi) p(z|pi)) summed over the batch."""

@@ -449,3 +449,62 @@ def test_full_size_shards_add_up_and_step_is_deterministic(abcd):
 	assert torch.allclose(l0 + l1, l_full, rtol=2e-6, atol=0), (l0 + l1, l_full)
 	worst = max(rel_to_max(a + b, f) for a, b, f in zip(g0, g1, g_full))
 	assert worst < 2e-5, worst
+
+
+@pytest.mark.parametrize('B,K,f,mode', [(93, 128, 256, 1), (512, 128, 256, 0), (7, 33, 40, 1), (200, 256, 96, 1), (5, 16, 512, 0)])
+def test_fused_sampler_matches_oracle_and_unfused(abcd, B, K, f, mode):
+	"""abcd_sampler_fused_fwd / _bwd (one kernel each way: logits, Gumbel-softmax or softmax, codebook features, Dirichlet KL)
+	against the fp64 oracle (model.py:581-639) and against the separate forward / sample / kl_divergence calls."""
+	tau, N = 0.7, 3000.0
+	smp = abcd.model.ABCDSampler(64, 32, K, f).cuda()
+	sd = CS.det_state(smp, 400 + B)
+	smp.load_state_dict(sd)
+	smp.cuda()
+	smp.temperature = tau
+	assert smp.fused_supported()
+	x = O.det_tensor((B, 64), 4100 + B, 'uniform', 1.0)
+	gum = O.det_tensor((B, K), 4200 + B, 'gumbel', 1.0)
+	wf = O.det_tensor((B, f), 4300 + B, 'uniform', 1.0)
+
+	def grads():
+		return {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in smp.named_parameters()}
+	# fused
+	smp.zero_grad(set_to_none=True)
+	xg = x.cuda().requires_grad_(True)
+	smp.injected_gumbel_noise = gum.cuda()
+	feats, kl, logits = smp.forward_sample_kl(xg, N, no_sample=(mode == 0))
+	((feats * wf.cuda()).sum() + 0.37 * kl).backward()
+	fused = dict(feats=feats.detach(), kl=kl.detach(), logits=logits.detach(), dx=xg.grad.clone(), grads=grads())
+	# separate calls
+	smp.zero_grad(set_to_none=True)
+	xg2 = x.cuda().requires_grad_(True)
+	lg = smp(xg2)
+	smp.injected_gumbel_noise = gum.cuda()
+	ft = smp.sample(lg, no_sample=(mode == 0))
+	k2 = smp.kl_divergence(lg, N)
+	((ft * wf.cuda()).sum() + 0.37 * k2).backward()
+	sep = dict(feats=ft.detach(), kl=k2.detach(), logits=lg.detach(), dx=xg2.grad.clone(), grads=grads())
+	# oracle, fp64
+	P = {k: v.double().clone().requires_grad_(v.dtype.is_floating_point and k != 'prior_concentration') for k, v in sd.items()}
+	xo = x.double().clone().requires_grad_(True)
+	ol = O.sampler_logits(xo, P)
+	of, _ = O.sampler_sample(ol, P, mode == 0, tau, gum.double())
+	ok = O.sampler_kl(ol, P, N, 1.0)
+	((of * wf.double()).sum() + 0.37 * ok).backward()
+	for name, got in (('fused', fused), ('separate', sep)):
+		assert rel_to_max(got['logits'], ol) < 1e-5, name
+		assert rel_to_max(got['feats'], of) < 1e-5, name
+		assert abs(got['kl'].item() - ok.item()) < 2e-5 * abs(ok.item()), (name, got['kl'].item(), ok.item())
+		assert rel_to_max(got['dx'], xo.grad) < 1e-4, name
+		for k, g in got['grads'].items():
+			assert g is not None, (name, k)
+			assert rel_to_max(g, P[k].grad) < 1e-4, (name, k, rel_to_max(g, P[k].grad))
+	# in-kernel Philox noise draws the same numbers as noise_like() on a [B, K] tensor
+	if mode == 1:
+		abcd.model.manual_noise_seed(99)
+		with torch.no_grad():
+			f1, _, _ = smp.forward_sample_kl(x.cuda(), N)
+		abcd.model.manual_noise_seed(99)
+		with torch.no_grad():
+			f2 = smp.sample(smp(x.cuda()))
+		assert rel_to_max(f1, f2) < 1e-5

@@ -67,6 +67,13 @@ def _hook_noise(learner, plain):
 				smp.injected_gumbel_noise = O.det_tensor(tuple(logits.shape), GUMBEL_SEED + state['call'] + 1, 'gumbel', 1.0).cuda()
 			return orig(logits, no_sample=no_sample)
 		smp.sample = sample
+		orig_fused = smp.forward_sample_kl
+
+		def forward_sample_kl(x, entire_data_size, no_sample=False):   # the Learner's fused path
+			if not no_sample:
+				smp.injected_gumbel_noise = O.det_tensor((x.shape[0], smp.num_categories), GUMBEL_SEED + state['call'] + 1, 'gumbel', 1.0).cuda()
+			return orig_fused(x, entire_data_size, no_sample=no_sample)
+		smp.forward_sample_kl = forward_sample_kl
 	return state
 
 
