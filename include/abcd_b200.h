@@ -102,7 +102,9 @@ int abcd_debug_dec_timing(unsigned long long* out16);
 int abcd_measure_cluster_exchange(int cluster_size, int iters, int mode, float* out2, float* scratch, void* stream);
 /* Recurrent contractions of the encoder forward / backward and the decoder backward (model.py:60-66, 165-196): on the tensor
  * cores (tcgen05 kind::tf32, weights resident in tensor memory, 3xTF32 split, fp32-grade; default) or on the FFMA path.  on = 1/0; -1 only queries.  Returns
- * the previous setting.  Initial value: env ABCD_RNN_TC (default 1). */
+ * the previous setting.  Initial value: env ABCD_RNN_TC (default 1).  This is a PROCESS-WIDE debug switch (PyTorch runs backward
+ * passes on its own threads, so it cannot be thread-local): the only mutable global of the library; every compute entry point is
+ * re-entrant across streams and threads as long as the switch is not flipped concurrently. */
 int abcd_set_rnn_tensorcore(int on);
 /* kernel launches enqueued by this library since load (what bench.py reports as gpu_launches) */
 long long abcd_launch_count(void);

@@ -735,6 +735,8 @@ size_t enc_fwd_smem(bool tc) {
 }
 // tensor-core recurrence (default); env ABCD_RNN_TC=0 or abcd_set_rnn_tensorcore(0) selects the FFMA path
 }  // namespace
+// process-wide debug switch (parity tests run the FFMA kernels through it); autograd runs the backward pass on another thread,
+// so it cannot be thread-local.  Not part of the re-entrant compute surface: set it before issuing work from several threads.
 static int g_rnn_tc = -1;
 bool rnn_use_tc() {
     if (g_rnn_tc < 0) { const char* e = getenv("ABCD_RNN_TC"); g_rnn_tc = (e && e[0] == '0') ? 0 : 1; }

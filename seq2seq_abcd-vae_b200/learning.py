@@ -269,15 +269,21 @@ class Learner(object):
 				with torch.cuda.stream(side):
 					pending.append(torch.distributed.all_reduce(tail, op=torch.distributed.ReduceOp.SUM, group=self.process_group, async_op=True))
 				return grad
+		nvtx = torch.cuda.nvtx
+		nvtx.range_push('abcd/forward')
 		emission_loss, end_loss, kl_loss, logits = self.forward_losses(packed_input, is_offset, speaker, num_strings, is_pretraining,
 																		hidden_grad_hook=hook)
 		batch_size = int(packed_input.batch_sizes[0]) if global_batch_size is None else global_batch_size
 		loss = (emission_loss + end_loss + kl_loss) / batch_size
+		nvtx.range_pop()
+		nvtx.range_push('abcd/backward')
 		# kernels add straight into the flat gradient arena; the decoder's weight-gradient GEMMs run on a second stream beside
 		# the sampler backward and the encoder BPTT (which leaves 36 of the 148 SMs idle)
 		with model.accumulate_into_grad(), model.weight_gradient_stream(side):
 			loss.backward()
 		torch.cuda.current_stream().wait_stream(side)
+		nvtx.range_pop()
+		nvtx.range_push('abcd/allreduce+clip+sgd')
 		if self.world_size > 1:
 			if pending:
 				head = self.arena.grad[:self.arena.offsets[self._n_enc_params]]
@@ -292,6 +298,7 @@ class Learner(object):
 		momentum = self.optimizer.param_groups[0]['momentum']
 		self.arena.clip_and_step(lr, momentum, self.gradient_clip)
 		model.noise_commit(self.device)
+		nvtx.range_pop()
 		return loss, emission_loss, end_loss, kl_loss, logits
 
 	# -- CUDA-graph replay of a recorded step ---------------------------------------------------------------

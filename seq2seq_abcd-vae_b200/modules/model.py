@@ -10,6 +10,7 @@ reference, hence identical weights under the same seed); their forward methods a
 Out of scope: ESN cells, the bidirectional decoder, decoder input dropout /
 greedy decoding and multi-layer encoders raise NotImplementedError instead of silently running something else.
 """
+import collections
 import ctypes as C
 import math
 
@@ -94,18 +95,27 @@ def _ws(nbytes, device):
 	return torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
 
 
+_DESC_CACHE_MAX = 8
+_DESC_CACHE = collections.OrderedDict()
+
+
 def as_packed_desc(batch_sizes, device, cache=None):
-	"""Build (or fetch from `cache`) the device descriptor for a PackedSequence.batch_sizes tensor."""
+	"""Build (or fetch from `cache`) the device descriptor for a PackedSequence.batch_sizes tensor.  The cache is ONE small
+	LRU shared by the encoder and the decoder (both see the same batch_sizes in a step), keyed by the raw bytes of the
+	tensor: shuffled training batches almost never repeat a layout, so it holds a handful of entries, not one per step."""
 	if isinstance(batch_sizes, L.Packed):
 		return batch_sizes
-	key = None
-	if cache is not None:
-		key = tuple(int(v) for v in batch_sizes)
-		if key in cache:
-			return cache[key]
-	desc = L.Packed(batch_sizes, device)
-	if cache is not None:
-		cache[key] = desc
+	cache = _DESC_CACHE
+	bs = torch.as_tensor(batch_sizes, dtype=torch.int64, device='cpu')
+	key = (str(device), bs.numpy().tobytes())
+	desc = cache.get(key)
+	if desc is not None:
+		cache.move_to_end(key)
+		return desc
+	desc = L.Packed(bs, device)
+	cache[key] = desc
+	while len(cache) > _DESC_CACHE_MAX:
+		cache.popitem(last=False)
 	return desc
 
 
