@@ -649,6 +649,322 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_pair_kernel(DecK p) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// forward, pair variant ONE STEP AHEAD (default for output_size <= 88; rnn_ts.cuh "one step ahead"): the recurrent product
+// h_t W_hh of step t + 1 runs on tcgen05 underneath the emission MLPs of step t, the critical path of P1 is the input product
+// x_t W_ih (FFMA, K = Fp, one staged chunk) plus the cell update:
+//   P1   gates = gpre (h_{t-1} W_hh, ready) + x_{t-1} W_ih;  cell;  h_t published (rows + operand-tile image)   -- cluster barrier A --
+//        [thread 224: bulk copies of the h_t image]
+//   P2   hidden layers of the two emission MLPs (staged FFMA, K = H)
+//        [thread 224: MMAs of h_t W_hh while warps 0..6 do P3a]      P3a partial emission parameters (K-split)
+//        accumulator read-back: own half -> gpre, partner's half -> L2                                            -- cluster barrier B --
+//   P3b  partner's half added to gpre;  emission parameters, sample x_t, NLL                                      -- cluster barrier C (split) --
+// Shared memory: [h ring 4 x 24 KB | W1 | W2s | Wx | gpre | staging (P2: 2 x KC = 64; x: one chunk of 128) | scratch]
+// -------------------------------------------------------------------------------------------------
+constexpr int DFA_KC = 64;     // staged K-chunk of P2
+constexpr int DFA_XKC = 128;   // the x rows are staged as ONE chunk (Fp <= 128)
+constexpr int DFA_STAGES = ABCD_H / TS_SLAB / 2;   // ring stages = h slabs of one CTA of a pair
+constexpr int DFA_MMA_TID = 224;                   // lane 0 of warp 7: copy + MMA thread (warp 7 has no share of the P2 epilogue and of P3a)
+__host__ __device__ constexpr size_t dfa_stage_floats() {
+    return (size_t)2 * ROWS * (DFA_KC + 4) > (size_t)ROWS * (DFA_XKC + 4) ? (size_t)2 * ROWS * (DFA_KC + 4) : (size_t)ROWS * (DFA_XKC + 4);
+}
+static_assert(DFA_STAGES <= TSP_STAGES && DFA_STAGES <= TSP_MAX_SLABS, "ring / tensor-memory geometry of the pair variant");
+static_assert((size_t)ROWS * 4 * U <= dfa_stage_floats(), "K-split scratch of the x product must fit in the staging area");
+
+template <int CELL>
+__global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
+    extern __shared__ __align__(1024) float smem_ahead[];
+    float* const smem = smem_ahead;
+    const int H = ABCD_H, M = ABCD_M;
+    const int F = p.F, Fp = p.Fp;
+    const int XC = xcols_per_cta(F);
+    constexpr int KC = DFA_KC;
+    constexpr int HSP = 2 * U + 4;            // pitch of the CTA's own hidden-layer slice kept in shared memory
+    float* W1 = reinterpret_cast<float*>(reinterpret_cast<char*>(smem) + (size_t)DFA_STAGES * TS_STAGE_BYTES);   // [H][2U]
+    float* W2s = W1 + H * (2 * U);            // [U][2Fp]: rows of the output layers that multiply this CTA's hidden units
+    float* Wx = W2s + U * 2 * Fp;             // [Fp][4U]: input rows of the gate weights of this CTA's units
+    float* gpre = Wx + Fp * (4 * U);          // [ROWS][TSP_GP]: h_{t-1} W_hh of this CTA's gate columns
+    float* stage_base = gpre + ROWS * TSP_GP;
+    float* red = stage_base + dfa_stage_floats();   // 40 floats
+    const Stage st = make_stage(stage_base, KC);
+    const Stage stx = make_stage(stage_base, DFA_XKC);   // only buf0 is used (one chunk)
+    float* Hs = st.buf0;                      // [ROWS][HSP] (the staging buffers are idle between phases)
+    __shared__ uint64_t tsp_bars[TSP_STAGES + 1];
+    __shared__ uint32_t tsp_tmem_slot;
+    TsPairCtx tsp;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int rank = (int)cluster_ctarank();
+    const int tile = blockIdx.x / CL;
+    const int u0 = rank * U;                  // the 16 units this CTA finalises (cell update, MLP slices)
+    const int pair_u0 = (rank >> 1) * 2 * U;  // the 32 units whose gate columns the pair contracts
+    const int xc0 = rank * XC;
+    const int xc1 = min(F, xc0 + XC);
+
+    // ---- resident weights ----
+    if ((umma::smem_u32(smem) & 1023u) != 0) __trap();
+    {
+        auto wval = [&](int col, int k) -> float {   // recurrent weights only: k < H
+            const int u = pair_u0 + (col >> 2), s = col & 3;
+            const int gate = CELL == 0 ? s : (s == 0 ? 0 : s == 1 ? 1 : s == 3 ? 2 : -1);
+            return gate >= 0 ? __ldg(p.w_hh + (long)(gate * H + u) * H + k) : 0.f;
+        };
+        ts_pair_init(tsp, reinterpret_cast<char*>(smem), tsp_bars, &tsp_tmem_slot, rank & 1, H / TS_SLAB, wval, tid);
+    }
+    char* himg[2];
+    himg[0] = p.himg + (size_t)(tile * 2) * ts_image_bytes(ABCD_H); himg[1] = himg[0] + ts_image_bytes(ABCD_H);
+    {   // clear the images once (rows that never become active are still fetched in 32-row chunks: keep them finite)
+        float4* z = reinterpret_cast<float4*>(himg[0]);
+        const size_t n16 = 2 * ts_image_bytes(ABCD_H) / 16;
+        for (size_t i = (size_t)rank * NTHREADS + tid; i < n16; i += (size_t)CL * NTHREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    ts_image_publish();
+    cluster_sync_all();
+    for (int idx = tid; idx < H * 2 * U; idx += NTHREADS) {
+        int col = idx % (2 * U), k = idx / (2 * U);
+        int which = col / U, u = col % U;
+        W1[idx] = p.em_w1[which][(long)(u0 + u) * H + k];
+    }
+    for (int idx = tid; idx < U * 2 * Fp; idx += NTHREADS) {
+        int c = idx % (2 * Fp), kk = idx / (2 * Fp);
+        int which = c >= Fp, cc = which ? c - Fp : c;     // mean columns [0,Fp), log-variance columns [Fp,2Fp)
+        W2s[idx] = cc < F ? p.em_w2[which][(long)cc * M + u0 + kk] : 0.f;
+    }
+    for (int idx = tid; idx < Fp * 4 * U; idx += NTHREADS) {
+        const int col = idx % (4 * U), k = idx / (4 * U);
+        const int u = u0 + (col >> 2), s = col & 3;
+        const int gate = CELL == 0 ? s : (s == 3 ? -1 : s);
+        Wx[idx] = (gate >= 0 && k < F) ? p.w_ih[(long)(gate * H + u) * F + k] : 0.f;
+    }
+
+    // ---- per-thread constants for the three phases ----
+    const int KS1 = min(2, pick_ks(U));
+    const ThreadMap tm1 = make_map(tid, U, KS1);      // x product: K split over two thread groups; cell update: group 0
+    const bool cell_thread = tm1.active && tm1.ks == 0;
+    const int unit = u0 + tm1.cg;
+    float bias1[4];
+    if (CELL == 0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) bias1[g] = p.b_ih[g * H + unit] + p.b_hh[g * H + unit];
+    } else {
+        bias1[0] = p.b_ih[unit] + p.b_hh[unit];
+        bias1[1] = p.b_ih[H + unit] + p.b_hh[H + unit];
+        bias1[2] = p.b_ih[2 * H + unit];
+        bias1[3] = p.b_hh[2 * H + unit];
+    }
+    const int KS2 = pick_ks_fit(2 * U / 4, 2 * U, KC);
+    const ThreadMap tm2 = make_map(tid, 2 * U / 4, KS2);
+    float bias2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int col = tm2.cg * 4 + j;
+        bias2[j] = p.em_b1[col / U][u0 + col % U];
+    }
+    const int ncg3 = 2 * Fp / 4;                                      // column groups of the local emission GEMM
+    float* Pmine = p.Pbuf + (long)blockIdx.x * ROWS * (2 * Fp);       // this CTA's partial emission parameters
+    const float* Ptile = p.Pbuf + (long)tile * CL * ROWS * (2 * Fp);  // partials of all CTAs of the cluster
+    // pair exchange of the gate partial sums (the backward pass's partial buffer is idle during the forward pass)
+    float* pair_send = p.Pb2 + (size_t)(blockIdx.x ^ 1) * ROWS * H;
+    const float* pair_recv = p.Pb2 + (size_t)blockIdx.x * ROWS * H;
+
+    // recurrent state of (row, unit) pairs owned by this thread
+    float creg[RT], hreg[RT];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+        int b = tile + p.n_tiles * (tm1.rg + i * RG);
+        creg[i] = 0.f; hreg[i] = 0.f;
+        if (b < p.B && cell_thread) {
+            hreg[i] = p.Hall[(long)b * H + unit];
+            if (CELL == 0) creg[i] = p.Call[(long)b * H + unit];
+        }
+    }
+    const int Tt = p.lengths[tile];
+    float nll = 0.f;
+    const int n_tiles = p.n_tiles, B = p.B;
+    const float* Hall = p.Hall; const float* Xall = p.Xall;
+    // image of the initial state and its recurrent product (gpre of step 0)
+    if (cell_thread) {
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            const int r = tm1.rg + i * RG;
+            if (tile + p.n_tiles * r < p.B) ts_image_store(himg[1], unit, r, hreg[i]);
+        }
+    }
+    ts_image_publish();
+    cluster_sync_all();
+    if (Tt > 0) {
+        const int na0 = active_rows(p.batch_sizes[0], tile, n_tiles);
+        if (tid == DFA_MMA_TID) { ts_pair_fetch(tsp, himg[1], na0); ts_pair_issue(tsp, na0); }
+        __syncwarp();
+        ts_pair_drain_send(tsp, gpre, pair_send, na0, tid);
+        cluster_sync_all();
+        ts_pair_drain_recv(tsp, gpre, pair_recv, na0, tid);
+    }
+    __syncthreads();
+    const bool timing = p.timing == 1 && blockIdx.x == 0 && tid == 64;
+    unsigned long long tacc[16];
+    for (int i = 0; i < 16; ++i) tacc[i] = 0;
+#define DEC_TICK(slot) if (timing) { long long now_ = clock64(); tacc[slot] += now_ - tick_; tick_ = now_; }
+
+    for (int t = 0; t < Tt; ++t) {
+        long long tick_ = timing ? clock64() : 0;
+        const int na = active_rows(p.batch_sizes[t], tile, n_tiles);
+        const int na_next = t + 1 < Tt ? active_rows(p.batch_sizes[t + 1], tile, n_tiles) : 0;
+        const long off_t = p.offsets[t];
+        const long prev_base = t == 0 ? 0 : (long)B + p.offsets[t - 1];
+
+        // ---- P1: gates + cell ----
+        {
+            float acc[RT][4];
+            zero_acc(acc);
+            if (t > 0) cluster_wait_acquire();   // x_{t-1} of every column owner is visible
+            DEC_TICK(0)
+            auto rpx = [=](int r) -> const float* { return Xall + (prev_base + tile + (long)n_tiles * r) * Fp; };
+            phase_gemm<NTHREADS, DFA_XKC, 4 * U>(acc, stx, Fp, rpx, 0, NullRow(), na, Wx, tm1, KS1, tid);
+            DEC_TICK(1)
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+                int r = tm1.rg + i * RG;
+                if (r >= na || !cell_thread) continue;
+                long frame = off_t + tile + (long)n_tiles * r;
+                const float4 hp = *reinterpret_cast<const float4*>(gpre + r * TSP_GP + tm1.cg * 4);
+                const float a0 = acc[i][0] + hp.x, a1 = acc[i][1] + hp.y, a2 = acc[i][2] + hp.z, a3 = acc[i][3] + hp.w;
+                float h;
+                if (CELL == 0) {
+                    float ig = sigmoid_acc(a0 + bias1[0]);
+                    float fg = sigmoid_acc(a1 + bias1[1]);
+                    float gg = tanhf(a2 + bias1[2]);
+                    float og = sigmoid_acc(a3 + bias1[3]);
+                    float c = fg * creg[i] + ig * gg;
+                    h = og * tanhf(c);
+                    creg[i] = c;
+                    *reinterpret_cast<float4*>(p.Gs + frame * (4 * H) + unit * 4) = make_float4(ig, fg, gg, og);
+                    p.Call[((long)B + frame) * H + unit] = c;
+                } else {
+                    float rg_ = sigmoid_acc(a0 + bias1[0]);
+                    float zg = sigmoid_acc(a1 + bias1[1]);
+                    float hn = a3 + bias1[3];
+                    float ng = tanhf(a2 + bias1[2] + rg_ * hn);
+                    h = (1.f - zg) * ng + zg * hreg[i];
+                    *reinterpret_cast<float4*>(p.Gs + frame * (4 * H) + unit * 4) = make_float4(rg_, zg, ng, hn);
+                }
+                hreg[i] = h;
+                p.Hall[((long)B + frame) * H + unit] = h;
+                if (na_next > 0) ts_image_store(himg[t & 1], unit, r, h);
+            }
+        }
+        ts_image_publish();
+        DEC_TICK(2)
+        cluster_sync_all();   // A: h_t visible
+        DEC_TICK(3)
+        if (tid == DFA_MMA_TID && na_next > 0) ts_pair_fetch(tsp, himg[t & 1], na_next);
+
+        // ---- P2: hidden layers of the two emission MLPs ----
+        {
+            float acc[RT][4];
+            zero_acc(acc);
+            auto rph = [=](int r) -> const float* { return Hall + ((long)B + off_t + tile + (long)n_tiles * r) * ABCD_H; };
+            phase_gemm<NTHREADS, KC, 2 * U>(acc, st, H, rph, 0, NullRow(), na, W1, tm2, KS2, tid);
+            DEC_TICK(4)
+            if (warp == 7) {
+                // (warp 7 holds a K-split share of P2 only: no epilogue rows, no P3a items)
+                if (tid == DFA_MMA_TID && na_next > 0) ts_pair_issue(tsp, na_next);
+                __syncwarp();
+            } else {
+                if (tm2.active && tm2.ks == 0) {
+#pragma unroll
+                    for (int i = 0; i < RT; ++i) {
+                        int r = tm2.rg + i * RG;
+                        if (r >= na) continue;
+                        long frame = off_t + tile + (long)n_tiles * r;
+                        int col = tm2.cg * 4;
+                        int which = col / U, uu = col % U;
+                        float4 v = make_float4(tanhf(acc[i][0] + bias2[0]), tanhf(acc[i][1] + bias2[1]),
+                                               tanhf(acc[i][2] + bias2[2]), tanhf(acc[i][3] + bias2[3]));
+                        *reinterpret_cast<float4*>(p.Hid + frame * (2 * M) + which * M + u0 + uu) = v;
+                        *reinterpret_cast<float4*>(Hs + r * HSP + col) = v;
+                    }
+                }
+                asm volatile("bar.sync 1, 224;\n" ::: "memory");   // warps 0..6: the hidden slice is complete
+                // ---- P3a: this CTA's share of the emission parameters (K-split over the hidden units, see dec_fwd_kernel) ----
+                for (int item = tid; item < ncg3 * 16; item += NTHREADS - 32) {
+                    const int cg = item % ncg3, r0 = item / ncg3;   // rows r0 + 16 i
+                    if (r0 >= na) continue;
+                    const float* a = Hs + r0 * HSP + ((cg * 4 < Fp) ? 0 : U);
+                    const float* w = W2s + cg * 4;
+                    float o[5][4];
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+#pragma unroll
+                    for (int kq = 0; kq < U / 4; ++kq) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(w + (kq * 4 + 0) * (2 * Fp));
+                        const float4 w1 = *reinterpret_cast<const float4*>(w + (kq * 4 + 1) * (2 * Fp));
+                        const float4 w2 = *reinterpret_cast<const float4*>(w + (kq * 4 + 2) * (2 * Fp));
+                        const float4 w3 = *reinterpret_cast<const float4*>(w + (kq * 4 + 3) * (2 * Fp));
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) {
+                            const float4 av = *reinterpret_cast<const float4*>(a + i * 16 * HSP + kq * 4);
+                            o[i][0] = fmaf(av.x, w0.x, o[i][0]); o[i][1] = fmaf(av.x, w0.y, o[i][1]); o[i][2] = fmaf(av.x, w0.z, o[i][2]); o[i][3] = fmaf(av.x, w0.w, o[i][3]);
+                            o[i][0] = fmaf(av.y, w1.x, o[i][0]); o[i][1] = fmaf(av.y, w1.y, o[i][1]); o[i][2] = fmaf(av.y, w1.z, o[i][2]); o[i][3] = fmaf(av.y, w1.w, o[i][3]);
+                            o[i][0] = fmaf(av.z, w2.x, o[i][0]); o[i][1] = fmaf(av.z, w2.y, o[i][1]); o[i][2] = fmaf(av.z, w2.z, o[i][2]); o[i][3] = fmaf(av.z, w2.w, o[i][3]);
+                            o[i][0] = fmaf(av.w, w3.x, o[i][0]); o[i][1] = fmaf(av.w, w3.y, o[i][1]); o[i][2] = fmaf(av.w, w3.z, o[i][2]); o[i][3] = fmaf(av.w, w3.w, o[i][3]);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        const int r = r0 + 16 * i;
+                        if (r < na) *reinterpret_cast<float4*>(Pmine + (long)r * (2 * Fp) + cg * 4) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+                    }
+                }
+            }
+        }
+        DEC_TICK(5)
+        // recurrent product of the NEXT step: own gate columns -> gpre, the partner's -> its receive buffer
+        if (na_next > 0) ts_pair_drain_send(tsp, gpre, pair_send, na_next, tid);
+        DEC_TICK(6)
+        cluster_sync_all();   // B: partial emission parameters and partner partials visible
+        DEC_TICK(7)
+
+        // ---- P3b: sum the partials of this CTA's x columns, reparameterised sample, NLL ----
+        for (int o = tid; o < na * XC; o += NTHREADS) {
+            const int r = o / XC, c = xc0 + o % XC;
+            if (c >= xc1) continue;
+            const long frame = off_t + tile + (long)n_tiles * r;
+            const float e = __ldg(p.eps + frame * p.ld_eps + c);
+            const float g = p.gt ? __ldg(p.gt + frame * p.ld_gt + c) : 0.f;
+            float pm[CL], pv[CL];
+#pragma unroll
+            for (int src = 0; src < CL; ++src) {
+                const float* q = Ptile + ((long)src * ROWS + r) * (2 * Fp) + c;
+                pm[src] = ld_cg(q);
+                pv[src] = ld_cg(q + Fp);
+            }
+            float mean = __ldg(p.em_b2[0] + c), lv = __ldg(p.em_b2[1] + c);
+#pragma unroll
+            for (int src = 0; src < CL; ++src) { mean += pm[src]; lv += pv[src]; }
+            const float x = mean + expf(0.5f * lv) * e;
+            p.Mean[frame * Fp + c] = mean;
+            p.Lv[frame * Fp + c] = lv;
+            p.Xall[((long)B + frame) * Fp + c] = x;
+            if (p.gt) {
+                const float d = g - mean;
+                nll += 0.5f * (LOG_2PI + lv + d * expf(-lv) * d);
+            }
+        }
+        DEC_TICK(8)
+        cluster_arrive_release();   // C: matched by the wait at the top of the next step (or the one after the loop)
+        if (na_next > 0) ts_pair_drain_recv(tsp, gpre, pair_recv, na_next, tid);   // off the critical path: under the barrier
+        DEC_TICK(9)
+    }
+#undef DEC_TICK
+    if (Tt > 0) cluster_wait_acquire();
+    if (timing) { tacc[15] = Tt; for (int i = 0; i < 16; ++i) g_dec_timing[i] = tacc[i]; }
+    float tot = block_sum(nll, red);
+    if (tid == 0) p.nll_partial[blockIdx.x] = tot;
+    ts_pair_fini(tsp, tid);
+}
+
+// -------------------------------------------------------------------------------------------------
 // backward
 // -------------------------------------------------------------------------------------------------
 // Backward.  Every contraction over a dimension that is partitioned over the cluster (the hidden units of the MLPs,
@@ -1544,7 +1860,17 @@ size_t dec_fwd_pair_smem(int F) {
     const int Fp = pad4(F);
     return (size_t)TSP_STAGES * TS_STAGE_BYTES + (size_t)(ABCD_H * 2 * U + U * 2 * Fp + 64) * sizeof(float);
 }
-// ABCD_DEC_FWD=pair (default) | ffma | tc64.  The pair variant pays one more exchange per step than the FFMA kernel and wins once a
+// one-step-ahead pair variant (default): [h ring | W1 | W2s | Wx | gpre | staging | scratch]
+size_t dec_fwd_ahead_smem(int F) {
+    const int Fp = pad4(F);
+    return (size_t)DFA_STAGES * TS_STAGE_BYTES + ((size_t)(ABCD_H * 2 * U + U * 2 * Fp + Fp * 4 * U + ROWS * TSP_GP + 64) + dfa_stage_floats()) * sizeof(float);
+}
+bool dec_fwd_use_ahead(int F) {
+    static int off = -1;
+    if (off < 0) { const char* e = getenv("ABCD_DEC_FWD"); off = (e && strcmp(e, "ahead")) ? 1 : 0; }   // any other explicit choice disables it
+    return !off && rnn_use_tc() && pad4(F) <= DFA_XKC && dec_fwd_ahead_smem(F) <= SMEM_MAX - 1024;
+}
+// ABCD_DEC_FWD=ahead (default) | pair | ffma | tc64.  The pair variant pays one more exchange per step than the FFMA kernel and wins once a
 // tile has enough rows for the tensor-core contraction to matter (measured: 1.41 vs 1.52 ms at 73 rows per tile, 1.20 vs 1.18 at 37, 1.03 vs 0.94 ms at
 // 10); below DEC_PAIR_MIN_ROWS rows per tile (small shards under strong scaling) the FFMA kernel runs.
 constexpr int DEC_PAIR_MIN_ROWS = 48;
@@ -1695,6 +2021,8 @@ int dec_max_clusters(int which, int F, int* out) {
     if (which == 1 && dec_bwd_use_ts(F))   // the tensor-memory backward
         return rnn_max_active_clusters(dec_bwd_ts_kc(F) == 64 ? (const void*)dec_bwd_ts_kernel<0, 64> : (const void*)dec_bwd_ts_kernel<0, 32>,
                                        dec_bwd_ts_smem(F), CL, NTHREADS, out);
+    if (which == 0 && dec_fwd_use_ahead(F))
+        return rnn_max_active_clusters((const void*)dec_fwd_ahead_kernel<0>, dec_fwd_ahead_smem(F), CL, NTHREADS, out);
     if (which == 0 && dec_fwd_mode(F) == 2)
         return rnn_max_active_clusters((const void*)dec_fwd_pair_kernel<0>, dec_fwd_pair_smem(F), CL, NTHREADS, out);
     const int kc = which == 0 ? dec_fwd_kc(F) : dec_bwd_kc(F);
@@ -1708,6 +2036,8 @@ int dec_init() {
     TRY(rnn_prepare_kernel((const void*)dec_bwd_ts_kernel<1, 64>, SMEM_MAX - 1024));   // the kernel also has static shared memory
     TRY(rnn_prepare_kernel((const void*)dec_bwd_ts_kernel<0, 32>, SMEM_MAX - 1024));   // the kernel also has static shared memory
     TRY(rnn_prepare_kernel((const void*)dec_bwd_ts_kernel<1, 32>, SMEM_MAX - 1024));   // the kernel also has static shared memory
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_ahead_kernel<0>, SMEM_MAX - 1024));
+    TRY(rnn_prepare_kernel((const void*)dec_fwd_ahead_kernel<1>, SMEM_MAX - 1024));
     TRY(rnn_prepare_kernel((const void*)dec_fwd_pair_kernel<0>, SMEM_MAX - 1024));
     TRY(rnn_prepare_kernel((const void*)dec_fwd_pair_kernel<1>, SMEM_MAX - 1024));
     TRY(rnn_prepare_kernel((const void*)dec_fwd_kernel<0, 64, true>, SMEM_MAX - 1024));
@@ -1761,7 +2091,11 @@ int dec_forward(const DecParams& P, const PackedMeta& pk, const float* feat_in, 
     {
         ProfScope ps(PROF_DEC_FWD, stream);
         const size_t sm = dec_fwd_smem(P.F);
-        if (dec_fwd_mode(P.F, pk.B) == 2) {
+        if (dec_fwd_use_ahead(P.F)) {
+            k.kc = DFA_KC;
+            if (P.cell == 0) TRY(launch_cluster_dec(dec_fwd_ahead_kernel<0>, n_tiles, dec_fwd_ahead_smem(P.F), stream, k));
+            else TRY(launch_cluster_dec(dec_fwd_ahead_kernel<1>, n_tiles, dec_fwd_ahead_smem(P.F), stream, k));
+        } else if (dec_fwd_mode(P.F, pk.B) == 2) {
             k.kc = DFP_KC;
             if (P.cell == 0) TRY(launch_cluster_dec(dec_fwd_pair_kernel<0>, n_tiles, dec_fwd_pair_smem(P.F), stream, k));
             else TRY(launch_cluster_dec(dec_fwd_pair_kernel<1>, n_tiles, dec_fwd_pair_smem(P.F), stream, k));

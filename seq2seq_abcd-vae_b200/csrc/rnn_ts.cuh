@@ -616,4 +616,118 @@ __device__ __forceinline__ void phase_gemm_ts_pair(float (&acc)[RT][4], TsPairCt
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Pair variant, ONE STEP AHEAD (decoder forward, default for output_size <= 88).  The gate pre-activations of step t + 1 are
+// h_t W_hh + x_t W_ih, and h_t is final a third of a step before x_t is: the recurrent product h_t W_hh (K = H, split over the
+// pair as above: 4 slabs per CTA, hi and lo weights in tensor memory) is therefore issued right after the cluster barrier that
+// publishes h_t and runs on the tensor pipe WHILE the CUDA cores compute the emission MLPs of step t; its partial-sum exchange
+// between the two CTAs rides on the cluster barrier that step already has between the hidden and the output layers.  What is
+// left on the critical path of step t + 1 is the small input product x_t W_ih (K = Fp, FFMA, one staged chunk).  The four
+// pieces below are called at the points of the step where their inputs are ready:
+//   ts_pair_fetch       (one thread)  bulk copies of this CTA's h slabs from the operand-tile image into the ring
+//   ts_pair_issue       (one thread)  waits for the slabs, issues the 3xTF32 MMAs, commits
+//   ts_pair_drain_send  (all threads) accumulator read-back: own 64 gate columns -> gpre [row][64 (+4)] in shared memory,
+//                                     the partner's 64 columns -> its receive buffer in global memory;  a cluster barrier follows
+//   ts_pair_drain_recv  (all threads) adds the partner's partial to gpre
+// The ring is touched by the async proxy only (bulk copies in, MMAs out), so no proxy fences are needed in the loop.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ts_pair_fetch(TsPairCtx& c, const char* himage, int nrows) {
+    const int n_mma = (nrows + 15) & ~15;
+    const uint32_t cbytes = (uint32_t)((n_mma + 31) / 32) * TS_CHUNK;
+    for (int s = 0; s < c.nsl; ++s) {
+        const uint32_t bar = umma::smem_u32(&c.full[s]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(2u * cbytes) : "memory");
+        const uint32_t dst = umma::smem_u32(c.tiles + (size_t)s * TS_STAGE_BYTES);
+        const char* src = himage + (size_t)(c.slab0 + s) * TS_STAGE_BYTES;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     ::"r"(dst), "l"(src), "r"(cbytes), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     ::"r"(dst + (uint32_t)TS_B_BYTES), "l"(src + TS_B_BYTES), "r"(cbytes), "r"(bar) : "memory");
+    }
+}
+__device__ __forceinline__ void ts_pair_issue(TsPairCtx& c, int nrows) {
+    const int n_mma = (nrows + 15) & ~15;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t par = c.n_phase & 1;
+    const uint64_t d_b0 = umma::make_desc(umma::smem_u32(c.tiles), TS_CHUNK, 512);
+    for (int s = 0; s < c.nsl; ++s) {
+        umma::mbar_wait(&c.full[s], par);
+        umma::fence_after_sync();
+        const uint64_t sb = d_b0 + (uint64_t)((s * TS_STAGE_BYTES) >> 4);
+#pragma unroll
+        for (int kg = 0; kg < TS_SLAB / 8; ++kg) {
+            const uint64_t dbh = sb + (uint64_t)((kg * 1024) >> 4);
+            const uint64_t dbl = dbh + (uint64_t)(TS_B_BYTES >> 4);
+            const uint32_t ta_hi = c.tmem + (uint32_t)(TSP_A_HI + s * TS_SLAB + kg * 8);
+            const uint32_t ta_lo = c.tmem + (uint32_t)(TSP_A_LO + s * TS_SLAB + kg * 8);
+            mma_tf32_ts(c.tmem, ta_hi, dbh, idesc, (s > 0 || kg > 0) ? 1u : 0u);
+            mma_tf32_ts(c.tmem, ta_hi, dbl, idesc, 1u);
+            mma_tf32_ts(c.tmem, ta_lo, dbh, idesc, 1u);
+        }
+    }
+    umma::commit(c.done);
+}
+constexpr int TSP_GP = 64 + 4;   // pitch of gpre
+__device__ __forceinline__ void ts_pair_drain_send(TsPairCtx& c, float* gpre, float* send, int nrows, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int n_mma = (nrows + 15) & ~15;
+    umma::mbar_wait(c.done, c.n_phase & 1);
+    c.n_phase += 1;
+    umma::fence_after_sync();
+    // accumulator lanes: quadrants 2 kh, 2 kh + 1 are this CTA's own units, the other two go to the partner.
+    // Warps w and w + 4 share lane quadrant w & 3 and split the 16-row blocks: warp < 4 takes blocks 0..2, warp >= 4 blocks 3..4.
+    const int lq = warp & 3;
+    const bool own = (lq >> 1) == c.kh;
+    const int col64 = (lq & 1) * 32 + lane;
+    const int rb0 = warp < 4 ? 0 : 3, rb1 = warp < 4 ? 3 : 5;
+#pragma unroll 1
+    for (int rb = rb0; rb < rb1; ++rb) {
+        if (rb * 16 >= n_mma) break;
+        uint32_t v[16];
+        umma::tmem_ld16(c.tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(rb * 16), v);
+        if (own) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (rb * 16 + j < nrows) gpre[(rb * 16 + j) * TSP_GP + col64] = __uint_as_float(v[j]);
+        } else {
+            float4* dst = reinterpret_cast<float4*>(send + (size_t)col64 * ROWS + rb * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        }
+    }
+    umma::fence_before_sync();
+}
+__device__ __forceinline__ void ts_pair_drain_recv(const TsPairCtx& c, float* gpre, const float* recv, int nrows, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int lq = warp & 3;
+    if ((lq >> 1) != c.kh) return;
+    const int col64 = (lq & 1) * 32 + lane;
+    const int rb0 = warp < 4 ? 0 : 3, rb1 = warp < 4 ? 3 : 5;
+    float4 pv[3][4];
+#pragma unroll
+    for (int bi = 0; bi < 3; ++bi) {
+        const int rb = rb0 + bi;
+        if (rb < rb1 && rb * 16 < nrows) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pv[bi][q] = ld_cg4(recv + (size_t)col64 * ROWS + rb * 16 + 4 * q);
+        }
+    }
+#pragma unroll
+    for (int bi = 0; bi < 3; ++bi) {
+        const int rb = rb0 + bi;
+        if (rb < rb1 && rb * 16 < nrows) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float a[4] = {pv[bi][q].x, pv[bi][q].y, pv[bi][q].z, pv[bi][q].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = rb * 16 + 4 * q + j;
+                    if (r < nrows) gpre[r * TSP_GP + col64] += a[j];
+                }
+            }
+        }
+    }
+}
+
 }  // namespace rnn

@@ -2,6 +2,7 @@
 """Turn ncu outputs brought back in gpurun_out/ into small text summaries under profiles/ (tracked).
     python tools/summarize_profiles.py <launches.csv> <report.ncu-rep> <tag>"""
 import csv
+import json
 import re
 import subprocess
 import sys
@@ -31,16 +32,37 @@ def launches(path, out):
 		out.write('  {:<66s} x{:<4d} {:>10.1f} us  {:5.1f}%\n'.format(k, c, v, 100 * v / total))
 
 
-def raw(rep, out):
+GROUPS = (('enc_fwd', 'enc_fwd_kernel'), ('enc_bwd', 'enc_bwd_kernel'), ('dec_fwd', 'dec_fwd_kernel'), ('dec_bwd', 'dec_bwd_kernel'))
+SCALE = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+
+
+def raw(rep, out, tag):
+	"""Per-kernel counters of a `ncu --set full` report; also writes profiles/ncu_constants.json -- the per-launch DRAM traffic and
+	pipe utilisation of the four persistent kernels that bench.py quotes in its `roofline` / `rooflines_kernels` blocks."""
 	txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 	rows = list(csv.reader(txt.splitlines()))
 	hdr = rows[0]; idx = {h: i for i, h in enumerate(hdr)}
 	units = rows[1]
+	consts = {'_source': 'profiles/{}.txt (ncu --set full --clock-control none; one launch per kernel)'.format(tag)}
 	for r in rows[2:]:
-		out.write('\nkernel: {}\n'.format(r[idx['Kernel Name']]))
+		name = r[idx['Kernel Name']]
+		out.write('\nkernel: {}\n'.format(name))
 		for k in KEYS:
 			if k in idx:
 				out.write('  {:<72s} {} {}\n'.format(k, r[idx[k]], units[idx[k]]))
+		for pat, group in GROUPS:
+			if pat in name and group not in consts:
+				def val(k):
+					return float(r[idx[k]].replace(',', '')) * SCALE.get(units[idx[k]], 1.0)
+				consts[group] = {'kernel': re.sub(r'\(.*', '', name).replace('void <unnamed>::', ''),
+								'dram_bytes': val('dram__bytes_read.sum') + val('dram__bytes_write.sum'),
+								'tensor_pct': val('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'),
+								'fma_pct': val('sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active'),
+								'issue_active_pct': val('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+								'duration_ms_under_ncu': val('gpu__time_duration.sum') * (1e-6 if units[idx['gpu__time_duration.sum']] in ('ns', 'nsecond') else
+																						1e-3 if units[idx['gpu__time_duration.sum']] in ('us', 'usecond') else 1.0)}
+	if len(consts) > 1:
+		json.dump(consts, open('profiles/ncu_constants.json', 'w'), indent=1, sort_keys=True)
 
 
 if __name__ == '__main__':
@@ -50,5 +72,5 @@ if __name__ == '__main__':
 		if ll != '-':
 			launches(ll, f)
 		if rep != '-':
-			raw(rep, f)
+			raw(rep, f, tag)
 	print(open('profiles/{}.txt'.format(tag)).read()[:3000])
