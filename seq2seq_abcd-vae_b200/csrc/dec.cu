@@ -38,7 +38,8 @@ struct DecK {
     // activations (see DecWs)
     float* Hall; float* Call; float* Xall; float* Gs; float* Hid; float* Mean; float* Lv;
     const float* eps; const float* gt;
-    int timing;   // debug: per-phase clock cycles of CTA 0 -> g_dec_timing
+    int timing;   // debug: per-phase clock cycles of CTA `timing_cta` -> g_dec_timing
+    int timing_cta;
     float* nll_partial;   // [gridDim.x]
     float* Pbuf;          // [n_tiles][CL][ROWS][2Fp] partial emission parameters exchanged inside a cluster
     char* himg; char* ximg;   // tensor-core forward: per tile, 2 parities of operand-tile images of h (K = H) and x (K = Fp)
@@ -650,25 +651,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_pair_kernel(DecK p) {
 
 // -------------------------------------------------------------------------------------------------
 // forward, pair variant ONE STEP AHEAD (default for output_size <= 88; rnn_ts.cuh "one step ahead"): the recurrent product
-// h_t W_hh of step t + 1 runs on tcgen05 underneath the emission MLPs of step t, the critical path of P1 is the input product
-// x_t W_ih (FFMA, K = Fp, one staged chunk) plus the cell update:
+// h_t W_hh of step t + 1 runs on tcgen05 underneath the emission MLPs of step t; the critical path of P1 is the input product
+// x_t W_ih (FFMA, K = Fp) plus the cell update, both on all 256 threads (16 units x 16 row groups, 5 rows per thread):
 //   P1   gates = gpre (h_{t-1} W_hh, ready) + x_{t-1} W_ih;  cell;  h_t published (rows + operand-tile image)   -- cluster barrier A --
-//        [thread 224: bulk copies of the h_t image]
+//        [thread 224: bulk copies of the h_t image]                  (saved gates / cell state are stored under the barrier)
 //   P2   hidden layers of the two emission MLPs (staged FFMA, K = H)
 //        [thread 224: MMAs of h_t W_hh while warps 0..6 do P3a]      P3a partial emission parameters (K-split)
 //        accumulator read-back: own half -> gpre, partner's half -> L2                                            -- cluster barrier B --
-//   P3b  partner's half added to gpre;  emission parameters, sample x_t, NLL                                      -- cluster barrier C (split) --
-// Shared memory: [h ring 4 x 24 KB | W1 | W2s | Wx | gpre | staging (P2: 2 x KC = 64; x: one chunk of 128) | scratch]
+//   P3b  emission parameters of this CTA's x columns, sample x_t, NLL;  x_t is PUSHED into the staging buffer of every CTA of
+//        the cluster through distributed shared memory with st.async: every 4-byte store also signals the consumer's mbarrier,
+//        so the third exchange of a step needs no fence, no cluster barrier and no L2 round trip               -- mbarrier (x bytes) --
+//        [off the critical path: Mean / Lv / Xall stores for the backward pass, partner's half of gpre added]
+// Shared memory: [h ring 4 x 24 KB | W1 | W2s | Wx | gpre | staging (P2: 2 x KC = 64;  x rows [ROWS][Fp + 4]) | scratch]
 // -------------------------------------------------------------------------------------------------
 constexpr int DFA_KC = 64;     // staged K-chunk of P2
-constexpr int DFA_XKC = 128;   // the x rows are staged as ONE chunk (Fp <= 128)
+constexpr int DFA_MAX_FP = 88; // x rows [ROWS][Fp + 4] must fit in the P2 staging area, weights in shared memory
 constexpr int DFA_STAGES = ABCD_H / TS_SLAB / 2;   // ring stages = h slabs of one CTA of a pair
 constexpr int DFA_MMA_TID = 224;                   // lane 0 of warp 7: copy + MMA thread (warp 7 has no share of the P2 epilogue and of P3a)
-__host__ __device__ constexpr size_t dfa_stage_floats() {
-    return (size_t)2 * ROWS * (DFA_KC + 4) > (size_t)ROWS * (DFA_XKC + 4) ? (size_t)2 * ROWS * (DFA_KC + 4) : (size_t)ROWS * (DFA_XKC + 4);
-}
+constexpr int DFA_RT = 5;                          // P1: rows per thread (rows rgx + 16 j)
+constexpr int DFA_XITEMS = 2;                      // P3b: (row, column) items per thread
+__host__ __device__ constexpr size_t dfa_stage_floats() { return (size_t)2 * ROWS * (DFA_KC + 4); }
+constexpr int DFA_P2_ONE_ROWS = 40;                // P2 stages all of K = H at once when at most this many rows are active
+static_assert((size_t)DFA_P2_ONE_ROWS * (ABCD_H + 4) <= dfa_stage_floats(), "one-chunk P2 staging must fit in the staging area");
 static_assert(DFA_STAGES <= TSP_STAGES && DFA_STAGES <= TSP_MAX_SLABS, "ring / tensor-memory geometry of the pair variant");
-static_assert((size_t)ROWS * 4 * U <= dfa_stage_floats(), "K-split scratch of the x product must fit in the staging area");
+static_assert((size_t)ROWS * (DFA_MAX_FP + 4) <= dfa_stage_floats(), "x rows must fit in the staging area");
+static_assert(ROWS * ((DFA_MAX_FP + CL - 1) / CL) <= DFA_XITEMS * NTHREADS, "P3b items per thread");
+static_assert(NTHREADS == 16 * U && ROWS == 16 * DFA_RT, "P1 thread map: 16 units x 16 row groups");
+
+// One 4-byte store into the shared memory of CTA `cta` of the cluster that also signals 4 bytes on that CTA's mbarrier (same
+// offsets as in this CTA): data and notification travel together, so the consumer needs neither a fence nor a cluster barrier.
+__device__ __forceinline__ void st_async_cluster_f32(uint32_t local_smem_addr, uint32_t local_bar_addr, unsigned cta, float v) {
+    uint32_t remote, rbar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(local_smem_addr), "r"(cta));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(rbar) : "r"(local_bar_addr), "r"(cta));
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];\n"
+                 ::"r"(remote), "r"(__float_as_uint(v)), "r"(rbar) : "memory");
+}
+
+// acc[j][0..3] += x[row rg + 16 j][0, 4 nk4) * W[.., 4 columns of this thread] (row pitch LDW)   for j < NJ (warp-uniform)
+template <int NJ, int LDW>
+__device__ __forceinline__ void rows_gemm(float (&acc)[DFA_RT][4], const float* xr, int ldx, const float* wq, int nk4) {
+#pragma unroll 2
+    for (int kq = 0; kq < nk4; ++kq) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wq + (kq * 4 + 0) * LDW);
+        const float4 w1 = *reinterpret_cast<const float4*>(wq + (kq * 4 + 1) * LDW);
+        const float4 w2 = *reinterpret_cast<const float4*>(wq + (kq * 4 + 2) * LDW);
+        const float4 w3 = *reinterpret_cast<const float4*>(wq + (kq * 4 + 3) * LDW);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const float4 a = *reinterpret_cast<const float4*>(xr + j * 16 * ldx + kq * 4);
+            acc[j][0] = fmaf(a.x, w0.x, acc[j][0]); acc[j][1] = fmaf(a.x, w0.y, acc[j][1]); acc[j][2] = fmaf(a.x, w0.z, acc[j][2]); acc[j][3] = fmaf(a.x, w0.w, acc[j][3]);
+            acc[j][0] = fmaf(a.y, w1.x, acc[j][0]); acc[j][1] = fmaf(a.y, w1.y, acc[j][1]); acc[j][2] = fmaf(a.y, w1.z, acc[j][2]); acc[j][3] = fmaf(a.y, w1.w, acc[j][3]);
+            acc[j][0] = fmaf(a.z, w2.x, acc[j][0]); acc[j][1] = fmaf(a.z, w2.y, acc[j][1]); acc[j][2] = fmaf(a.z, w2.z, acc[j][2]); acc[j][3] = fmaf(a.z, w2.w, acc[j][3]);
+            acc[j][0] = fmaf(a.w, w3.x, acc[j][0]); acc[j][1] = fmaf(a.w, w3.y, acc[j][1]); acc[j][2] = fmaf(a.w, w3.z, acc[j][2]); acc[j][3] = fmaf(a.w, w3.w, acc[j][3]);
+        }
+    }
+}
 
 template <int CELL>
 __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
@@ -677,6 +715,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
     const int H = ABCD_H, M = ABCD_M;
     const int F = p.F, Fp = p.Fp;
     const int XC = xcols_per_cta(F);
+    const int LDX = Fp + 4;                   // pitch of the x rows
     constexpr int KC = DFA_KC;
     constexpr int HSP = 2 * U + 4;            // pitch of the CTA's own hidden-layer slice kept in shared memory
     float* W1 = reinterpret_cast<float*>(reinterpret_cast<char*>(smem) + (size_t)DFA_STAGES * TS_STAGE_BYTES);   // [H][2U]
@@ -686,20 +725,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
     float* stage_base = gpre + ROWS * TSP_GP;
     float* red = stage_base + dfa_stage_floats();   // 40 floats
     const Stage st = make_stage(stage_base, KC);
-    const Stage stx = make_stage(stage_base, DFA_XKC);   // only buf0 is used (one chunk)
+    const Stage st1 = make_stage(stage_base, ABCD_H);   // one-chunk staging of P2 (only buf0, at most DFA_P2_ONE_ROWS rows)
     float* Hs = st.buf0;                      // [ROWS][HSP] (the staging buffers are idle between phases)
+    float* xs = stage_base;                   // [ROWS][LDX]: x_{t-1}, written by the column owners of the whole cluster during their P3b
     __shared__ uint64_t tsp_bars[TSP_STAGES + 1];
+    __shared__ uint64_t xbar;                 // bytes of x_t pushed into xs by the column owners (one phase per step)
     __shared__ uint32_t tsp_tmem_slot;
     TsPairCtx tsp;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
+    if (tid == 0) umma::mbar_init(&xbar, 1);  // (made visible cluster-wide by the fence + barriers of ts_pair_init / the prologue)
     const int rank = (int)cluster_ctarank();
     const int tile = blockIdx.x / CL;
     const int u0 = rank * U;                  // the 16 units this CTA finalises (cell update, MLP slices)
     const int pair_u0 = (rank >> 1) * 2 * U;  // the 32 units whose gate columns the pair contracts
     const int xc0 = rank * XC;
-    const int xc1 = min(F, xc0 + XC);
+    const int xc1 = min(Fp, xc0 + XC);        // (columns F..Fp-1 are padding: their owner pushes zeros)
 
     // ---- resident weights ----
     if ((umma::smem_u32(smem) & 1023u) != 0) __trap();
@@ -738,10 +780,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
     }
 
     // ---- per-thread constants for the three phases ----
-    const int KS1 = min(2, pick_ks(U));
-    const ThreadMap tm1 = make_map(tid, U, KS1);      // x product: K split over two thread groups; cell update: group 0
-    const bool cell_thread = tm1.active && tm1.ks == 0;
-    const int unit = u0 + tm1.cg;
+    const int cgx = tid & (U - 1), rgx = tid >> 4;   // P1: unit, row group (rows rgx + 16 j, j < 5)
+    const int unit = u0 + cgx;
     float bias1[4];
     if (CELL == 0) {
 #pragma unroll
@@ -766,29 +806,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
     // pair exchange of the gate partial sums (the backward pass's partial buffer is idle during the forward pass)
     float* pair_send = p.Pb2 + (size_t)(blockIdx.x ^ 1) * ROWS * H;
     const float* pair_recv = p.Pb2 + (size_t)blockIdx.x * ROWS * H;
+    const uint32_t xs_addr = umma::smem_u32(xs), xbar_addr = umma::smem_u32(&xbar);
+    // P3b item order: the four warps that do NOT own accumulator lanes of the pair product come first, so that at typical row
+    // counts the owners start adding the partner's half of gpre (an L2 round trip) while the others sum the emission partials
+    const bool recv_warp = (((warp & 3) >> 1) == (rank & 1));
+    const int p3b_tid = ((recv_warp ? 4 : 0) + (((warp >> 2) << 1) | (warp & 1))) * 32 + (tid & 31);
 
     // recurrent state of (row, unit) pairs owned by this thread
-    float creg[RT], hreg[RT];
+    float creg[DFA_RT], hreg[DFA_RT];
 #pragma unroll
-    for (int i = 0; i < RT; ++i) {
-        int b = tile + p.n_tiles * (tm1.rg + i * RG);
-        creg[i] = 0.f; hreg[i] = 0.f;
-        if (b < p.B && cell_thread) {
-            hreg[i] = p.Hall[(long)b * H + unit];
-            if (CELL == 0) creg[i] = p.Call[(long)b * H + unit];
+    for (int j = 0; j < DFA_RT; ++j) {
+        int b = tile + p.n_tiles * (rgx + 16 * j);
+        creg[j] = 0.f; hreg[j] = 0.f;
+        if (b < p.B) {
+            hreg[j] = p.Hall[(long)b * H + unit];
+            if (CELL == 0) creg[j] = p.Call[(long)b * H + unit];
         }
     }
     const int Tt = p.lengths[tile];
     float nll = 0.f;
     const int n_tiles = p.n_tiles, B = p.B;
-    const float* Hall = p.Hall; const float* Xall = p.Xall;
+    const float* Hall = p.Hall;
     // image of the initial state and its recurrent product (gpre of step 0)
-    if (cell_thread) {
 #pragma unroll
-        for (int i = 0; i < RT; ++i) {
-            const int r = tm1.rg + i * RG;
-            if (tile + p.n_tiles * r < p.B) ts_image_store(himg[1], unit, r, hreg[i]);
-        }
+    for (int j = 0; j < DFA_RT; ++j) {
+        const int r = rgx + 16 * j;
+        if (tile + p.n_tiles * r < p.B) ts_image_store(himg[1], unit, r, hreg[j]);
     }
     ts_image_publish();
     cluster_sync_all();
@@ -801,9 +844,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
         ts_pair_drain_recv(tsp, gpre, pair_recv, na0, tid);
     }
     __syncthreads();
-    const bool timing = p.timing == 1 && blockIdx.x == 0 && tid == 64;
+    const bool timing = p.timing == 1 && blockIdx.x == p.timing_cta && tid == 64;
     unsigned long long tacc[16];
     for (int i = 0; i < 16; ++i) tacc[i] = 0;
+    unsigned long long issue_cycles = 0;
 #define DEC_TICK(slot) if (timing) { long long now_ = clock64(); tacc[slot] += now_ - tick_; tick_ = now_; }
 
     for (int t = 0; t < Tt; ++t) {
@@ -811,51 +855,77 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
         const int na = active_rows(p.batch_sizes[t], tile, n_tiles);
         const int na_next = t + 1 < Tt ? active_rows(p.batch_sizes[t + 1], tile, n_tiles) : 0;
         const long off_t = p.offsets[t];
-        const long prev_base = t == 0 ? 0 : (long)B + p.offsets[t - 1];
 
         // ---- P1: gates + cell ----
         {
-            float acc[RT][4];
-            zero_acc(acc);
-            if (t > 0) cluster_wait_acquire();   // x_{t-1} of every column owner is visible
-            DEC_TICK(0)
-            auto rpx = [=](int r) -> const float* { return Xall + (prev_base + tile + (long)n_tiles * r) * Fp; };
-            phase_gemm<NTHREADS, DFA_XKC, 4 * U>(acc, stx, Fp, rpx, 0, NullRow(), na, Wx, tm1, KS1, tid);
-            DEC_TICK(1)
+            float acc[DFA_RT][4];
 #pragma unroll
-            for (int i = 0; i < RT; ++i) {
-                int r = tm1.rg + i * RG;
-                if (r >= na || !cell_thread) continue;
-                long frame = off_t + tile + (long)n_tiles * r;
-                const float4 hp = *reinterpret_cast<const float4*>(gpre + r * TSP_GP + tm1.cg * 4);
-                const float a0 = acc[i][0] + hp.x, a1 = acc[i][1] + hp.y, a2 = acc[i][2] + hp.z, a3 = acc[i][3] + hp.w;
+            for (int j = 0; j < DFA_RT; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+            if (t > 0) {
+                umma::mbar_wait(&xbar, (uint32_t)(t - 1) & 1u);   // C: x_{t-1} of every column owner has landed in xs
+                __syncthreads();          // gpre was completed by other threads of this CTA (partner's half) after barrier B
+                DEC_TICK(0)
+                // rows of this warp: 2 row groups; the trip count is warp-uniform (rows >= na are computed on stale data and dropped)
+                const int njw = min(DFA_RT, (na - 2 * warp + 15) >> 4);
+                const float* xr = xs + rgx * LDX;
+                const float* wq = Wx + cgx * 4;
+                switch (njw) {
+                    case 1: rows_gemm<1, 4 * U>(acc, xr, LDX, wq, Fp >> 2); break;
+                    case 2: rows_gemm<2, 4 * U>(acc, xr, LDX, wq, Fp >> 2); break;
+                    case 3: rows_gemm<3, 4 * U>(acc, xr, LDX, wq, Fp >> 2); break;
+                    case 4: rows_gemm<4, 4 * U>(acc, xr, LDX, wq, Fp >> 2); break;
+                    case 5: rows_gemm<5, 4 * U>(acc, xr, LDX, wq, Fp >> 2); break;
+                    default: break;
+                }
+            }
+            DEC_TICK(1)
+            float4 gsv[DFA_RT];
+            float csv[DFA_RT];
+#pragma unroll
+            for (int j = 0; j < DFA_RT; ++j) {
+                const int r = rgx + 16 * j;
+                if (r >= na) continue;
+                const long frame = off_t + tile + (long)n_tiles * r;
+                const float4 hp = *reinterpret_cast<const float4*>(gpre + r * TSP_GP + cgx * 4);
+                const float a0 = acc[j][0] + hp.x, a1 = acc[j][1] + hp.y, a2 = acc[j][2] + hp.z, a3 = acc[j][3] + hp.w;
                 float h;
                 if (CELL == 0) {
                     float ig = sigmoid_acc(a0 + bias1[0]);
                     float fg = sigmoid_acc(a1 + bias1[1]);
                     float gg = tanhf(a2 + bias1[2]);
                     float og = sigmoid_acc(a3 + bias1[3]);
-                    float c = fg * creg[i] + ig * gg;
+                    float c = fg * creg[j] + ig * gg;
                     h = og * tanhf(c);
-                    creg[i] = c;
-                    *reinterpret_cast<float4*>(p.Gs + frame * (4 * H) + unit * 4) = make_float4(ig, fg, gg, og);
-                    p.Call[((long)B + frame) * H + unit] = c;
+                    creg[j] = c;
+                    gsv[j] = make_float4(ig, fg, gg, og);
+                    csv[j] = c;
                 } else {
                     float rg_ = sigmoid_acc(a0 + bias1[0]);
                     float zg = sigmoid_acc(a1 + bias1[1]);
                     float hn = a3 + bias1[3];
                     float ng = tanhf(a2 + bias1[2] + rg_ * hn);
-                    h = (1.f - zg) * ng + zg * hreg[i];
-                    *reinterpret_cast<float4*>(p.Gs + frame * (4 * H) + unit * 4) = make_float4(rg_, zg, ng, hn);
+                    h = (1.f - zg) * ng + zg * hreg[j];
+                    gsv[j] = make_float4(rg_, zg, ng, hn);
                 }
-                hreg[i] = h;
+                hreg[j] = h;
                 p.Hall[((long)B + frame) * H + unit] = h;
                 if (na_next > 0) ts_image_store(himg[t & 1], unit, r, h);
             }
+            ts_image_publish();
+            DEC_TICK(2)
+            cluster_arrive_release();   // A: h_t on its way to the other CTAs
+            DEC_TICK(11)
+            // saved for the backward pass only: stored under the barrier
+#pragma unroll
+            for (int j = 0; j < DFA_RT; ++j) {
+                const int r = rgx + 16 * j;
+                if (r >= na) continue;
+                const long frame = off_t + tile + (long)n_tiles * r;
+                *reinterpret_cast<float4*>(p.Gs + frame * (4 * H) + unit * 4) = gsv[j];
+                if (CELL == 0) p.Call[((long)B + frame) * H + unit] = csv[j];
+            }
+            cluster_wait_acquire();
         }
-        ts_image_publish();
-        DEC_TICK(2)
-        cluster_sync_all();   // A: h_t visible
         DEC_TICK(3)
         if (tid == DFA_MMA_TID && na_next > 0) ts_pair_fetch(tsp, himg[t & 1], na_next);
 
@@ -864,11 +934,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
             float acc[RT][4];
             zero_acc(acc);
             auto rph = [=](int r) -> const float* { return Hall + ((long)B + off_t + tile + (long)n_tiles * r) * ABCD_H; };
-            phase_gemm<NTHREADS, KC, 2 * U>(acc, st, H, rph, 0, NullRow(), na, W1, tm2, KS2, tid);
+            // few active rows (most steps): all of h_t[rows, H] fits in the staging area -> one L2 round trip, one CTA barrier
+            if (na <= DFA_P2_ONE_ROWS) phase_gemm<NTHREADS, ABCD_H, 2 * U>(acc, st1, H, rph, 0, NullRow(), na, W1, tm2, KS2, tid);
+            else phase_gemm<NTHREADS, KC, 2 * U>(acc, st, H, rph, 0, NullRow(), na, W1, tm2, KS2, tid);
             DEC_TICK(4)
             if (warp == 7) {
                 // (warp 7 holds a K-split share of P2 only: no epilogue rows, no P3a items)
-                if (tid == DFA_MMA_TID && na_next > 0) ts_pair_issue(tsp, na_next);
+                if (tid == DFA_MMA_TID && na_next > 0) {
+                    const long long i0 = p.timing == 1 ? clock64() : 0;
+                    ts_pair_issue(tsp, na_next);
+                    if (p.timing == 1) issue_cycles += clock64() - i0;
+                }
                 __syncwarp();
             } else {
                 if (tm2.active && tm2.ks == 0) {
@@ -922,43 +998,70 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
         // recurrent product of the NEXT step: own gate columns -> gpre, the partner's -> its receive buffer
         if (na_next > 0) ts_pair_drain_send(tsp, gpre, pair_send, na_next, tid);
         DEC_TICK(6)
-        cluster_sync_all();   // B: partial emission parameters and partner partials visible
+        cluster_arrive_release();   // B: partial emission parameters and partner partials visible; every CTA is done with its staging area
+        DEC_TICK(12)
+        cluster_wait_acquire();
         DEC_TICK(7)
+        // x_t arrives as 4-byte pushes from the owners of its columns: na_next rows x Fp columns
+        if (tid == 0 && na_next > 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(xbar_addr), "r"((uint32_t)(na_next * Fp * 4)) : "memory");
+        }
 
-        // ---- P3b: sum the partials of this CTA's x columns, reparameterised sample, NLL ----
-        for (int o = tid; o < na * XC; o += NTHREADS) {
+        // ---- P3b: sum the partials of this CTA's x columns, reparameterised sample, NLL; push x_t to every CTA of the cluster ----
+        float sv_mean[DFA_XITEMS], sv_lv[DFA_XITEMS], sv_x[DFA_XITEMS];
+        long sv_frame[DFA_XITEMS];
+        int sv_c[DFA_XITEMS];
+#pragma unroll
+        for (int it = 0; it < DFA_XITEMS; ++it) {
+            const int o = p3b_tid + it * NTHREADS;
+            sv_c[it] = -1;
+            if (o >= na * XC) continue;
             const int r = o / XC, c = xc0 + o % XC;
             if (c >= xc1) continue;
-            const long frame = off_t + tile + (long)n_tiles * r;
-            const float e = __ldg(p.eps + frame * p.ld_eps + c);
-            const float g = p.gt ? __ldg(p.gt + frame * p.ld_gt + c) : 0.f;
-            float pm[CL], pv[CL];
+            float x = 0.f;
+            if (c < F) {
+                const long frame = off_t + tile + (long)n_tiles * r;
+                const float e = __ldg(p.eps + frame * p.ld_eps + c);
+                const float g = p.gt ? __ldg(p.gt + frame * p.ld_gt + c) : 0.f;
+                float pm[CL], pv[CL];
 #pragma unroll
-            for (int src = 0; src < CL; ++src) {
-                const float* q = Ptile + ((long)src * ROWS + r) * (2 * Fp) + c;
-                pm[src] = ld_cg(q);
-                pv[src] = ld_cg(q + Fp);
+                for (int src = 0; src < CL; ++src) {
+                    const float* q = Ptile + ((long)src * ROWS + r) * (2 * Fp) + c;
+                    pm[src] = ld_cg(q);
+                    pv[src] = ld_cg(q + Fp);
+                }
+                float mean = __ldg(p.em_b2[0] + c), lv = __ldg(p.em_b2[1] + c);
+#pragma unroll
+                for (int src = 0; src < CL; ++src) { mean += pm[src]; lv += pv[src]; }
+                x = mean + expf(0.5f * lv) * e;
+                if (p.gt) {
+                    const float d = g - mean;
+                    nll += 0.5f * (LOG_2PI + lv + d * expf(-lv) * d);
+                }
+                sv_mean[it] = mean; sv_lv[it] = lv; sv_x[it] = x; sv_frame[it] = frame; sv_c[it] = c;
             }
-            float mean = __ldg(p.em_b2[0] + c), lv = __ldg(p.em_b2[1] + c);
+            if (na_next > 0 && r < na_next) {
+                const uint32_t a = xs_addr + (uint32_t)(r * LDX + c) * 4u;
 #pragma unroll
-            for (int src = 0; src < CL; ++src) { mean += pm[src]; lv += pv[src]; }
-            const float x = mean + expf(0.5f * lv) * e;
-            p.Mean[frame * Fp + c] = mean;
-            p.Lv[frame * Fp + c] = lv;
-            p.Xall[((long)B + frame) * Fp + c] = x;
-            if (p.gt) {
-                const float d = g - mean;
-                nll += 0.5f * (LOG_2PI + lv + d * expf(-lv) * d);
+                for (unsigned q = 0; q < (unsigned)CL; ++q) st_async_cluster_f32(a, xbar_addr, q, x);
             }
         }
         DEC_TICK(8)
-        cluster_arrive_release();   // C: matched by the wait at the top of the next step (or the one after the loop)
-        if (na_next > 0) ts_pair_drain_recv(tsp, gpre, pair_recv, na_next, tid);   // off the critical path: under the barrier
+        // off the critical path (the next step waits for x_t on its mbarrier; WAR hazards on the exchange buffers are covered by
+        // barriers A and B of the next step): activations saved for the backward pass, partner's half of the next gate pre-activations
+#pragma unroll
+        for (int it = 0; it < DFA_XITEMS; ++it) {
+            if (sv_c[it] < 0) continue;
+            p.Mean[sv_frame[it] * Fp + sv_c[it]] = sv_mean[it];
+            p.Lv[sv_frame[it] * Fp + sv_c[it]] = sv_lv[it];
+            p.Xall[((long)B + sv_frame[it]) * Fp + sv_c[it]] = sv_x[it];
+        }
+        if (na_next > 0) ts_pair_drain_recv(tsp, gpre, pair_recv, na_next, tid);
         DEC_TICK(9)
     }
 #undef DEC_TICK
-    if (Tt > 0) cluster_wait_acquire();
-    if (timing) { tacc[15] = Tt; for (int i = 0; i < 16; ++i) g_dec_timing[i] = tacc[i]; }
+    if (timing) { tacc[15] = Tt; for (int i = 0; i < 16; ++i) if (i != 10) g_dec_timing[i] = tacc[i]; }
+    if (p.timing == 1 && blockIdx.x == p.timing_cta && tid == DFA_MMA_TID) g_dec_timing[10] = issue_cycles;
     float tot = block_sum(nll, red);
     if (tid == 0) p.nll_partial[blockIdx.x] = tot;
     ts_pair_fini(tsp, tid);
@@ -1738,6 +1841,520 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_ts_kernel(DecK p) {
     if (warp == 0) umma::tmem_dealloc<512>(tmem);
 }
 
+// Push variant of the tensor-core backward (default for pad4(F) <= 68): the third exchange of a step -- dx_t folded into dML of the
+// previous frame, which every CTA then needs in full for B3 -- no longer goes through L2 and a cluster barrier.  The owner of
+// an x column updates dML in global memory (the weight-gradient GEMMs read it later) and PUSHES the updated pair
+// (d mean, d log-variance) into the B3 input buffer of every CTA of the cluster with st.async (8 bytes + 8 bytes signalled on
+// the consumer's mbarrier).  B3 then is a GEMM on shared-memory operands (no staging, no chunk barriers), on all 256 threads
+// (8 column groups x 16 row groups x 2 K halves).  The reduction of the recurrent carry dh (not needed before the gate
+// gradients) moves off the critical path, under the MMAs of B2'.  Two cluster barriers per step instead of three.
+template <int CELL>
+__global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_push_kernel(DecK p) {
+    constexpr int KC = 64;
+    // (a distinct symbol: the alignment of an extern shared array is a property of the symbol, and `smem` is declared
+    // 16-byte aligned by the FFMA kernels of this file)
+    extern __shared__ __align__(1024) float smem_push[];
+    float* const smem = smem_push;
+    const int H = ABCD_H, M = ABCD_M;
+    const int F = p.F, Fp = p.Fp;
+    const int XC = xcols_per_cta(F);
+    const int N1 = H + Fp;                    // columns of the B1' partial: [dh_prev (H) | dx (Fp)]
+    constexpr int DSP = 2 * U + 4;            // pitch of the dHidPre slice in shared memory
+    constexpr int GSP = 4 * U + 4;            // pitch of the dG slice in shared memory
+    char* b_hi = reinterpret_cast<char*>(smem);                     // one 32-k slab of [k][rows] operand tiles
+    char* b_lo = b_hi + TS_B_BYTES;
+    char* wlo1 = b_lo + TS_B_BYTES;                                 // B1': [2 slabs][12 chunks (384 columns)][4 KB]
+    char* wlo2 = wlo1 + DBT_WLO1_BYTES;                             // B2': [1 slab][8 chunks (256 units)][4 KB]
+    float* WB3 = reinterpret_cast<float*>(wlo2 + DBT_WLO2_BYTES);   // [2Fp][2U]
+    float* dh_sm = WB3 + 2 * Fp * (2 * U);    // [ROWS][U]
+    float* dc_sm = dh_sm + ROWS * U;          // [ROWS][U]
+    const Stage st = make_stage(dc_sm + ROWS * U, KC);
+    const int LDA = 2 * Fp;                   // pitch of the B3 input rows
+    float* As = st.buf0;                      // [ROWS][2Fp]: dML rows of the frame B3 works on, column 2c = d mean_c, 2c + 1 = d log-variance_c;
+                                              // written by the owners of the x columns of the whole cluster (st.async) after the second barrier
+    float* Ds = st.buf0;                      // [ROWS][DSP]  (As is dead once B3 has multiplied), piece-swizzled
+    float* Gsm = st.buf0;                     // [ROWS][GSP]  (Ds is dead by then; may run into buf1), piece-swizzled
+    __shared__ uint64_t bar;
+    __shared__ uint64_t dbar;                 // bytes of the dML rows pushed into As (one phase per step)
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x;
+    const int rank = (int)cluster_ctarank();
+    const int tile = blockIdx.x / CL;
+    const int u0 = rank * U;
+    const int xc0 = rank * XC;
+    const int xc1 = min(Fp, xc0 + XC);        // (columns F..Fp-1 are padding: their owner pushes zeros)
+
+    for (int idx = tid; idx < 2 * Fp * 2 * U; idx += NTHREADS) {
+        int col = idx % (2 * U), k = idx / (2 * U);   // row k of the interleaved input: x column k / 2, mean (0) or log-variance (1) head
+        int which = col / U, u = col % U;
+        float v = 0.f;
+        if ((k & 1) == which && (k >> 1) < F) v = p.em_w2[which][(long)(k >> 1) * M + u0 + u];
+        WB3[idx] = v;
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+    if ((umma::smem_u32(smem) & 1023u) != 0) __trap();
+    if (warp == 0) umma::tmem_alloc<512>(&tmem_slot);
+    if (tid == 0) {
+        umma::mbar_init(&bar, 1);
+        umma::mbar_init(&dbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    uint32_t bar_uses = 0;
+    {
+        // element (gate row kphys of this CTA, column j of [W_hh | W_ih]); columns >= H + F are zero
+        auto w1 = [&](int kphys, int j) -> float {
+            const int uu = u0 + (kphys >> 2), s = kphys & 3;
+            if (j < H) {
+                const int gate = CELL == 0 ? s : (s == 0 ? 0 : s == 1 ? 1 : s == 3 ? 2 : -1);
+                return gate >= 0 ? __ldg(p.w_hh + (long)(gate * H + uu) * H + j) : 0.f;
+            }
+            const int c = j - H;
+            const int gate = CELL == 0 ? s : (s == 3 ? -1 : s);
+            return (gate >= 0 && c < F) ? __ldg(p.w_ih + (long)(gate * H + uu) * F + c) : 0.f;
+        };
+        auto w2 = [&](int k, int j) -> float { return __ldg(p.em_w1[k / U] + (long)(u0 + k % U) * H + j); };
+        auto tmem_store16 = [&](uint32_t taddr, const uint32_t (&r)[16]) {
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                  "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+        };
+        const int lq = warp & 3;
+        // hi parts into tensor memory: lane = output column / unit within a 128-wide block
+        for (int b = warp >> 2; b < 3; b += 2) {
+            const int j = b * 128 + lq * 32 + lane;
+            for (int k0 = 0; k0 < 4 * U; k0 += 16) {
+                uint32_t r[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) r[q] = __float_as_uint(j < N1 ? w1(k0 + q, j) : 0.f);
+                tmem_store16(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(DBT_A1_COL + b * 4 * U + k0), r);
+            }
+        }
+        {
+            const int b = warp >> 2;
+            const int j = b * 128 + lq * 32 + lane;
+            for (int k0 = 0; k0 < 2 * U; k0 += 16) {
+                uint32_t r[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) r[q] = __float_as_uint(w2(k0 + q, j));
+                tmem_store16(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(DBT_A2_COL + b * 2 * U + k0), r);
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        // lo parts: MN-major tiles [k][column]
+        for (int idx = tid; idx < 4 * U * (DBT_M1 / 4); idx += NTHREADS) {
+            const int j4 = idx % (DBT_M1 / 4), k = idx / (DBT_M1 / 4);
+            float4 v;
+            v.x = 4 * j4 + 0 < N1 ? w1(k, 4 * j4 + 0) : 0.f; v.y = 4 * j4 + 1 < N1 ? w1(k, 4 * j4 + 1) : 0.f;
+            v.z = 4 * j4 + 2 < N1 ? w1(k, 4 * j4 + 2) : 0.f; v.w = 4 * j4 + 3 < N1 ? w1(k, 4 * j4 + 3) : 0.f;
+            *reinterpret_cast<float4*>(wlo1 + (size_t)(k / TS_SLAB) * (DBT_M1 / 32) * TS_CHUNK + umma::tile_off<TS_CHUNK>(k % TS_SLAB, j4)) = umma::lo_of(v);
+        }
+        for (int idx = tid; idx < 2 * U * (H / 4); idx += NTHREADS) {
+            const int j4 = idx % (H / 4), k = idx / (H / 4);
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.em_w1[k / U] + (long)(u0 + k % U) * H + j4 * 4));
+            *reinterpret_cast<float4*>(wlo2 + umma::tile_off<TS_CHUNK>(k, j4)) = umma::lo_of(v);
+        }
+        umma::fence_proxy_async();
+    }
+    for (int idx = tid; idx < ROWS * U; idx += NTHREADS) { dh_sm[idx] = 0.f; dc_sm[idx] = 0.f; }
+
+    // B3 thread map: 8 column groups (4 columns) x 16 row groups (rows rg + 16 j, j < 5) x 2 halves of K = 2Fp
+    const int b3_cg = tid & 7, b3_rg = (tid >> 3) & 15, b3_ks = tid >> 7;
+    const int b3_nq0 = (Fp / 2 + 1) / 2, b3_nq = b3_ks == 0 ? b3_nq0 : Fp / 2 - b3_nq0;   // k-quads of this thread's half
+    float* b3_scratch = reinterpret_cast<float*>(b_hi);   // [128][20]: partial tiles of the second K half (the operand tiles are idle during B3)
+    const uint32_t as_addr = umma::smem_u32(As), dbar_addr = umma::smem_u32(&dbar);
+    constexpr int PRG = NTHREADS / U;   // pointwise mapping: 16 row groups x 16 units, rows prg + i*PRG
+    constexpr int PR = ROWS / PRG;      // rows per pointwise thread
+    const int pu = tid % U, prg = tid / U;
+    const int unit = u0 + pu;
+
+    const int Tt = p.lengths[tile];
+    const int n_tiles = p.n_tiles, B = p.B;
+    const float* dML = p.dML;
+    float* Pb2 = p.Pb2 + (long)blockIdx.x * ROWS * H;
+    const float* Pb2t = p.Pb2 + (long)tile * CL * ROWS * H;
+    float* Pb1 = p.Pb1 + (long)blockIdx.x * ROWS * N1;
+    const float* Pb1t = p.Pb1 + (long)tile * CL * ROWS * N1;
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);   // this thread's share of sum(dG) over rows and steps
+    float4 hsum = make_float4(0.f, 0.f, 0.f, 0.f);   // ... and of sum(dHidPre) (bias gradients of the MLP input layers)
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+
+    // dML rows (row r of frame t - 1, this CTA's x columns) -> every CTA's As; for rows that were active at step t (r < na_t) the
+    // gradient dx_t that came back through the cell is folded in first.  Pb1t: partials of step t ([16][H + Fp][ROWS], transposed).
+    auto push_dml = [&](int t_prev, int na_t) {
+        const int na_p = active_rows(p.batch_sizes[t_prev], tile, n_tiles);
+        if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(dbar_addr), "r"((uint32_t)(na_p * 2 * Fp * 4)) : "memory");
+        const long pbase = p.offsets[t_prev] + tile;
+        for (int idx = tid; idx < na_p * XC; idx += NTHREADS) {
+            const int r = idx % na_p, c = xc0 + idx / na_p;   // rows fastest: contiguous in the transposed partials
+            if (c >= xc1) continue;
+            float m0 = 0.f, m1 = 0.f;
+            if (c < F) {
+                const long pf = pbase + (long)n_tiles * r;   // frame that produced x_t
+                float* dm = p.dML + pf * (2 * Fp) + c;
+                m0 = dm[0]; m1 = dm[Fp];
+                if (r < na_t) {
+                    float v[CL];
+#pragma unroll
+                    for (int src = 0; src < CL; ++src) v[src] = ld_cg(Pb1t + ((long)src * N1 + H + c) * ROWS + r);
+                    const float lv = __ldg(p.Lv + pf * Fp + c);
+                    const float e = __ldg(p.eps + pf * p.ld_eps + c);
+                    float dx = v[0];
+#pragma unroll
+                    for (int src = 1; src < CL; ++src) dx += v[src];
+                    m0 += dx;
+                    m1 += dx * 0.5f * expf(0.5f * lv) * e;
+                    dm[0] = m0;
+                    dm[Fp] = m1;
+                }
+            }
+            const uint32_t a = as_addr + (uint32_t)(r * LDA + 2 * c) * 4u;
+#pragma unroll
+            for (unsigned q = 0; q < (unsigned)CL; ++q) {
+                uint32_t remote, rbar;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(a), "r"(q));
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(rbar) : "r"(dbar_addr), "r"(q));
+                asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];\n"
+                             ::"r"(remote), "r"(__float_as_uint(m0)), "r"(__float_as_uint(m1)), "r"(rbar) : "memory");
+            }
+        }
+    };
+    // recurrent carry dh of this CTA's units = sum of the B1' partials of the step that has just finished (rows < na_t)
+    auto reduce_dh = [&](int na_t) {
+        for (int idx = tid; idx < ((na_t + 3) >> 2) * U; idx += NTHREADS) {
+            const int rq = idx % ((na_t + 3) >> 2), j = idx / ((na_t + 3) >> 2);
+            float4 v[CL];
+#pragma unroll
+            for (int src = 0; src < CL; ++src) v[src] = ld_cg4(Pb1t + ((long)src * N1 + u0 + j) * ROWS + 4 * rq);
+            float4 a = v[0];
+#pragma unroll
+            for (int src = 1; src < CL; ++src) { a.x += v[src].x; a.y += v[src].y; a.z += v[src].z; a.w += v[src].w; }
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (4 * rq + i < na_t) dh_sm[(4 * rq + i) * U + j] = av[i];
+        }
+    };
+    cluster_sync_all();   // every CTA's mbarriers are initialised before the first remote store
+    if (Tt > 0) push_dml(Tt - 1, 0);
+    int na_last = 0;      // active rows of the step whose B1' partials have not been reduced into dh_sm yet
+
+    const bool timing = p.timing == 3 && blockIdx.x == p.timing_cta && tid == 32;
+    unsigned long long tacc[16];
+    for (int i = 0; i < 16; ++i) tacc[i] = 0;
+#define DEC_TICK(slot) if (timing) { long long now_ = clock64(); tacc[slot] += now_ - tick_; tick_ = now_; }
+    for (int t = Tt - 1; t >= 0; --t) {
+        long long tick_ = timing ? clock64() : 0;
+        const int na = active_rows(p.batch_sizes[t], tile, n_tiles);
+        const long off_t = p.offsets[t];
+        const long prev_base = t == 0 ? 0 : (long)B + p.offsets[t - 1];
+
+        // saved forward activations for the gate-gradient step: fetched now, consumed after the first barrier
+        float4 g4v[PR];
+        float cv[PR], pv[PR], hov[PR];
+#pragma unroll
+        for (int i = 0; i < PR; ++i) {
+            int r = prg + i * PRG;
+            g4v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            cv[i] = pv[i] = hov[i] = 0.f;
+            if (r >= na) continue;
+            long b = tile + (long)n_tiles * r;
+            long frame = off_t + b;
+            long prow = prev_base + b;
+            g4v[i] = __ldg(reinterpret_cast<const float4*>(p.Gs + frame * (4 * H) + unit * 4));
+            hov[i] = __ldg(p.dHoff + frame * H + unit);
+            if (CELL == 0) {
+                cv[i] = __ldg(p.Call + ((long)B + frame) * H + unit);
+                pv[i] = __ldg(p.Call + prow * H + unit);
+            } else {
+                pv[i] = __ldg(p.Hall + prow * H + unit);
+            }
+        }
+
+        // ---- B3: gradient w.r.t. this CTA's MLP hidden pre-activations (operands in shared memory) ----
+        {
+            float acc[DFA_RT][4];
+#pragma unroll
+            for (int j = 0; j < DFA_RT; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+            // tanh outputs of this thread's tile: fetched before the GEMM so the latency hides behind it
+            float4 hdv[DFA_RT];
+            if (b3_ks == 0) {
+#pragma unroll
+                for (int j = 0; j < DFA_RT; ++j) {
+                    const int r = b3_rg + 16 * j;
+                    hdv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r >= na) continue;
+                    const long frame = off_t + tile + (long)n_tiles * r;
+                    const int col = b3_cg * 4;
+                    hdv[j] = __ldg(reinterpret_cast<const float4*>(p.Hid + frame * (2 * M) + (col / U) * M + u0 + col % U));
+                }
+            }
+            umma::mbar_wait(&dbar, (uint32_t)(Tt - 1 - t) & 1u);   // the dML rows of frame t have landed in As
+            DEC_TICK(0)
+            {
+                const int njw = min(DFA_RT, (na - 4 * (warp & 3) + 15) >> 4);   // warp-uniform trip count (its 4 row groups)
+                const float* ar = As + b3_rg * LDA + b3_ks * b3_nq0 * 4;
+                const float* wq = WB3 + (b3_ks * b3_nq0 * 4) * (2 * U) + b3_cg * 4;
+                switch (njw) {
+                    case 1: rows_gemm<1, 2 * U>(acc, ar, LDA, wq, b3_nq); break;
+                    case 2: rows_gemm<2, 2 * U>(acc, ar, LDA, wq, b3_nq); break;
+                    case 3: rows_gemm<3, 2 * U>(acc, ar, LDA, wq, b3_nq); break;
+                    case 4: rows_gemm<4, 2 * U>(acc, ar, LDA, wq, b3_nq); break;
+                    case 5: rows_gemm<5, 2 * U>(acc, ar, LDA, wq, b3_nq); break;
+                    default: break;
+                }
+            }
+            if (b3_ks == 1) {
+#pragma unroll
+                for (int j = 0; j < DFA_RT; ++j)
+                    *reinterpret_cast<float4*>(b3_scratch + ((tid - 128) * DFA_RT + j) * 4) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+            }
+            __syncthreads();   // partial tiles visible; every thread is done reading As (Ds aliases it)
+            DEC_TICK(1)
+            if (b3_ks == 0) {
+#pragma unroll
+                for (int j = 0; j < DFA_RT; ++j) {
+                    const int r = b3_rg + 16 * j;
+                    if (r >= na) continue;
+                    const float4 o2 = *reinterpret_cast<const float4*>(b3_scratch + (tid * DFA_RT + j) * 4);
+                    const long frame = off_t + tile + (long)n_tiles * r;
+                    const int col = b3_cg * 4;
+                    const int which = col / U, uu = col % U;
+                    const long o = frame * (2 * M) + which * M + u0 + uu;
+                    const float4 hd = hdv[j];
+                    const float4 v = make_float4((acc[j][0] + o2.x) * (1.f - hd.x * hd.x), (acc[j][1] + o2.y) * (1.f - hd.y * hd.y),
+                                                 (acc[j][2] + o2.z) * (1.f - hd.z * hd.z), (acc[j][3] + o2.w) * (1.f - hd.w * hd.w));
+                    *reinterpret_cast<float4*>(p.dHidPre + o) = v;
+                    *reinterpret_cast<float4*>(Ds + r * DSP + ((((col >> 2) ^ ((r >> 3) & 3))) << 2)) = v;
+                    hsum.x += v.x; hsum.y += v.y; hsum.z += v.z; hsum.w += v.w;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- B2': partial dh over all H units from this CTA's hidden slice ----
+        const int nq = (na + 3) >> 2;
+        const int n_mma = (na + 15) & ~15;
+        const uint32_t idesc_ts = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_ss = idesc_ts | (1u << 15);
+        // re-lay `pieces` 16-byte pieces (4 k each) starting at piece `pc0` of the rows of `src` (pitch SP, piece-swizzled)
+        // into the [k][row] operand tiles
+        auto relayout = [&](const float* src, int SP, int pc0) {
+            for (int idx = tid; idx < (ROWS / 4) * (TS_SLAB / 4); idx += NTHREADS) {
+                const int q = idx % (ROWS / 4), kq = idx / (ROWS / 4);
+                if (q >= nq) continue;
+                const float* rb = src + (4 * q) * SP + (((pc0 + kq) ^ ((q >> 1) & 3)) << 2);
+                const float4 r0 = *reinterpret_cast<const float4*>(rb);
+                const float4 r1 = *reinterpret_cast<const float4*>(rb + SP);
+                const float4 r2 = *reinterpret_cast<const float4*>(rb + 2 * SP);
+                const float4 r3 = *reinterpret_cast<const float4*>(rb + 3 * SP);
+                umma::split_store(b_hi, b_lo, umma::tile_off<TS_CHUNK>(kq * 4 + 0, q), make_float4(r0.x, r1.x, r2.x, r3.x));
+                umma::split_store(b_hi, b_lo, umma::tile_off<TS_CHUNK>(kq * 4 + 1, q), make_float4(r0.y, r1.y, r2.y, r3.y));
+                umma::split_store(b_hi, b_lo, umma::tile_off<TS_CHUNK>(kq * 4 + 2, q), make_float4(r0.z, r1.z, r2.z, r3.z));
+                umma::split_store(b_hi, b_lo, umma::tile_off<TS_CHUNK>(kq * 4 + 3, q), make_float4(r0.w, r1.w, r2.w, r3.w));
+            }
+            umma::fence_proxy_async();
+            umma::fence_before_sync();
+            __syncthreads();
+        };
+        // accumulator blocks D^T[column][row] -> out[column][ROWS] (global partials stay transposed: every thread writes 64
+        // contiguous bytes per tcgen05.ld; the owners reduce them after the barrier)
+        auto push_blocks = [&](int nblk, int ncols, float* out) {
+            const int lq = warp & 3;
+            for (int b = warp >> 2; b < nblk; b += 2) {
+                const int j = b * 128 + lq * 32 + lane;
+#pragma unroll 1
+                for (int r0 = 0; r0 < na; r0 += 16) {
+                    uint32_t r[16];
+                    umma::tmem_ld16(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * DBT_DCOLS + r0), r);
+                    if (j < ncols) {
+                        float4* o = reinterpret_cast<float4*>(out + (long)j * ROWS + r0);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v)
+                            o[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                    }
+                }
+            }
+            umma::fence_before_sync();
+        };
+        DEC_TICK(2)
+        // ---- B2' on the tensor cores: partial dh over all H units from this CTA's hidden slice (K = 2U = 32) ----
+        relayout(Ds, DSP, 0);
+        if (tid == 0) {
+            umma::fence_after_sync();
+            const uint32_t bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo), wl = umma::smem_u32(wlo2);
+#pragma unroll 1
+            for (int b = 0; b < 2; ++b) {
+#pragma unroll
+                for (int kg = 0; kg < TS_SLAB / 8; ++kg) {
+                    const uint64_t dbh = umma::make_desc(bh + kg * 1024, TS_CHUNK, 512);
+                    const uint64_t dbl = umma::make_desc(bl + kg * 1024, TS_CHUNK, 512);
+                    const uint64_t dwl = umma::make_desc(wl + b * 4 * TS_CHUNK + kg * 1024, TS_CHUNK, 512);
+                    const uint32_t ta = tmem + (uint32_t)(DBT_A2_COL + b * 2 * U + kg * 8);
+                    const uint32_t td = tmem + (uint32_t)(b * DBT_DCOLS);
+                    mma_tf32_ts(td, ta, dbh, idesc_ts, kg > 0 ? 1u : 0u);
+                    mma_tf32_ts(td, ta, dbl, idesc_ts, 1u);
+                    umma::mma_tf32(td, dwl, dbh, idesc_ss, 1u);
+                }
+            }
+            umma::commit(&bar);
+        }
+        bar_uses += 1;
+        // under the MMAs: the recurrent carry left by the previous iteration's B1' (its partials stay valid until this step's B1')
+        if (na_last > 0) reduce_dh(na_last);
+        umma::mbar_wait(&bar, (bar_uses - 1) & 1);
+        umma::fence_after_sync();
+        push_blocks(2, H, Pb2);
+        DEC_TICK(3)
+        cluster_sync_all();
+        DEC_TICK(4)
+
+        // ---- dh of this CTA's units = sum of the partials (+ carry), then the gate gradients ----
+        for (int idx = tid; idx < ((na + 3) >> 2) * U; idx += NTHREADS) {
+            const int rq = idx % ((na + 3) >> 2), j = idx / ((na + 3) >> 2);   // 4 rows of one unit: contiguous in the transposed partials
+            float4 v[CL];
+#pragma unroll
+            for (int src = 0; src < CL; ++src) v[src] = ld_cg4(Pb2t + ((long)src * H + u0 + j) * ROWS + 4 * rq);
+            float4 a = v[0];
+#pragma unroll
+            for (int src = 1; src < CL; ++src) { a.x += v[src].x; a.y += v[src].y; a.z += v[src].z; a.w += v[src].w; }
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (4 * rq + i < na) dh_sm[(4 * rq + i) * U + j] += av[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < PR; ++i) {
+            int r = prg + i * PRG;
+            if (r >= na) continue;
+            long frame = off_t + tile + (long)n_tiles * r;
+            float dh = dh_sm[r * U + pu] + hov[i];
+            float carry = dc_sm[r * U + pu];
+            const float4 g4 = g4v[i];
+            float4 dgv;
+            if (CELL == 0) {
+                float c = cv[i];
+                float c_prev = pv[i];
+                float tc = tanhf(c);
+                float ig = g4.x, fg = g4.y, gg = g4.z, og = g4.w;
+                float dc = carry + dh * og * (1.f - tc * tc);
+                dgv.x = dc * gg * ig * (1.f - ig);
+                dgv.y = dc * c_prev * fg * (1.f - fg);
+                dgv.z = dc * ig * (1.f - gg * gg);
+                dgv.w = dh * tc * og * (1.f - og);
+                dc_sm[r * U + pu] = dc * fg;
+            } else {
+                dh += carry;
+                float h_prev = pv[i];
+                float rg_ = g4.x, zg = g4.y, ng = g4.z, hn = g4.w;
+                float dn_pre = dh * (1.f - zg) * (1.f - ng * ng);
+                dgv.x = dn_pre * hn * rg_ * (1.f - rg_);
+                dgv.y = dh * (h_prev - ng) * zg * (1.f - zg);
+                dgv.z = dn_pre;
+                dgv.w = dn_pre * rg_;
+                dc_sm[r * U + pu] = dh * zg;
+            }
+            *reinterpret_cast<float4*>(p.dG + frame * (4 * H) + unit * 4) = dgv;
+            *reinterpret_cast<float4*>(Gsm + r * GSP + ((pu ^ ((r >> 3) & 3)) << 2)) = dgv;
+            bsum.x += dgv.x; bsum.y += dgv.y; bsum.z += dgv.z; bsum.w += dgv.w;
+        }
+        __syncthreads();
+
+        // ---- B1': partial [dh_{t-1} | dx_t] from this CTA's gate columns ----
+        DEC_TICK(6)
+        // ---- B1' on the tensor cores: partial [dh_{t-1} | dx_t] from this CTA's gate columns (K = 4U = 64, two halves) ----
+        for (int half = 0; half < 2; ++half) {
+            if (half == 1) umma::mbar_wait(&bar, (bar_uses - 1) & 1);   // the MMAs of the first half have read the tiles
+            relayout(Gsm, GSP, half * (TS_SLAB / 4));
+            if (tid == 0) {
+                umma::fence_after_sync();
+                const uint32_t bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo), wl = umma::smem_u32(wlo1);
+#pragma unroll 1
+                for (int b = 0; b < 3; ++b) {
+#pragma unroll
+                    for (int kg = 0; kg < TS_SLAB / 8; ++kg) {
+                        const uint64_t dbh = umma::make_desc(bh + kg * 1024, TS_CHUNK, 512);
+                        const uint64_t dbl = umma::make_desc(bl + kg * 1024, TS_CHUNK, 512);
+                        const uint64_t dwl = umma::make_desc(wl + half * ((DBT_M1 / 32) * TS_CHUNK) + b * 4 * TS_CHUNK + kg * 1024, TS_CHUNK, 512);
+                        const uint32_t ta = tmem + (uint32_t)(DBT_A1_COL + b * 4 * U + half * TS_SLAB + kg * 8);
+                        const uint32_t td = tmem + (uint32_t)(b * DBT_DCOLS);
+                        mma_tf32_ts(td, ta, dbh, idesc_ts, (half > 0 || kg > 0) ? 1u : 0u);
+                        mma_tf32_ts(td, ta, dbl, idesc_ts, 1u);
+                        umma::mma_tf32(td, dwl, dbh, idesc_ss, 1u);
+                    }
+                }
+                umma::commit(&bar);
+            }
+            bar_uses += 1;
+        }
+        umma::mbar_wait(&bar, (bar_uses - 1) & 1);
+        umma::fence_after_sync();
+        push_blocks(3, N1, Pb1);
+        DEC_TICK(7)
+        cluster_sync_all();
+        DEC_TICK(8)
+
+        // ---- dx for this CTA's x columns, folded into dML of the previous frame and pushed to every CTA's B3 input ----
+        if (t > 0) push_dml(t - 1, na);
+        na_last = na;
+        DEC_TICK(9)
+    }
+#undef DEC_TICK
+    if (na_last > 0) reduce_dh(na_last);   // carry out of step 0: gradient of the initial state
+    __syncthreads();
+    if (timing) { tacc[15] = Tt; for (int i = 0; i < 16; ++i) g_dec_timing[i] = tacc[i]; }
+    // gradient w.r.t. the initial state produced by feature2hidden (h0 = even, c0 = odd columns; model.py:100)
+    for (int i = 0; i < PR; ++i) {
+        int r = prg + i * PRG;
+        long b = tile + (long)n_tiles * r;
+        if (b >= B || r >= ROWS) continue;
+        if (CELL == 0) {
+            p.dHC0[b * (2 * H) + 2 * unit] = dh_sm[r * U + pu];
+            p.dHC0[b * (2 * H) + 2 * unit + 1] = dc_sm[r * U + pu];
+        } else {
+            p.dHC0[b * H + unit] = dh_sm[r * U + pu] + dc_sm[r * U + pu];
+        }
+    }
+    // recurrent bias gradients: fixed-order reduction over the row groups, one row of partial sums per tile
+    {
+        __syncthreads();
+        float4* red = reinterpret_cast<float4*>(st.buf0);
+        red[prg * U + pu] = bsum;
+        __syncthreads();
+        if (tid < U) {
+            float4 a = red[tid];
+            for (int g = 1; g < PRG; ++g) {
+                const float4 b = red[g * U + tid];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            *reinterpret_cast<float4*>(p.dbias + (long)tile * (4 * H) + (u0 + tid) * 4) = a;
+        }
+        // MLP input-layer bias gradients: threads of the B3 epilogue hold sums for (4 columns, their row group)
+        __syncthreads();
+        if (b3_ks == 0) red[b3_rg * (2 * U / 4) + b3_cg] = hsum;
+        __syncthreads();
+        if (tid < 2 * U / 4) {
+            float4 a = red[tid];
+            for (int g = 1; g < 16; ++g) {
+                const float4 b = red[g * (2 * U / 4) + tid];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            const int col = tid * 4;   // column of this CTA's slice: [which][u0 + col % U]
+            *reinterpret_cast<float4*>(p.dbias1 + (long)tile * (2 * M) + (col / U) * M + u0 + col % U) = a;
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc<512>(tmem);
+}
+
 // -------------------------------------------------------------------------------------------------
 // helper kernels outside the time loop
 // -------------------------------------------------------------------------------------------------
@@ -1868,7 +2485,7 @@ size_t dec_fwd_ahead_smem(int F) {
 bool dec_fwd_use_ahead(int F) {
     static int off = -1;
     if (off < 0) { const char* e = getenv("ABCD_DEC_FWD"); off = (e && strcmp(e, "ahead")) ? 1 : 0; }   // any other explicit choice disables it
-    return !off && rnn_use_tc() && pad4(F) <= DFA_XKC && dec_fwd_ahead_smem(F) <= SMEM_MAX - 1024;
+    return !off && rnn_use_tc() && pad4(F) <= DFA_MAX_FP && dec_fwd_ahead_smem(F) <= SMEM_MAX - 1024;
 }
 // ABCD_DEC_FWD=ahead (default) | pair | ffma | tc64.  The pair variant pays one more exchange per step than the FFMA kernel and wins once a
 // tile has enough rows for the tensor-core contraction to matter (measured: 1.41 vs 1.52 ms at 73 rows per tile, 1.20 vs 1.18 at 37, 1.03 vs 0.94 ms at
@@ -1910,6 +2527,13 @@ int dec_bwd_ts_kc(int F) {
 }
 bool dec_bwd_use_ts(int F) { return rnn_use_tc() && ABCD_H + pad4(F) <= DBT_M1 && dec_bwd_ts_kc(F) != 0; }
 size_t dec_bwd_ts_smem(int F) { return dec_bwd_ts_fixed_bytes(F) + stage_floats(dec_bwd_ts_kc(F)) * sizeof(float); }
+// push variant (default): same shared-memory layout with the 64-wide staging area, which must hold the B3 input rows [ROWS][2Fp];
+// ABCD_DEC_BWD=ts selects the barrier-exchange kernel
+bool dec_bwd_use_push(int F) {
+    static int off = -1;
+    if (off < 0) { const char* e = getenv("ABCD_DEC_BWD"); off = (e && strcmp(e, "push")) ? 1 : 0; }
+    return !off && dec_bwd_use_ts(F) && dec_bwd_ts_kc(F) == 64 && (size_t)ROWS * 2 * pad4(F) <= stage_floats(64);
+}
 
 template <class K>
 int launch_cluster_dec(K kernel, int n_clusters, size_t smem, cudaStream_t stream, const DecK& params) {
@@ -1998,6 +2622,7 @@ DecK make_k(const DecParams& P, const PackedMeta& pk, const DecWs& w) {
     k.Hall = w.Hall; k.Call = w.Call; k.Xall = w.Xall; k.Gs = w.Gs; k.Hid = w.Hid; k.Mean = w.Mean; k.Lv = w.Lv;
     k.nll_partial = w.nll_partial; k.Pbuf = w.Pbuf; k.himg = w.himg; k.ximg = w.ximg;
     k.timing = getenv("ABCD_TIMING") ? atoi(getenv("ABCD_TIMING")) : 0;   // 1: forward kernel, 3: backward kernel
+    k.timing_cta = getenv("ABCD_TIMING_CTA") ? atoi(getenv("ABCD_TIMING_CTA")) : 0;
     k.dML = w.dML; k.dHidPre = w.dHidPre; k.dG = w.dG; k.dHoff = w.dHoff; k.dHC0 = w.dHC0; k.dbias = w.dbias; k.dbias1 = w.dbias1; k.Pb2 = w.Pb2; k.Pb1 = w.Pb1;
     return k;
 }
@@ -2018,6 +2643,8 @@ int dec_read_timing(unsigned long long* out16) {
     return ABCD_OK;
 }
 int dec_max_clusters(int which, int F, int* out) {
+    if (which == 1 && dec_bwd_use_push(F))
+        return rnn_max_active_clusters((const void*)dec_bwd_push_kernel<0>, dec_bwd_ts_smem(F), CL, NTHREADS, out);
     if (which == 1 && dec_bwd_use_ts(F))   // the tensor-memory backward
         return rnn_max_active_clusters(dec_bwd_ts_kc(F) == 64 ? (const void*)dec_bwd_ts_kernel<0, 64> : (const void*)dec_bwd_ts_kernel<0, 32>,
                                        dec_bwd_ts_smem(F), CL, NTHREADS, out);
@@ -2032,6 +2659,8 @@ int dec_max_clusters(int which, int F, int* out) {
 }
 
 int dec_init() {
+    TRY(rnn_prepare_kernel((const void*)dec_bwd_push_kernel<0>, SMEM_MAX - 1024));
+    TRY(rnn_prepare_kernel((const void*)dec_bwd_push_kernel<1>, SMEM_MAX - 1024));
     TRY(rnn_prepare_kernel((const void*)dec_bwd_ts_kernel<0, 64>, SMEM_MAX - 1024));   // the kernel also has static shared memory
     TRY(rnn_prepare_kernel((const void*)dec_bwd_ts_kernel<1, 64>, SMEM_MAX - 1024));   // the kernel also has static shared memory
     TRY(rnn_prepare_kernel((const void*)dec_bwd_ts_kernel<0, 32>, SMEM_MAX - 1024));   // the kernel also has static shared memory
@@ -2179,7 +2808,11 @@ int dec_backward(const DecParams& P, const DecGrads& G, const PackedMeta& pk, co
     {
         ProfScope ps(PROF_DEC_BWD, stream);
         const size_t sm = dec_bwd_smem(P.F);
-        if (dec_bwd_use_ts(P.F)) {
+        if (dec_bwd_use_push(P.F)) {
+            k.kc = 64;
+            if (P.cell == 0) TRY(launch_cluster_dec(dec_bwd_push_kernel<0>, n_tiles, dec_bwd_ts_smem(P.F), stream, k));
+            else TRY(launch_cluster_dec(dec_bwd_push_kernel<1>, n_tiles, dec_bwd_ts_smem(P.F), stream, k));
+        } else if (dec_bwd_use_ts(P.F)) {
             k.kc = dec_bwd_ts_kc(P.F);
             const size_t smt = dec_bwd_ts_smem(P.F);
             if (k.kc == 64) {

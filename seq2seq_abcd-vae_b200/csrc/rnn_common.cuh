@@ -95,11 +95,11 @@ __device__ __forceinline__ void zero_acc(float (&acc)[RT][4]) {
 }
 
 // A row r of the tile is the concatenation [rp0(r)[0,K0) | rp1(r)[0,K1)] (a null pointer means zeros).
-// K0 and K1 are multiples of 4 and all row pointers are 16-byte aligned.  KC = staged K-chunk (32/64/128).
+// K0 and K1 are multiples of 4 and all row pointers are 16-byte aligned.  KC = staged K-chunk (32/64/128/256).
 template <int NT, int KC, class RP0, class RP1>
 __device__ __forceinline__ void stage_chunk(float* dst, int k_begin, int k_len, int nrows, int K0,
                                             RP0 rp0, RP1 rp1, int tid) {
-    constexpr int LG = KC == 128 ? 5 : (KC == 64 ? 4 : 3);   // log2 of 16-byte pieces per staged row
+    constexpr int LG = KC == 256 ? 6 : KC == 128 ? 5 : (KC == 64 ? 4 : 3);   // log2 of 16-byte pieces per staged row
     constexpr int LDA = KC + 4;
     const int total = nrows << LG;
     for (int idx = tid; idx < total; idx += NT) {

@@ -74,9 +74,12 @@ def dec_timing():
 	v = list(out)
 	if v[15]:
 		n = float(v[15])
-		names = ['P1 setup', 'P1 gemm', 'P1 cell', 'barrier', 'P2 gemm', 'P2 store', 'barrier', 'P3 setup+gemm', 'P3 sample', 'barrier']
+		if os.environ.get('ABCD_DEC_FWD', 'ahead') == 'ahead':   # one-step-ahead pair kernel (default)
+			names = ['wait C', 'P1 x product', 'P1 cell + publish', 'barrier A', 'P2 gemm', 'P2 store + P3a', 'read-back + send', 'barrier B', 'P3b + x push', 'arrive C + saves + recv']
+		else:
+			names = ['P1 setup', 'P1 gemm', 'P1 cell', 'barrier', 'P2 gemm', 'P2 store', 'barrier', 'P3 setup+gemm', 'P3 sample', 'barrier']
 		print('dec_fwd CTA0 cycles/step: ' + ', '.join('%s %.0f' % (nm, x / n) for nm, x in zip(names, v[:10])) + ' (steps %d, total %.0f)' % (v[15], sum(v[:10]) / n))
-		print('   P1 gemm: stage-issue %.0f wait+sync %.0f mma %.0f chunks %.2f tail-sync %.0f' % tuple(x / n for x in v[10:15]))
+		print('   slots 10..14 (ahead: MMA issue cycles of the issuing thread, arrive A, arrive B, arrive C / others: P1 gemm detail): ' + ' '.join('%.0f' % (x / n) for x in v[10:15]))
 
 
 if os.environ.get('ABCD_TIMING') == '3':
