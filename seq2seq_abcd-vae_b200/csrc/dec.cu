@@ -669,13 +669,12 @@ constexpr int DFA_MAX_FP = 88; // x rows [ROWS][Fp + 4] must fit in the P2 stagi
 constexpr int DFA_STAGES = ABCD_H / TS_SLAB / 2;   // ring stages = h slabs of one CTA of a pair
 constexpr int DFA_MMA_TID = 224;                   // lane 0 of warp 7: copy + MMA thread (warp 7 has no share of the P2 epilogue and of P3a)
 constexpr int DFA_RT = 5;                          // P1: rows per thread (rows rgx + 16 j)
-constexpr int DFA_XITEMS = 2;                      // P3b: (row, column) items per thread
 __host__ __device__ constexpr size_t dfa_stage_floats() { return (size_t)2 * ROWS * (DFA_KC + 4); }
 constexpr int DFA_P2_ONE_ROWS = 40;                // P2 stages all of K = H at once when at most this many rows are active
 static_assert((size_t)DFA_P2_ONE_ROWS * (ABCD_H + 4) <= dfa_stage_floats(), "one-chunk P2 staging must fit in the staging area");
 static_assert(DFA_STAGES <= TSP_STAGES && DFA_STAGES <= TSP_MAX_SLABS, "ring / tensor-memory geometry of the pair variant");
 static_assert((size_t)ROWS * (DFA_MAX_FP + 4) <= dfa_stage_floats(), "x rows must fit in the staging area");
-static_assert(ROWS * ((DFA_MAX_FP + CL - 1) / CL) <= DFA_XITEMS * NTHREADS, "P3b items per thread");
+static_assert(2 * ROWS * ((DFA_MAX_FP / 4 + CL - 1) / CL) <= 2 * NTHREADS, "P3b: two lanes per (row, column group) item");
 static_assert(NTHREADS == 16 * U && ROWS == 16 * DFA_RT, "P1 thread map: 16 units x 16 row groups");
 
 // One 4-byte store into the shared memory of CTA `cta` of the cluster that also signals 4 bytes on that CTA's mbarrier (same
@@ -689,6 +688,14 @@ __device__ __forceinline__ void st_async_cluster_f32(uint32_t local_smem_addr, u
 }
 
 // acc[j][0..3] += x[row rg + 16 j][0, 4 nk4) * W[.., 4 columns of this thread] (row pitch LDW)   for j < NJ (warp-uniform)
+__device__ __forceinline__ void st_async_cluster_v4(uint32_t local_smem_addr, uint32_t local_bar_addr, unsigned cta, float a, float b, float c, float d) {
+    uint32_t remote, rbar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(local_smem_addr), "r"(cta));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(rbar) : "r"(local_bar_addr), "r"(cta));
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n"
+                 ::"r"(remote), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)), "r"(rbar) : "memory");
+}
+
 template <int NJ, int LDW>
 __device__ __forceinline__ void rows_gemm(float (&acc)[DFA_RT][4], const float* xr, int ldx, const float* wq, int nk4) {
 #pragma unroll 2
@@ -714,7 +721,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
     float* const smem = smem_ahead;
     const int H = ABCD_H, M = ABCD_M;
     const int F = p.F, Fp = p.Fp;
-    const int XC = xcols_per_cta(F);
     const int LDX = Fp + 4;                   // pitch of the x rows
     constexpr int KC = DFA_KC;
     constexpr int HSP = 2 * U + 4;            // pitch of the CTA's own hidden-layer slice kept in shared memory
@@ -740,8 +746,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
     const int tile = blockIdx.x / CL;
     const int u0 = rank * U;                  // the 16 units this CTA finalises (cell update, MLP slices)
     const int pair_u0 = (rank >> 1) * 2 * U;  // the 32 units whose gate columns the pair contracts
-    const int xc0 = rank * XC;
-    const int xc1 = min(Fp, xc0 + XC);        // (columns F..Fp-1 are padding: their owner pushes zeros)
+    const int ng_mine = (Fp / 4 - rank + CL - 1) / CL;   // x column groups (4 columns) owned by this CTA: rank, rank + 16, ...
 
     // ---- resident weights ----
     if ((umma::smem_u32(smem) & 1023u) != 0) __trap();
@@ -801,8 +806,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
         bias2[j] = p.em_b1[col / U][u0 + col % U];
     }
     const int ncg3 = 2 * Fp / 4;                                      // column groups of the local emission GEMM
-    float* Pmine = p.Pbuf + (long)blockIdx.x * ROWS * (2 * Fp);       // this CTA's partial emission parameters
-    const float* Ptile = p.Pbuf + (long)tile * CL * ROWS * (2 * Fp);  // partials of all CTAs of the cluster
+    const int NG = Fp / 4;                                            // x column groups
+    // partial emission parameters, laid out for the reader: [source CTA][x column group][row][mean x 4 | log-variance x 4]
+    float* Pmine = p.Pbuf + (long)blockIdx.x * ROWS * (2 * Fp);
+    const float* Ptile = p.Pbuf + (long)tile * CL * ROWS * (2 * Fp);
     // pair exchange of the gate partial sums (the backward pass's partial buffer is idle during the forward pass)
     float* pair_send = p.Pb2 + (size_t)(blockIdx.x ^ 1) * ROWS * H;
     const float* pair_recv = p.Pb2 + (size_t)blockIdx.x * ROWS * H;
@@ -989,7 +996,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
 #pragma unroll
                     for (int i = 0; i < 5; ++i) {
                         const int r = r0 + 16 * i;
-                        if (r < na) *reinterpret_cast<float4*>(Pmine + (long)r * (2 * Fp) + cg * 4) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+                        if (r < na) *reinterpret_cast<float4*>(Pmine + ((long)(cg % NG) * ROWS + r) * 8 + (cg / NG) * 4) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
                     }
                 }
             }
@@ -1007,55 +1014,70 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(xbar_addr), "r"((uint32_t)(na_next * Fp * 4)) : "memory");
         }
 
-        // ---- P3b: sum the partials of this CTA's x columns, reparameterised sample, NLL; push x_t to every CTA of the cluster ----
-        float sv_mean[DFA_XITEMS], sv_lv[DFA_XITEMS], sv_x[DFA_XITEMS];
-        long sv_frame[DFA_XITEMS];
-        int sv_c[DFA_XITEMS];
-#pragma unroll
-        for (int it = 0; it < DFA_XITEMS; ++it) {
-            const int o = p3b_tid + it * NTHREADS;
-            sv_c[it] = -1;
-            if (o >= na * XC) continue;
-            const int r = o / XC, c = xc0 + o % XC;
-            if (c >= xc1) continue;
-            float x = 0.f;
-            if (c < F) {
+        // ---- P3b: emission parameters of this CTA's x column groups (group g of 4 columns belongs to rank g % 16), reparameterised
+        // sample, NLL; x_t pushed to every CTA of the cluster, 16 bytes per store.  Two lanes per (row, group) item: the even lane
+        // sums the 16 partial means, the odd lane the 16 partial log-variances (one L2 round trip, fixed order), then they swap ----
+        {
+            const int n_items = na * ng_mine;
+            for (int vt = p3b_tid; (vt & ~31) < 2 * n_items; vt += NTHREADS) {   // (warp-uniform: the lanes exchange their sums with shuffles)
+                const int item = vt >> 1, which = vt & 1;
+                const bool valid = item < n_items;
+                const int r = valid ? item / ng_mine : 0, c0 = 4 * (rank + CL * (valid ? item % ng_mine : 0));
                 const long frame = off_t + tile + (long)n_tiles * r;
-                const float e = __ldg(p.eps + frame * p.ld_eps + c);
-                const float g = p.gt ? __ldg(p.gt + frame * p.ld_gt + c) : 0.f;
-                float pm[CL], pv[CL];
+                // noise / ground truth of this lane's two columns come from HBM: issued first, their latency hides behind the partial sums
+                const int cj = c0 + 2 * which;
+                float ev[2], gv[2];
 #pragma unroll
-                for (int src = 0; src < CL; ++src) {
-                    const float* q = Ptile + ((long)src * ROWS + r) * (2 * Fp) + c;
-                    pm[src] = ld_cg(q);
-                    pv[src] = ld_cg(q + Fp);
+                for (int j = 0; j < 2; ++j) {
+                    ev[j] = (valid && cj + j < F) ? __ldg(p.eps + frame * p.ld_eps + cj + j) : 0.f;
+                    gv[j] = (valid && p.gt && cj + j < F) ? __ldg(p.gt + frame * p.ld_gt + cj + j) : 0.f;
                 }
-                float mean = __ldg(p.em_b2[0] + c), lv = __ldg(p.em_b2[1] + c);
+                float4 pp[CL];
+                const float* src0 = Ptile + ((long)(c0 >> 2) * ROWS + r) * 8 + which * 4;
 #pragma unroll
-                for (int src = 0; src < CL; ++src) { mean += pm[src]; lv += pv[src]; }
-                x = mean + expf(0.5f * lv) * e;
-                if (p.gt) {
-                    const float d = g - mean;
-                    nll += 0.5f * (LOG_2PI + lv + d * expf(-lv) * d);
+                for (int src = 0; src < CL; ++src) pp[src] = valid ? ld_cg4(src0 + (long)src * ROWS * (2 * Fp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 acc4;
+                acc4.x = c0 + 0 < F ? __ldg(p.em_b2[which] + c0 + 0) : 0.f; acc4.y = c0 + 1 < F ? __ldg(p.em_b2[which] + c0 + 1) : 0.f;
+                acc4.z = c0 + 2 < F ? __ldg(p.em_b2[which] + c0 + 2) : 0.f; acc4.w = c0 + 3 < F ? __ldg(p.em_b2[which] + c0 + 3) : 0.f;
+#pragma unroll
+                for (int src = 0; src < CL; ++src) { acc4.x += pp[src].x; acc4.y += pp[src].y; acc4.z += pp[src].z; acc4.w += pp[src].w; }
+                if (c0 + 0 >= F) acc4.x = 0.f;   // padding columns carry zeros
+                if (c0 + 1 >= F) acc4.y = 0.f;
+                if (c0 + 2 >= F) acc4.z = 0.f;
+                if (c0 + 3 >= F) acc4.w = 0.f;
+                float4 oth;
+                oth.x = __shfl_xor_sync(0xffffffffu, acc4.x, 1); oth.y = __shfl_xor_sync(0xffffffffu, acc4.y, 1);
+                oth.z = __shfl_xor_sync(0xffffffffu, acc4.z, 1); oth.w = __shfl_xor_sync(0xffffffffu, acc4.w, 1);
+                const float4 mean4 = which ? oth : acc4, lv4 = which ? acc4 : oth;
+                // this lane finalises columns cj, cj + 1; the sample quad is completed by one more swap
+                const float m0 = which ? mean4.z : mean4.x, m1 = which ? mean4.w : mean4.y;
+                const float l0 = which ? lv4.z : lv4.x, l1 = which ? lv4.w : lv4.y;
+                float x0 = 0.f, x1 = 0.f;
+                if (cj < F) {
+                    x0 = m0 + expf(0.5f * l0) * ev[0];
+                    if (p.gt && valid) { const float d = gv[0] - m0; nll += 0.5f * (LOG_2PI + l0 + d * expf(-l0) * d); }
                 }
-                sv_mean[it] = mean; sv_lv[it] = lv; sv_x[it] = x; sv_frame[it] = frame; sv_c[it] = c;
-            }
-            if (na_next > 0 && r < na_next) {
-                const uint32_t a = xs_addr + (uint32_t)(r * LDX + c) * 4u;
+                if (cj + 1 < F) {
+                    x1 = m1 + expf(0.5f * l1) * ev[1];
+                    if (p.gt && valid) { const float d = gv[1] - m1; nll += 0.5f * (LOG_2PI + l1 + d * expf(-l1) * d); }
+                }
+                const float y0 = __shfl_xor_sync(0xffffffffu, x0, 1), y1 = __shfl_xor_sync(0xffffffffu, x1, 1);
+                const float4 x4 = which ? make_float4(y0, y1, x0, x1) : make_float4(x0, x1, y0, y1);
+                DEC_TICK(13)
+                if (valid && r < na_next) {
+                    const uint32_t a = xs_addr + (uint32_t)(r * LDX + c0) * 4u;
 #pragma unroll
-                for (unsigned q = 0; q < (unsigned)CL; ++q) st_async_cluster_f32(a, xbar_addr, q, x);
+                    for (unsigned q = 0; q < (unsigned)CL / 2; ++q) st_async_cluster_v4(a, xbar_addr, 8u * which + q, x4.x, x4.y, x4.z, x4.w);
+                }
+                if (valid) {   // saved for the backward pass
+                    *reinterpret_cast<float4*>((which ? p.Lv : p.Mean) + frame * Fp + c0) = which ? lv4 : mean4;
+                    if (which == 0) *reinterpret_cast<float4*>(p.Xall + ((long)B + frame) * Fp + c0) = x4;
+                }
             }
         }
         DEC_TICK(8)
         // off the critical path (the next step waits for x_t on its mbarrier; WAR hazards on the exchange buffers are covered by
-        // barriers A and B of the next step): activations saved for the backward pass, partner's half of the next gate pre-activations
-#pragma unroll
-        for (int it = 0; it < DFA_XITEMS; ++it) {
-            if (sv_c[it] < 0) continue;
-            p.Mean[sv_frame[it] * Fp + sv_c[it]] = sv_mean[it];
-            p.Lv[sv_frame[it] * Fp + sv_c[it]] = sv_lv[it];
-            p.Xall[((long)B + sv_frame[it]) * Fp + sv_c[it]] = sv_x[it];
-        }
+        // barriers A and B of the next step): partner's half of the next gate pre-activations
         if (na_next > 0) ts_pair_drain_recv(tsp, gpre, pair_recv, na_next, tid);
         DEC_TICK(9)
     }
@@ -1857,7 +1879,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_push_kernel(DecK p) {
     float* const smem = smem_push;
     const int H = ABCD_H, M = ABCD_M;
     const int F = p.F, Fp = p.Fp;
-    const int XC = xcols_per_cta(F);
     const int N1 = H + Fp;                    // columns of the B1' partial: [dh_prev (H) | dx (Fp)]
     constexpr int DSP = 2 * U + 4;            // pitch of the dHidPre slice in shared memory
     constexpr int GSP = 4 * U + 4;            // pitch of the dG slice in shared memory
@@ -1882,8 +1903,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_push_kernel(DecK p) {
     const int rank = (int)cluster_ctarank();
     const int tile = blockIdx.x / CL;
     const int u0 = rank * U;
-    const int xc0 = rank * XC;
-    const int xc1 = min(Fp, xc0 + XC);        // (columns F..Fp-1 are padding: their owner pushes zeros)
+    const int ng_mine = (Fp / 4 - rank + CL - 1) / CL;   // x column groups (4 columns) owned by this CTA: rank, rank + 16, ...
 
     for (int idx = tid; idx < 2 * Fp * 2 * U; idx += NTHREADS) {
         int col = idx % (2 * U), k = idx / (2 * U);   // row k of the interleaved input: x column k / 2, mean (0) or log-variance (1) head
@@ -1992,38 +2012,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_push_kernel(DecK p) {
         const int na_p = active_rows(p.batch_sizes[t_prev], tile, n_tiles);
         if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(dbar_addr), "r"((uint32_t)(na_p * 2 * Fp * 4)) : "memory");
         const long pbase = p.offsets[t_prev] + tile;
-        for (int idx = tid; idx < na_p * XC; idx += NTHREADS) {
-            const int r = idx % na_p, c = xc0 + idx / na_p;   // rows fastest: contiguous in the transposed partials
-            if (c >= xc1) continue;
-            float m0 = 0.f, m1 = 0.f;
-            if (c < F) {
-                const long pf = pbase + (long)n_tiles * r;   // frame that produced x_t
-                float* dm = p.dML + pf * (2 * Fp) + c;
-                m0 = dm[0]; m1 = dm[Fp];
-                if (r < na_t) {
-                    float v[CL];
+        // items: (row, pair of x columns): 16 bytes of the interleaved B3 input row
+        for (int idx = tid; idx < na_p * ng_mine * 2; idx += NTHREADS) {
+            const int r = idx % na_p, hp = idx / na_p;                  // rows fastest: contiguous in the transposed partials
+            const int c0 = 4 * (rank + CL * (hp >> 1)) + 2 * (hp & 1);   // columns c0, c0 + 1
+            const long pf = pbase + (long)n_tiles * r;                   // frame that produced x_t
+            float* dm = p.dML + pf * (2 * Fp) + c0;
+            float2 m0 = *reinterpret_cast<const float2*>(dm), m1 = *reinterpret_cast<const float2*>(dm + Fp);
+            if (r < na_t) {
+                // saved activations and noise come from HBM: issued first, their latency hides behind the partial sums
+                const float2 lv = __ldg(reinterpret_cast<const float2*>(p.Lv + pf * Fp + c0));
+                float e[2];
 #pragma unroll
-                    for (int src = 0; src < CL; ++src) v[src] = ld_cg(Pb1t + ((long)src * N1 + H + c) * ROWS + r);
-                    const float lv = __ldg(p.Lv + pf * Fp + c);
-                    const float e = __ldg(p.eps + pf * p.ld_eps + c);
-                    float dx = v[0];
+                for (int j = 0; j < 2; ++j) e[j] = c0 + j < F ? __ldg(p.eps + pf * p.ld_eps + c0 + j) : 0.f;
+                float v[2][CL];
 #pragma unroll
-                    for (int src = 1; src < CL; ++src) dx += v[src];
-                    m0 += dx;
-                    m1 += dx * 0.5f * expf(0.5f * lv) * e;
-                    dm[0] = m0;
-                    dm[Fp] = m1;
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int src = 0; src < CL; ++src) v[j][src] = c0 + j < F ? ld_cg(Pb1t + ((long)src * N1 + H + c0 + j) * ROWS + r) : 0.f;
+                float dx[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    dx[j] = v[j][0];
+#pragma unroll
+                    for (int src = 1; src < CL; ++src) dx[j] += v[j][src];
                 }
+                m0.x += dx[0]; m0.y += dx[1];
+                m1.x += dx[0] * 0.5f * expf(0.5f * lv.x) * e[0]; m1.y += dx[1] * 0.5f * expf(0.5f * lv.y) * e[1];
             }
-            const uint32_t a = as_addr + (uint32_t)(r * LDA + 2 * c) * 4u;
+            // padding columns carry zeros (their rows of the output weights are zero, but stale bits could be NaN)
+            if (c0 + 0 >= F) { m0.x = 0.f; m1.x = 0.f; }
+            if (c0 + 1 >= F) { m0.y = 0.f; m1.y = 0.f; }
+            if (r < na_t) {
+                *reinterpret_cast<float2*>(dm) = m0;
+                *reinterpret_cast<float2*>(dm + Fp) = m1;
+            }
+            const uint32_t a = as_addr + (uint32_t)(r * LDA + 2 * c0) * 4u;
 #pragma unroll
-            for (unsigned q = 0; q < (unsigned)CL; ++q) {
-                uint32_t remote, rbar;
-                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(a), "r"(q));
-                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(rbar) : "r"(dbar_addr), "r"(q));
-                asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];\n"
-                             ::"r"(remote), "r"(__float_as_uint(m0)), "r"(__float_as_uint(m1)), "r"(rbar) : "memory");
-            }
+            for (unsigned q = 0; q < (unsigned)CL; ++q) st_async_cluster_v4(a, dbar_addr, q, m0.x, m1.x, m0.y, m1.y);
         }
     };
     // recurrent carry dh of this CTA's units = sum of the B1' partials of the step that has just finished (rows < na_t)
