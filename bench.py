@@ -34,8 +34,10 @@ if ROOT not in sys.path:
 METRIC = 'train segments/sec (fwd+bwd+step)'
 CFG = dict(rnn='LSTM', F=65, K=128, f=256, H=256, M=256, B=512, N_data=100000)
 PERSISTENT = ('enc_fwd_kernel', 'enc_bwd_kernel', 'dec_fwd_kernel', 'dec_bwd_kernel')
-# exchanges (publish -> cluster barrier -> consume) per time step and cluster size of each persistent kernel
-EXCHANGES = {'enc_fwd_kernel': (1, 8), 'enc_bwd_kernel': (1, 8), 'dec_fwd_kernel': (3, 16), 'dec_bwd_kernel': (3, 16)}
+# exchanges through L2 (publish -> cluster barrier -> consume) per time step and cluster size of each persistent kernel (DESIGN.md
+# section 4).  The decoder kernels' third exchange (x_t forward, the dML rows backward) is a st.async push into the consumers'
+# shared memory that completes on an mbarrier: no fence, no barrier, no L2 round trip -- it is not counted here.
+EXCHANGES = {'enc_fwd_kernel': (1, 8), 'enc_bwd_kernel': (1, 8), 'dec_fwd_kernel': (2, 16), 'dec_bwd_kernel': (2, 16)}
 
 
 def parse():
@@ -486,7 +488,8 @@ def main():
 								'bound by the per-timestep latency chain, see latency_roofline'}
 		latency_roofline = {'T_max': T_max, 'kernels': latency, 'exchange_ns': exch,
 							'note': 'us per time step of each persistent kernel against the measured cost of its publish -> cluster barrier -> consume '
-									'exchanges (abcd_measure_cluster_exchange, 16-way fan-in rows through L2); the remainder is the dependent chain '
+									'exchanges through L2 (abcd_measure_cluster_exchange, 16-way fan-in rows; the decoder kernels have a third, '
+									'barrier-free exchange: st.async pushes into the consumers\' shared memory); the remainder is the dependent chain '
 									'operand fetch -> tcgen05.mma / FFMA -> tcgen05.ld -> cell update inside a step'}
 		n_params = learner.arena.numel
 		hbm_peak = peaks.get('hbm_gbs', 6650.0)

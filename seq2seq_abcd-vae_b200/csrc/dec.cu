@@ -2622,14 +2622,13 @@ DecWs dec_carve(void* base, size_t cap, int cell, int F, int fin, int B, int sum
     w.Pb2 = a.take<float>((size_t)n_tiles * CL * ROWS * H);
     w.Pb1 = a.take<float>((size_t)n_tiles * CL * ROWS * (H + Fp));
     w.prev = a.take<int>((size_t)sumT);
-    // largest split-K partial: dW_hh / dW_ih ([4H] x [H|F]) or MLP weights ([M] x [H])
+    // split-K partials of ALL weight-gradient GEMMs (their epilogues are deferred and batched, see EpilogueBatch) plus the
+    // scratch of the batched column sums
     size_t mx = 0;
     {
-        int dims[][3] = {{4 * H, H, sumT}, {4 * H, F, sumT}, {M, H, sumT}, {F, M, sumT}, {1, M, sumT}, {hc, fin, B}};
-        for (auto& d : dims) {
-            size_t v = (size_t)sgemm_pick_splits(d[0], d[1], d[2]) * d[0] * d[1];
-            if (v > mx) mx = v;
-        }
+        int dims[][3] = {{4 * H, H, sumT}, {4 * H, F, sumT}, {M, H, sumT}, {M, H, sumT}, {M, H, sumT}, {F, M, sumT}, {F, M, sumT}, {1, M, sumT}, {hc, fin, B}};
+        for (auto& d : dims) mx += (((size_t)sgemm_pick_splits(d[0], d[1], d[2]) * d[0] * d[1]) + 3) & ~(size_t)3;
+        mx += (size_t)12 * 600 * 64;   // column sums: <= ~600 row splits x 32-column strips per job
     }
     w.partial_floats = mx;
     w.partials = a.take<float>(mx);
@@ -2871,7 +2870,8 @@ int dec_backward(const DecParams& P, const DecGrads& G, const PackedMeta& pk, co
     }   // do_data
     if (!do_wgrad) return ABCD_OK;
 
-    // ---- weight gradients: reductions over all packed frames ----
+    // ---- weight gradients: reductions over all packed frames (epilogues and column sums deferred into three batched launches) ----
+    EpilogueBatch epilogues(w.partials, w.partial_floats, stream);
     dec_prev_index_kernel<<<min(pk.T_max, 592), 128, 0, stream>>>(pk.T_max, pk.B, pk.batch_sizes, pk.offsets, w.prev);
     KERNEL_CHECK();
     auto tn = [&](int Mo, int No, const float* A, long lda, const float* Bm, long ldb, const int* gather, GateMap md,
@@ -2906,5 +2906,5 @@ int dec_backward(const DecParams& P, const DecGrads& G, const PackedMeta& pk, co
     // feature2hidden
     TRY(tn(hc, P.fin, w.dHC0, hc, feat_in, P.fin, nullptr, gate_map_none(), G.w_f2h, P.fin, pk.B));
     TRY(colsum_launch(w.dHC0, hc, pk.B, hc, 1.f, G.b_f2h, 1, gate_map_none(), stream));
-    return ABCD_OK;
+    return epilogues.flush();
 }

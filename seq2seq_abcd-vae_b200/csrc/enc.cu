@@ -861,7 +861,8 @@ static EncWs enc_carve(void* base, size_t cap, int cell, int F, int B, int sumT,
         w.prev_fwd = a.take<int>(sumT);
         w.prev_bwd = a.take<int>(sumT);
         int s1 = sgemm_pick_splits(4 * H, H, sumT), s2 = sgemm_pick_splits(4 * H, F, sumT);
-        w.partial_floats = (size_t)4 * H * ((size_t)s1 * H > (size_t)s2 * F ? (size_t)s1 * H : (size_t)s2 * F);
+        // split-K partials of all four weight-gradient GEMMs (deferred, batched epilogues) + scratch of the column sums
+        w.partial_floats = (size_t)ndirs * 4 * H * ((size_t)s1 * H + (size_t)s2 * F) + 64 + (size_t)4 * 600 * 64;
         w.partials = a.take<float>(w.partial_floats);
     }
     w.bytes = a.off;
@@ -960,6 +961,7 @@ int enc_backward(const EncParams& P, const EncGrads& G, const PackedMeta& pk, co
 
     prev_index_kernel<<<min(pk.T_max, 592), 128, 0, stream>>>(pk.T_max, pk.batch_sizes, pk.offsets, w.prev_fwd, w.prev_bwd);
     KERNEL_CHECK();
+    EpilogueBatch epilogues(w.partials, w.partial_floats, stream);   // split-K epilogues + bias column sums: three launches at the end
     for (int d = 0; d < ndirs; ++d) {
         const GateMap map_ih = P.cell == 0 ? gate_map(H, 0, 1, 2, 3) : gate_map(H, 0, 1, 2, -1);
         const GateMap map_hh = P.cell == 0 ? gate_map(H, 0, 1, 2, 3) : gate_map(H, 0, 1, -1, 2);
@@ -985,5 +987,5 @@ int enc_backward(const EncParams& P, const EncGrads& G, const PackedMeta& pk, co
         TRY(colsum_launch(w.dbias[d], 4 * H, n_tiles, 4 * H, 1.f, G.b_ih[d], 1, map_ih, stream));
         TRY(colsum_launch(w.dbias[d], 4 * H, n_tiles, 4 * H, 1.f, G.b_hh[d], 1, map_hh, stream));
     }
-    return ABCD_OK;
+    return epilogues.flush();
 }

@@ -298,9 +298,9 @@ sgemm_kernel(GemmArgs g, int a_vec, int b_vec) {
     }
 }
 
-__global__ void splitk_reduce_kernel(GemmArgs g) {
+__device__ __forceinline__ void splitk_reduce_body(const GemmArgs& g, long first, long stride) {
     long total = (long)g.M * g.N;
-    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    for (long idx = first; idx < total; idx += stride) {
         int m = (int)(idx / g.N), n = (int)(idx % g.N);
         float s = 0.f;
         for (int z = 0; z < g.splits; ++z) s += g.partials[(long)z * total + idx];
@@ -317,17 +317,34 @@ __global__ void splitk_reduce_kernel(GemmArgs g) {
         *dst = v;
     }
 }
+__global__ void splitk_reduce_kernel(GemmArgs g) {
+    splitk_reduce_body(g, blockIdx.x * (long)blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x);
+}
+// deferred epilogues of several GEMMs in one launch (EpilogueBatch): blocks [bstart[j], bstart[j+1]) work on job j
+constexpr int EB_MAX = 16;
+struct ReduceJobs {
+    int n;
+    int bstart[EB_MAX + 1];
+    GemmArgs g[EB_MAX];
+};
+__global__ void splitk_reduce_batch_kernel(const __grid_constant__ ReduceJobs J) {
+    int j = 0;
+    while (j + 1 < J.n && (int)blockIdx.x >= J.bstart[j + 1]) ++j;
+    const int nb = J.bstart[j + 1] - J.bstart[j], lb = blockIdx.x - J.bstart[j];
+    splitk_reduce_body(J.g[j], lb * (long)blockDim.x + threadIdx.x, (long)nb * blockDim.x);
+}
 
 // Column sums (bias gradients).  blockIdx.x: 32-column strip, blockIdx.y: row split; 8 warps stride the rows of
 // the split, deterministic tree reduce in shared memory.  With gridDim.y > 1 the per-split sums go to
 // scratch[y][cols] and colsum_finish_kernel adds them in a fixed order.
-__global__ void colsum_kernel(const float* __restrict__ A, long lda, int rows, int cols, float alpha,
-                              float* __restrict__ out, int accumulate, GateMap dst, float* __restrict__ scratch) {
+__device__ __forceinline__ void colsum_body(const float* __restrict__ A, long lda, int rows, int cols, float alpha,
+                                            float* __restrict__ out, int accumulate, const GateMap& dst, float* __restrict__ scratch,
+                                            int strip, int split, int nsplit) {
     __shared__ float red[8][33];
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int c = strip * 32 + (threadIdx.x & 31);
     const int w = threadIdx.x >> 5;
-    const int per = (rows + gridDim.y - 1) / gridDim.y;
-    const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+    const int per = (rows + nsplit - 1) / nsplit;
+    const int r0 = split * per, r1 = min(rows, r0 + per);
     float s = 0.f;
     if (c < cols) {
         // four independent partial sums keep four loads in flight (the loop is latency-bound); fixed order
@@ -348,8 +365,8 @@ __global__ void colsum_kernel(const float* __restrict__ A, long lda, int rows, i
         float t = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
-        if (gridDim.y > 1) {
-            scratch[(long)blockIdx.y * cols + c] = t;
+        if (nsplit > 1) {
+            scratch[(long)split * cols + c] = t;
         } else {
             int d = gate_src_row(dst, c);
             if (d >= 0) {
@@ -359,12 +376,16 @@ __global__ void colsum_kernel(const float* __restrict__ A, long lda, int rows, i
         }
     }
 }
-// blockIdx.x: 32-column strip; warp w adds splits w, w+8, ... (four loads in flight), warp 0 adds the 8 warps: fixed order
-__global__ void colsum_finish_kernel(const float* __restrict__ scratch, int nsplit, int cols, float alpha,
-                                     float* __restrict__ out, int accumulate, GateMap dst) {
+__global__ void colsum_kernel(const float* __restrict__ A, long lda, int rows, int cols, float alpha,
+                              float* __restrict__ out, int accumulate, GateMap dst, float* __restrict__ scratch) {
+    colsum_body(A, lda, rows, cols, alpha, out, accumulate, dst, scratch, blockIdx.x, blockIdx.y, gridDim.y);
+}
+// strip: 32-column strip; warp w adds splits w, w+8, ... (four loads in flight), warp 0 adds the 8 warps: fixed order
+__device__ __forceinline__ void colsum_finish_body(const float* __restrict__ scratch, int nsplit, int cols, float alpha,
+                                                   float* __restrict__ out, int accumulate, const GateMap& dst, int strip) {
     __shared__ float red[8][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + lane;
+    const int c = strip * 32 + lane;
     float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
     if (c < cols) {
         int y = w;
@@ -388,6 +409,32 @@ __global__ void colsum_finish_kernel(const float* __restrict__ scratch, int nspl
             out[d] = accumulate ? out[d] + t : t;
         }
     }
+}
+__global__ void colsum_finish_kernel(const float* __restrict__ scratch, int nsplit, int cols, float alpha,
+                                     float* __restrict__ out, int accumulate, GateMap dst) {
+    colsum_finish_body(scratch, nsplit, cols, alpha, out, accumulate, dst, blockIdx.x);
+}
+// deferred column sums of several inputs in one launch per pass (EpilogueBatch)
+struct ColsumJob {
+    const float* A; long lda; int rows, cols; float alpha; float* out; int accumulate; GateMap dst; float* scratch; int nsplit, strips;
+};
+struct ColsumJobs {
+    int n;
+    int bstart[EB_MAX + 1];
+    ColsumJob j[EB_MAX];
+};
+__global__ void colsum_batch_kernel(const __grid_constant__ ColsumJobs J) {
+    int j = 0;
+    while (j + 1 < J.n && (int)blockIdx.x >= J.bstart[j + 1]) ++j;
+    const ColsumJob& q = J.j[j];
+    const int lb = blockIdx.x - J.bstart[j];
+    colsum_body(q.A, q.lda, q.rows, q.cols, q.alpha, q.out, q.accumulate, q.dst, q.scratch, lb % q.strips, lb / q.strips, q.nsplit);
+}
+__global__ void colsum_finish_batch_kernel(const __grid_constant__ ColsumJobs J) {   // bstart: strips of the jobs with nsplit > 1
+    int j = 0;
+    while (j + 1 < J.n && (int)blockIdx.x >= J.bstart[j + 1]) ++j;
+    const ColsumJob& q = J.j[j];
+    colsum_finish_body(q.scratch, q.nsplit, q.cols, q.alpha, q.out, q.accumulate, q.dst, blockIdx.x - J.bstart[j]);
 }
 
 template <int BM, int BN, int TM, int TN>
@@ -459,6 +506,85 @@ int sgemm_pick_splits(int M, int N, int K) {
     return s;
 }
 
+// ---- EpilogueBatch: deferred split-K epilogues and column sums of the calling thread ----
+namespace {
+struct EpilogueBatchState {
+    float* pool; size_t cap, used;
+    cudaStream_t stream;
+    ReduceJobs rj;
+    ColsumJobs cj;
+};
+thread_local EpilogueBatchState* t_eb = nullptr;
+int reduce_blocks(const GemmArgs& g) {
+    long total = (long)g.M * g.N;
+    int blocks = (int)((total + 255) / 256);
+    return blocks > 148 * 8 ? 148 * 8 : (blocks < 1 ? 1 : blocks);
+}
+int eb_flush(EpilogueBatchState* e) {
+    if (e->rj.n > 0) {
+        int total = 0;
+        for (int j = 0; j < e->rj.n; ++j) { e->rj.bstart[j] = total; total += reduce_blocks(e->rj.g[j]); }
+        e->rj.bstart[e->rj.n] = total;
+        ProfScope ps(PROF_GEMM, e->stream);
+        splitk_reduce_batch_kernel<<<total, 256, 0, e->stream>>>(e->rj);
+        KERNEL_CHECK();
+        e->rj.n = 0;
+    }
+    if (e->cj.n > 0) {
+        ProfScope ps(PROF_GEMM, e->stream);
+        int total = 0;
+        for (int j = 0; j < e->cj.n; ++j) { e->cj.bstart[j] = total; total += e->cj.j[j].strips * e->cj.j[j].nsplit; }
+        e->cj.bstart[e->cj.n] = total;
+        colsum_batch_kernel<<<total, 256, 0, e->stream>>>(e->cj);
+        KERNEL_CHECK();
+        ColsumJobs fin;
+        fin.n = 0;
+        total = 0;
+        for (int j = 0; j < e->cj.n; ++j)
+            if (e->cj.j[j].nsplit > 1) { fin.bstart[fin.n] = total; fin.j[fin.n++] = e->cj.j[j]; total += e->cj.j[j].strips; }
+        if (fin.n > 0) {
+            fin.bstart[fin.n] = total;
+            colsum_finish_batch_kernel<<<total, 256, 0, e->stream>>>(fin);
+            KERNEL_CHECK();
+        }
+        e->cj.n = 0;
+    }
+    e->used = 0;
+    return ABCD_OK;
+}
+// `floats` floats of the pool (flushing the batch first when it is full); nullptr when the request can never fit
+float* eb_take(EpilogueBatchState* e, size_t floats, int* err) {
+    floats = (floats + 3) & ~(size_t)3;
+    *err = ABCD_OK;
+    if (floats > e->cap) return nullptr;
+    if (e->used + floats > e->cap) { *err = eb_flush(e); if (*err != ABCD_OK) return nullptr; }
+    float* p = e->pool + e->used;
+    e->used += floats;
+    return p;
+}
+}  // namespace
+EpilogueBatch::EpilogueBatch(float* pool, size_t pool_floats, cudaStream_t stream) {
+    EpilogueBatchState* e = new EpilogueBatchState();
+    e->pool = pool; e->cap = pool ? pool_floats : 0; e->used = 0; e->stream = stream;
+    e->rj.n = 0; e->cj.n = 0;
+    t_eb = e;
+}
+int EpilogueBatch::flush() { return t_eb ? eb_flush(t_eb) : ABCD_OK; }
+EpilogueBatch::~EpilogueBatch() {
+    if (t_eb) { eb_flush(t_eb); delete t_eb; t_eb = nullptr; }
+}
+// split-K epilogue of `g`: deferred into the active batch, or launched now
+static int reduce_or_defer(const GemmArgs& g, cudaStream_t stream) {
+    if (t_eb && t_eb->stream == stream) {
+        if (t_eb->rj.n == EB_MAX) TRY(eb_flush(t_eb));   // (never with a job's partials still pending: they were taken before)
+        t_eb->rj.g[t_eb->rj.n++] = g;
+        return ABCD_OK;
+    }
+    splitk_reduce_kernel<<<reduce_blocks(g), 256, 0, stream>>>(g);
+    KERNEL_CHECK();
+    return ABCD_OK;
+}
+
 int sgemm_launch(const GemmArgs& gin, cudaStream_t stream) {
     GemmArgs g = gin;
     if (g.M <= 0 || g.N <= 0) return ABCD_OK;
@@ -469,15 +595,20 @@ int sgemm_launch(const GemmArgs& gin, cudaStream_t stream) {
     ARG_CHECK(!(g.b_nsrc.enabled && !g.b_kmajor), "sgemm: n source map needs k-major B");
     ProfScope ps(PROF_GEMM, stream);
     if (umma_enabled() && umma_rm_eligible(g)) return umma_rm_launch(g, stream);   // tall row-major products on tcgen05
-    if (umma_enabled() && umma_tn_eligible(g)) {
+    const bool tn = umma_enabled() && umma_tn_eligible(g);
+    if (t_eb && t_eb->stream == stream && (tn || g.splits > 1)) {
+        // deferred epilogue: the partials live in the batch's pool until its flush
+        if (t_eb->rj.n == EB_MAX) TRY(eb_flush(t_eb));
+        int err;
+        float* part = eb_take(t_eb, (size_t)g.splits * g.M * g.N, &err);
+        if (err != ABCD_OK) return err;
+        if (part) g.partials = part;
+        else TRY(eb_flush(t_eb));   // larger than the pool: the caller's own buffer, nothing else may be pending in it
+    }
+    if (tn) {
         // tensor-core path (tcgen05 3xTF32): partial tiles per split, then the common reduce/epilogue kernel
         TRY(umma_tn_launch(g, g.splits, stream));
-        long total = (long)g.M * g.N;
-        int blocks = (int)((total + 255) / 256);
-        if (blocks > 148 * 8) blocks = 148 * 8;
-        splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(g);
-        KERNEL_CHECK();
-        return ABCD_OK;
+        return reduce_or_defer(g, stream);
     }
     const int a_vec = ((uintptr_t)g.A % 16 == 0) && (g.lda % 4 == 0);
     const int b_vec = ((uintptr_t)g.B % 16 == 0) && (g.ldb % 4 == 0);
@@ -492,13 +623,7 @@ int sgemm_launch(const GemmArgs& gin, cudaStream_t stream) {
     if (use_small_tiles(g.M, g.N, g.splits)) r = launch_cfg<64, 64, 4, 4>(g, a_vec, b_vec, stream);
     else r = launch_cfg<128, 128, 8, 8>(g, a_vec, b_vec, stream);
     if (r != ABCD_OK) return r;
-    if (g.splits > 1) {
-        long total = (long)g.M * g.N;
-        int blocks = (int)((total + 255) / 256);
-        if (blocks > 148 * 8) blocks = 148 * 8;
-        splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(g);
-        KERNEL_CHECK();
-    }
+    if (g.splits > 1) return reduce_or_defer(g, stream);
     return ABCD_OK;
 }
 
@@ -510,10 +635,28 @@ ColsumScratch::~ColsumScratch() { t_colsum_scratch = nullptr; t_colsum_floats = 
 int colsum_launch(const float* A, long lda, int rows, int cols, float alpha, float* out, int accumulate,
                   GateMap dst, cudaStream_t stream) {
     float* scratch = t_colsum_scratch;
-    const size_t scratch_floats = t_colsum_floats;
+    size_t scratch_floats = t_colsum_floats;
     if (cols <= 0) return ABCD_OK;
-    ProfScope ps(PROF_GEMM, stream);
     const int strips = (cols + 31) / 32;
+    if (t_eb && t_eb->stream == stream) {
+        // deferred: one batched launch per pass at the flush; scratch from the batch's pool
+        if (t_eb->cj.n == EB_MAX) TRY(eb_flush(t_eb));
+        int nsplit = (148 * 4 + strips - 1) / strips;
+        if (nsplit > rows / 64) nsplit = rows / 64;
+        if (nsplit < 1) nsplit = 1;
+        float* sc = nullptr;
+        if (nsplit > 1) {
+            int err;
+            sc = eb_take(t_eb, (size_t)nsplit * cols, &err);
+            if (err != ABCD_OK) return err;
+            if (!sc) nsplit = 1;
+        }
+        ColsumJob& q = t_eb->cj.j[t_eb->cj.n++];
+        q.A = A; q.lda = lda; q.rows = rows; q.cols = cols; q.alpha = alpha; q.out = out; q.accumulate = accumulate; q.dst = dst;
+        q.scratch = sc; q.nsplit = nsplit; q.strips = strips;
+        return ABCD_OK;
+    }
+    ProfScope ps(PROF_GEMM, stream);
     // enough row splits to cover the GPU (~4 CTAs/SM), at least 64 rows per split
     int nsplit = 1;
     if (scratch) {

@@ -57,6 +57,16 @@ int sgemm_pick_splits(int M, int N, int K);
 // A caller-owned scratch buffer (see ColsumScratch) enables a row-split two-pass reduction for tall inputs.
 int colsum_launch(const float* A, long lda, int rows, int cols, float alpha, float* out, int accumulate,
                   GateMap dst, cudaStream_t stream);
+// RAII: inside its scope the split-K reduce / epilogue kernels of sgemm_launch and the column sums of colsum_launch issued by
+// this thread are DEFERRED and run as at most three batched launches at flush() (or at the end of the scope): the
+// weight-gradient sections issue ~10 GEMMs and ~10 column sums back to back, whose ~30 tiny epilogue launches become three.
+// `pool` (caller's workspace) holds every deferred GEMM's split-K partials and the column sums' scratch until the flush; when
+// it runs out the batch is flushed early.  GemmArgs::partials / ColsumScratch are ignored inside the scope.
+struct EpilogueBatch {
+    EpilogueBatch(float* pool, size_t pool_floats, cudaStream_t stream);
+    int flush();
+    ~EpilogueBatch();
+};
 // RAII: lends `floats` floats of the caller's workspace to colsum_launch calls made by this thread in this scope.
 struct ColsumScratch {
     ColsumScratch(float* p, size_t floats);

@@ -23,7 +23,7 @@ if [ "$DO_NCU" = ncu ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu_a.log 2>&1
   $CMD > $O/${TAG}_ncu_plain2.log 2>&1 &&
   ncu --set full --clock-control none --import-source on \
-      -k regex:'dec_bwd_ts_kernel|dec_fwd_pair_kernel|enc_fwd_kernel|enc_bwd_ts_kernel|umma_tn_kernel|umma_rm_kernel|sampler_fused' \
+      -k regex:'dec_bwd_push_kernel|dec_fwd_ahead_kernel|enc_fwd_kernel|enc_bwd_ts_kernel|umma_tn_kernel|umma_rm_kernel|sampler_fused' \
       -s 42 -c 21 -o $O/${TAG}_full -f $CMD > $O/${TAG}_ncu_b.log 2>&1
 fi
 ls -la $O | tail -n 20
