@@ -130,6 +130,11 @@ __device__ __forceinline__ float ld_cg(const float* p) {
     asm volatile("ld.global.cg.f32 %0, [%1];\n" : "=f"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ float2 ld_cg2(const float* p) {
+    float2 v;
+    asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ float4 ld_cg4(const float* p) {
     float4 v;
     asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];\n"

@@ -2007,14 +2007,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_push_kernel(DecK p) {
     umma::fence_after_sync();
 
     // dML rows (row r of frame t - 1, this CTA's x columns) -> every CTA's As; for rows that were active at step t (r < na_t) the
-    // gradient dx_t that came back through the cell is folded in first.  Pb1t: partials of step t ([16][H + Fp][ROWS], transposed).
+    // gradient dx_t that came back through the cell is folded in first.  Pb1t: partials of step t ([16][ROWS][H + Fp]).
     auto push_dml = [&](int t_prev, int na_t) {
         const int na_p = active_rows(p.batch_sizes[t_prev], tile, n_tiles);
         if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(dbar_addr), "r"((uint32_t)(na_p * 2 * Fp * 4)) : "memory");
         const long pbase = p.offsets[t_prev] + tile;
         // items: (row, pair of x columns): 16 bytes of the interleaved B3 input row
         for (int idx = tid; idx < na_p * ng_mine * 2; idx += NTHREADS) {
-            const int r = idx % na_p, hp = idx / na_p;                  // rows fastest: contiguous in the transposed partials
+            const int hp = idx % (ng_mine * 2), r = idx / (ng_mine * 2);   // column pairs fastest: adjacent in the row-major partials
             const int c0 = 4 * (rank + CL * (hp >> 1)) + 2 * (hp & 1);   // columns c0, c0 + 1
             const long pf = pbase + (long)n_tiles * r;                   // frame that produced x_t
             float* dm = p.dML + pf * (2 * Fp) + c0;
@@ -2025,18 +2025,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_push_kernel(DecK p) {
                 float e[2];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) e[j] = c0 + j < F ? __ldg(p.eps + pf * p.ld_eps + c0 + j) : 0.f;
-                float v[2][CL];
+                float2 v[CL];
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
+                for (int src = 0; src < CL; ++src) v[src] = ld_cg2(Pb1t + ((long)src * ROWS + r) * N1 + H + c0);
+                float dx[2] = {v[0].x, v[0].y};
 #pragma unroll
-                    for (int src = 0; src < CL; ++src) v[j][src] = c0 + j < F ? ld_cg(Pb1t + ((long)src * N1 + H + c0 + j) * ROWS + r) : 0.f;
-                float dx[2];
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    dx[j] = v[j][0];
-#pragma unroll
-                    for (int src = 1; src < CL; ++src) dx[j] += v[j][src];
-                }
+                for (int src = 1; src < CL; ++src) { dx[0] += v[src].x; dx[1] += v[src].y; }
                 m0.x += dx[0]; m0.y += dx[1];
                 m1.x += dx[0] * 0.5f * expf(0.5f * lv.x) * e[0]; m1.y += dx[1] * 0.5f * expf(0.5f * lv.y) * e[1];
             }
@@ -2054,18 +2048,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_push_kernel(DecK p) {
     };
     // recurrent carry dh of this CTA's units = sum of the B1' partials of the step that has just finished (rows < na_t)
     auto reduce_dh = [&](int na_t) {
-        for (int idx = tid; idx < ((na_t + 3) >> 2) * U; idx += NTHREADS) {
-            const int rq = idx % ((na_t + 3) >> 2), j = idx / ((na_t + 3) >> 2);
+        for (int idx = tid; idx < na_t * (U / 4); idx += NTHREADS) {
+            const int jq = idx % (U / 4), r = idx / (U / 4);
             float4 v[CL];
 #pragma unroll
-            for (int src = 0; src < CL; ++src) v[src] = ld_cg4(Pb1t + ((long)src * N1 + u0 + j) * ROWS + 4 * rq);
+            for (int src = 0; src < CL; ++src) v[src] = ld_cg4(Pb1t + ((long)src * ROWS + r) * N1 + u0 + 4 * jq);
             float4 a = v[0];
 #pragma unroll
             for (int src = 1; src < CL; ++src) { a.x += v[src].x; a.y += v[src].y; a.z += v[src].z; a.w += v[src].w; }
-            const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (4 * rq + i < na_t) dh_sm[(4 * rq + i) * U + j] = av[i];
+            *reinterpret_cast<float4*>(dh_sm + r * U + 4 * jq) = a;
         }
     };
     cluster_sync_all();   // every CTA's mbarriers are initialised before the first remote store
@@ -2171,7 +2162,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_push_kernel(DecK p) {
         const uint32_t idesc_ss = idesc_ts | (1u << 15);
         // re-lay `pieces` 16-byte pieces (4 k each) starting at piece `pc0` of the rows of `src` (pitch SP, piece-swizzled)
         // into the [k][row] operand tiles
-        auto relayout = [&](const float* src, int SP, int pc0) {
+        // `toff`: byte offset of the destination tile inside b_hi / b_lo (a second 32-row tile when at most 32 rows are active)
+        auto relayout_nosync = [&](const float* src, int SP, int pc0, uint32_t toff) {
             for (int idx = tid; idx < (ROWS / 4) * (TS_SLAB / 4); idx += NTHREADS) {
                 const int q = idx % (ROWS / 4), kq = idx / (ROWS / 4);
                 if (q >= nq) continue;
@@ -2180,30 +2172,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_push_kernel(DecK p) {
                 const float4 r1 = *reinterpret_cast<const float4*>(rb + SP);
                 const float4 r2 = *reinterpret_cast<const float4*>(rb + 2 * SP);
                 const float4 r3 = *reinterpret_cast<const float4*>(rb + 3 * SP);
-                umma::split_store(b_hi, b_lo, umma::tile_off<TS_CHUNK>(kq * 4 + 0, q), make_float4(r0.x, r1.x, r2.x, r3.x));
-                umma::split_store(b_hi, b_lo, umma::tile_off<TS_CHUNK>(kq * 4 + 1, q), make_float4(r0.y, r1.y, r2.y, r3.y));
-                umma::split_store(b_hi, b_lo, umma::tile_off<TS_CHUNK>(kq * 4 + 2, q), make_float4(r0.z, r1.z, r2.z, r3.z));
-                umma::split_store(b_hi, b_lo, umma::tile_off<TS_CHUNK>(kq * 4 + 3, q), make_float4(r0.w, r1.w, r2.w, r3.w));
+                umma::split_store(b_hi, b_lo, toff + umma::tile_off<TS_CHUNK>(kq * 4 + 0, q), make_float4(r0.x, r1.x, r2.x, r3.x));
+                umma::split_store(b_hi, b_lo, toff + umma::tile_off<TS_CHUNK>(kq * 4 + 1, q), make_float4(r0.y, r1.y, r2.y, r3.y));
+                umma::split_store(b_hi, b_lo, toff + umma::tile_off<TS_CHUNK>(kq * 4 + 2, q), make_float4(r0.z, r1.z, r2.z, r3.z));
+                umma::split_store(b_hi, b_lo, toff + umma::tile_off<TS_CHUNK>(kq * 4 + 3, q), make_float4(r0.w, r1.w, r2.w, r3.w));
             }
+        };
+        auto relayout = [&](const float* src, int SP, int pc0) {
+            relayout_nosync(src, SP, pc0, 0u);
             umma::fence_proxy_async();
             umma::fence_before_sync();
             __syncthreads();
         };
-        // accumulator blocks D^T[column][row] -> out[column][ROWS] (global partials stay transposed: every thread writes 64
-        // contiguous bytes per tcgen05.ld; the owners reduce them after the barrier)
+        // accumulator blocks D^T[column][row] -> out[row][ncols] (global partials, row-major: the 32 lanes of a warp hold 32
+        // consecutive columns, so every store instruction writes 128 contiguous bytes; the owners reduce them after the barrier)
         auto push_blocks = [&](int nblk, int ncols, float* out) {
             const int lq = warp & 3;
             for (int b = warp >> 2; b < nblk; b += 2) {
                 const int j = b * 128 + lq * 32 + lane;
 #pragma unroll 1
-                for (int r0 = 0; r0 < na; r0 += 16) {
-                    uint32_t r[16];
-                    umma::tmem_ld16(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * DBT_DCOLS + r0), r);
-                    if (j < ncols) {
-                        float4* o = reinterpret_cast<float4*>(out + (long)j * ROWS + r0);
+                for (int r0 = 0; r0 < na; r0 += 32) {
+                    const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * DBT_DCOLS + r0);
+                    float* o = out + (long)r0 * ncols + j;
+                    if (r0 + 16 < na) {   // 32 rows with one load (r0 + 32 <= 80 accumulator columns for r0 = 0, 32)
+                        uint32_t r[32];
+                        umma::tmem_ld32(taddr, r);
+                        if (j < ncols) {
 #pragma unroll
-                        for (int v = 0; v < 4; ++v)
-                            o[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                            for (int v = 0; v < 32; ++v)
+                                if (r0 + v < na) o[(long)v * ncols] = __uint_as_float(r[v]);
+                        }
+                    } else {
+                        uint32_t r[16];
+                        umma::tmem_ld16(taddr, r);
+                        if (j < ncols) {
+#pragma unroll
+                            for (int v = 0; v < 16; ++v)
+                                if (r0 + v < na) o[(long)v * ncols] = __uint_as_float(r[v]);
+                        }
                     }
                 }
             }
@@ -2242,18 +2248,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_push_kernel(DecK p) {
         DEC_TICK(4)
 
         // ---- dh of this CTA's units = sum of the partials (+ carry), then the gate gradients ----
-        for (int idx = tid; idx < ((na + 3) >> 2) * U; idx += NTHREADS) {
-            const int rq = idx % ((na + 3) >> 2), j = idx / ((na + 3) >> 2);   // 4 rows of one unit: contiguous in the transposed partials
+        for (int idx = tid; idx < na * (U / 4); idx += NTHREADS) {
+            const int jq = idx % (U / 4), r = idx / (U / 4);   // 4 units of one row: contiguous in the row-major partials
             float4 v[CL];
 #pragma unroll
-            for (int src = 0; src < CL; ++src) v[src] = ld_cg4(Pb2t + ((long)src * H + u0 + j) * ROWS + 4 * rq);
+            for (int src = 0; src < CL; ++src) v[src] = ld_cg4(Pb2t + ((long)src * ROWS + r) * H + u0 + 4 * jq);
             float4 a = v[0];
 #pragma unroll
             for (int src = 1; src < CL; ++src) { a.x += v[src].x; a.y += v[src].y; a.z += v[src].z; a.w += v[src].w; }
-            const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (4 * rq + i < na) dh_sm[(4 * rq + i) * U + j] += av[i];
+            float4* d = reinterpret_cast<float4*>(dh_sm + r * U + 4 * jq);
+            const float4 o = *d;
+            *d = make_float4(o.x + a.x, o.y + a.y, o.z + a.z, o.w + a.w);
         }
         __syncthreads();
 #pragma unroll
@@ -2296,6 +2301,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_push_kernel(DecK p) {
         // ---- B1': partial [dh_{t-1} | dx_t] from this CTA's gate columns ----
         DEC_TICK(6)
         // ---- B1' on the tensor cores: partial [dh_{t-1} | dx_t] from this CTA's gate columns (K = 4U = 64, two halves) ----
+        if (n_mma <= 32) {
+            // at most 32 active rows: a K half needs one 4 KB chunk of the operand tiles, so both halves are laid out side by side
+            // and all 72 MMAs are issued in one go (one relayout round, one completion wait)
+            relayout_nosync(Gsm, GSP, 0, 0u);
+            relayout_nosync(Gsm, GSP, TS_SLAB / 4, (uint32_t)TS_CHUNK);
+            umma::fence_proxy_async();
+            umma::fence_before_sync();
+            __syncthreads();
+            DEC_TICK(10)
+            if (tid == 0) {
+                umma::fence_after_sync();
+                const uint32_t bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo), wl = umma::smem_u32(wlo1);
+                // consecutive instructions go to different accumulator blocks (an instruction that accumulates into the block
+                // of its predecessor waits for it)
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int kg = 0; kg < TS_SLAB / 8; ++kg) {
+                        const uint64_t dbh = umma::make_desc(bh + half * TS_CHUNK + kg * 1024, TS_CHUNK, 512);
+                        const uint64_t dbl = umma::make_desc(bl + half * TS_CHUNK + kg * 1024, TS_CHUNK, 512);
+#pragma unroll
+                        for (int prod = 0; prod < 3; ++prod) {
+#pragma unroll
+                            for (int b = 0; b < 3; ++b) {
+                                const uint32_t ta = tmem + (uint32_t)(DBT_A1_COL + b * 4 * U + half * TS_SLAB + kg * 8);
+                                const uint32_t td = tmem + (uint32_t)(b * DBT_DCOLS);
+                                if (prod == 0) mma_tf32_ts(td, ta, dbh, idesc_ts, (half > 0 || kg > 0) ? 1u : 0u);
+                                else if (prod == 1) mma_tf32_ts(td, ta, dbl, idesc_ts, 1u);
+                                else umma::mma_tf32(td, umma::make_desc(wl + half * ((DBT_M1 / 32) * TS_CHUNK) + b * 4 * TS_CHUNK + kg * 1024, TS_CHUNK, 512), dbh, idesc_ss, 1u);
+                            }
+                        }
+                    }
+                }
+                umma::commit(&bar);
+            }
+            bar_uses += 1;
+        } else
         for (int half = 0; half < 2; ++half) {
             if (half == 1) umma::mbar_wait(&bar, (bar_uses - 1) & 1);   // the MMAs of the first half have read the tiles
             relayout(Gsm, GSP, half * (TS_SLAB / 4));
@@ -2322,6 +2364,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_bwd_push_kernel(DecK p) {
         }
         umma::mbar_wait(&bar, (bar_uses - 1) & 1);
         umma::fence_after_sync();
+        DEC_TICK(11)
         push_blocks(3, N1, Pb1);
         DEC_TICK(7)
         cluster_sync_all();

@@ -668,6 +668,8 @@ __device__ __forceinline__ void ts_pair_issue(TsPairCtx& c, int nrows) {
     umma::commit(c.done);
 }
 constexpr int TSP_GP = 64 + 4;   // pitch of gpre
+// send / recv: [ROWS][64] floats in global memory (row-major: the 32 lanes of a warp hold 32 consecutive gate columns, so every
+// store and load instruction covers 128 contiguous bytes)
 __device__ __forceinline__ void ts_pair_drain_send(TsPairCtx& c, float* gpre, float* send, int nrows, int tid) {
     const int warp = tid >> 5, lane = tid & 31;
     const int n_mma = (nrows + 15) & ~15;
@@ -675,25 +677,29 @@ __device__ __forceinline__ void ts_pair_drain_send(TsPairCtx& c, float* gpre, fl
     c.n_phase += 1;
     umma::fence_after_sync();
     // accumulator lanes: quadrants 2 kh, 2 kh + 1 are this CTA's own units, the other two go to the partner.
-    // Warps w and w + 4 share lane quadrant w & 3 and split the 16-row blocks: warp < 4 takes blocks 0..2, warp >= 4 blocks 3..4.
+    // Warps w and w + 4 share lane quadrant w & 3 and split the 32-row blocks: warp < 4 takes rows [0, 32) and [64, 80), warp >= 4 [32, 64).
     const int lq = warp & 3;
     const bool own = (lq >> 1) == c.kh;
     const int col64 = (lq & 1) * 32 + lane;
-    const int rb0 = warp < 4 ? 0 : 3, rb1 = warp < 4 ? 3 : 5;
+    float* dst = own ? gpre + col64 : send + col64;
+    const int pitch = own ? TSP_GP : 64;
 #pragma unroll 1
-    for (int rb = rb0; rb < rb1; ++rb) {
-        if (rb * 16 >= n_mma) break;
-        uint32_t v[16];
-        umma::tmem_ld16(c.tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(rb * 16), v);
-        if (own) {
+    for (int blk = (warp < 4 ? 0 : 1); blk < 3; blk += 2) {
+        const int r0 = blk * 32;
+        if (r0 >= n_mma) break;
+        const uint32_t taddr = c.tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)r0;
+        if (r0 + 16 < nrows && r0 + 32 <= TS_D_COLS_M) {
+            uint32_t v[32];
+            umma::tmem_ld32(taddr, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (r0 + j < nrows) dst[(r0 + j) * pitch] = __uint_as_float(v[j]);
+        } else {
+            uint32_t v[16];
+            umma::tmem_ld16(taddr, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                if (rb * 16 + j < nrows) gpre[(rb * 16 + j) * TSP_GP + col64] = __uint_as_float(v[j]);
-        } else {
-            float4* dst = reinterpret_cast<float4*>(send + (size_t)col64 * ROWS + rb * 16);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                if (r0 + j < nrows) dst[(r0 + j) * pitch] = __uint_as_float(v[j]);
         }
     }
     umma::fence_before_sync();
@@ -703,30 +709,15 @@ __device__ __forceinline__ void ts_pair_drain_recv(const TsPairCtx& c, float* gp
     const int lq = warp & 3;
     if ((lq >> 1) != c.kh) return;
     const int col64 = (lq & 1) * 32 + lane;
-    const int rb0 = warp < 4 ? 0 : 3, rb1 = warp < 4 ? 3 : 5;
-    float4 pv[3][4];
+    // the four receiving warps: columns by (lq & 1, lane), rows interleaved between warp < 4 and warp >= 4
+#pragma unroll 1
+    for (int r0 = (warp < 4 ? 0 : 8); r0 < nrows; r0 += 16) {
+        float pv[8];
 #pragma unroll
-    for (int bi = 0; bi < 3; ++bi) {
-        const int rb = rb0 + bi;
-        if (rb < rb1 && rb * 16 < nrows) {
+        for (int j = 0; j < 8; ++j) pv[j] = r0 + j < nrows ? ld_cg(recv + (size_t)(r0 + j) * 64 + col64) : 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) pv[bi][q] = ld_cg4(recv + (size_t)col64 * ROWS + rb * 16 + 4 * q);
-        }
-    }
-#pragma unroll
-    for (int bi = 0; bi < 3; ++bi) {
-        const int rb = rb0 + bi;
-        if (rb < rb1 && rb * 16 < nrows) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float a[4] = {pv[bi][q].x, pv[bi][q].y, pv[bi][q].z, pv[bi][q].w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int r = rb * 16 + 4 * q + j;
-                    if (r < nrows) gpre[r * TSP_GP + col64] += a[j];
-                }
-            }
-        }
+        for (int j = 0; j < 8; ++j)
+            if (r0 + j < nrows) gpre[(r0 + j) * TSP_GP + col64] += pv[j];
     }
 }
 

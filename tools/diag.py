@@ -91,6 +91,7 @@ if os.environ.get('ABCD_TIMING') == '3':
 	v = list(out); n = float(max(v[15], 1))
 	names = ['prefetch', 'B3 gemm', 'B3 store', 'B2 local gemm', 'barrier', 'B2 reduce', 'pointwise', 'B1 local gemm', 'barrier', 'B1 reduce', 'barrier']
 	print('dec_bwd CTA0 cycles/step: ' + ', '.join('%s %.0f' % (nm, x / n) for nm, x in zip(names, v[:11])) + ' (steps %d, total %.0f)' % (v[15], sum(v[:11]) / n))
+	print('   B1 detail (push kernel; slots 10, 11 are part of the step but not of the list above): relayout (<= 32 rows) %.0f, MMA issue -> done %.0f' % (v[10] / n, v[11] / n))
 elif os.environ.get('ABCD_TIMING'):
 	enc_timing()
 	dec_timing()
