@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
     float* Wx = W2s + U * 2 * Fp;             // [Fp][4U]: input rows of the gate weights of this CTA's units
     float* gpre = Wx + Fp * (4 * U);          // [ROWS][TSP_GP]: h_{t-1} W_hh of this CTA's gate columns
     float* stage_base = gpre + ROWS * TSP_GP;
-    float* red = stage_base + dfa_stage_floats();   // 40 floats
+    float* red = stage_base + dfa_stage_floats();   // 64 floats
     const Stage st = make_stage(stage_base, KC);
     const Stage st1 = make_stage(stage_base, ABCD_H);   // one-chunk staging of P2 (only buf0, at most DFA_P2_ONE_ROWS rows)
     float* Hs = st.buf0;                      // [ROWS][HSP] (the staging buffers are idle between phases)
@@ -807,7 +807,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
     }
     const int ncg3 = 2 * Fp / 4;                                      // column groups of the local emission GEMM
     const int NG = Fp / 4;                                            // x column groups
-    // partial emission parameters, laid out for the reader: [source CTA][x column group][row][mean x 4 | log-variance x 4]
+    // partial emission parameters, laid out for writer and reader alike: [source CTA][x column group][mean | log-variance][row][4]
     float* Pmine = p.Pbuf + (long)blockIdx.x * ROWS * (2 * Fp);
     const float* Ptile = p.Pbuf + (long)tile * CL * ROWS * (2 * Fp);
     // pair exchange of the gate partial sums (the backward pass's partial buffer is idle during the forward pass)
@@ -916,6 +916,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
                 }
                 hreg[j] = h;
                 p.Hall[((long)B + frame) * H + unit] = h;
+                // (a transposed copy in shared memory + 16-byte image stores, 4x fewer sectors, measured slower: 1.23 vs 1.17 ms)
                 if (na_next > 0) ts_image_store(himg[t & 1], unit, r, h);
             }
             ts_image_publish();
@@ -970,9 +971,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
                 }
                 asm volatile("bar.sync 1, 224;\n" ::: "memory");   // warps 0..6: the hidden slice is complete
                 // ---- P3a: this CTA's share of the emission parameters (K-split over the hidden units, see dec_fwd_kernel) ----
-                for (int item = tid; item < ncg3 * 16; item += NTHREADS - 32) {
-                    const int cg = item % ncg3, r0 = item / ncg3;   // rows r0 + 16 i
-                    if (r0 >= na) continue;
+                const int nr0 = min(16, na);
+                for (int item = tid; item < ncg3 * nr0; item += NTHREADS - 32) {
+                    const int r0 = item % nr0, cg = item / nr0;   // rows r0 + 16 i; consecutive lanes write consecutive rows (contiguous bytes)
                     const float* a = Hs + r0 * HSP + ((cg * 4 < Fp) ? 0 : U);
                     const float* w = W2s + cg * 4;
                     float o[5][4];
@@ -996,7 +997,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
 #pragma unroll
                     for (int i = 0; i < 5; ++i) {
                         const int r = r0 + 16 * i;
-                        if (r < na) *reinterpret_cast<float4*>(Pmine + ((long)(cg % NG) * ROWS + r) * 8 + (cg / NG) * 4) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+                        if (r < na) *reinterpret_cast<float4*>(Pmine + (((long)(cg % NG) * 2 + cg / NG) * ROWS + r) * 4) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
                     }
                 }
             }
@@ -1033,7 +1034,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_fwd_ahead_kernel(DecK p) {
                     gv[j] = (valid && p.gt && cj + j < F) ? __ldg(p.gt + frame * p.ld_gt + cj + j) : 0.f;
                 }
                 float4 pp[CL];
-                const float* src0 = Ptile + ((long)(c0 >> 2) * ROWS + r) * 8 + which * 4;
+                const float* src0 = Ptile + (((long)(c0 >> 2) * 2 + which) * ROWS + r) * 4;
 #pragma unroll
                 for (int src = 0; src < CL; ++src) pp[src] = valid ? ld_cg4(src0 + (long)src * ROWS * (2 * Fp)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 float4 acc4;
