@@ -21,9 +21,15 @@ if [ "$DO_NCU" = ncu ]; then
   CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph"
   $CMD > $O/${TAG}_ncu_plain.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu_a.log 2>&1
+  # full-set captures: the four persistent kernels of one step with source correlation, then the GEMM / sampler kernels of a
+  # step without it (the report must stay below the 64 MiB that travel back)
   $CMD > $O/${TAG}_ncu_plain2.log 2>&1 &&
   ncu --set full --clock-control none --import-source on \
-      -k regex:'dec_bwd_push_kernel|dec_fwd_ahead_kernel|enc_fwd_kernel|enc_bwd_ts_kernel|umma_tn_kernel|umma_rm_kernel|sampler_fused' \
-      -s 42 -c 21 -o $O/${TAG}_full -f $CMD > $O/${TAG}_ncu_b.log 2>&1
+      -k regex:'dec_bwd_push_kernel|dec_fwd_ahead_kernel|enc_fwd_kernel|enc_bwd_ts_kernel' \
+      -s 8 -c 4 -o $O/${TAG}_full -f $CMD > $O/${TAG}_ncu_b.log 2>&1
+  $CMD > $O/${TAG}_ncu_plain3.log 2>&1 &&
+  ncu --set full --clock-control none \
+      -k regex:'umma_tn_kernel|umma_rm_kernel|sampler_fused' \
+      -s 34 -c 17 -o $O/${TAG}_gemm -f $CMD > $O/${TAG}_ncu_c.log 2>&1
 fi
 ls -la $O | tail -n 20
