@@ -31,5 +31,8 @@ if [ "$DO_NCU" = ncu ]; then
   ncu --set full --clock-control none \
       -k regex:'umma_tn_kernel|umma_rm_kernel|sampler_fused' \
       -s 34 -c 17 -o $O/${TAG}_gemm -f $CMD > $O/${TAG}_ncu_c.log 2>&1
+  # only the counters of the GEMM capture travel back (at most 64 MiB of gpurun_out/ are copied)
+  ncu -i $O/${TAG}_gemm.ncu-rep --page raw --csv > $O/${TAG}_gemm_raw.csv 2>/dev/null && rm -f $O/${TAG}_gemm.ncu-rep
 fi
-ls -la $O | tail -n 20
+cat $O/${TAG}_tests.log $O/${TAG}_smoke.log 2>/dev/null | tail -n 6
+du -sh $O; ls -la $O | tail -n 20
