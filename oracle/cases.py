@@ -24,6 +24,11 @@ EXTRA_CASES = {
 	'train_lstm_f5': dict(rnn='LSTM', F=5, K=16, f=32, lengths=[7, 5, 5, 3, 1], pretrain=False, tau=1.0, N_data=50, seed=7),
 	'train_gru_f129_speaker': dict(rnn='GRU', F=129, K=32, f=64, lengths=[12, 12, 9, 4, 4, 4, 2, 1, 1], pretrain=False, tau=0.7, N_data=9, seed=8,
 								num_speakers=4, E=256),
+	# 88 < F <= 128: the output size is too wide for the two-barrier decoder kernels, the library falls back to the barrier-exchange
+	# ones (forward: CTA-pair tcgen05 kernel at >= 48 rows per tile, FFMA below; backward: dec_bwd_ts_kernel with 32-wide staging)
+	'train_lstm_f97_7tiles': dict(rnn='LSTM', F=97, K=32, f=64, lengths=sorted([(i * 7) % 11 + 1 for i in range(343)], reverse=True),
+								pretrain=False, tau=0.9, N_data=2000, seed=9),
+	'train_gru_f97': dict(rnn='GRU', F=97, K=32, f=64, lengths=[9, 9, 7, 4, 4, 2, 1], pretrain=True, tau=1.0, N_data=7, seed=10),
 }
 # plain/ variant (Gaussian latent, BASELINE.json configs[1]); `f` is the latent size (plain/learning.py -f, default 16)
 PLAIN_CASES = {
