@@ -92,8 +92,12 @@ int abcd_max_active_clusters(int which, int F);
 /* debug (env ABCD_TIMING=1): per-phase clock cycles of CTA 0 of the last enc_fwd launch: out10[0..4] = setup, gemm,
  * epilogue, barrier, steps; out10[5..9] = breakdown of the gemm phase */
 int abcd_debug_enc_timing(unsigned long long* out10);
-/* same for the last dec_fwd launch: out16[0..9] = P1 setup, P1 gemm, P1 cell, barrier, P2 gemm, P2 store, barrier, P3 setup+gemm,
- * P3 sample, barrier; out16[10..14] = breakdown of the P1 gemm; out16[15] = steps */
+/* same for the last decoder launch (env ABCD_TIMING=1: forward kernel, 3: backward kernel; env ABCD_TIMING_CTA=k: the CTA that
+ * records, default 0): out16[0..10] = cycles per phase in program order, out16[15] = steps.  The phase list depends on the
+ * kernel that ran -- tools/diag.py names the slots of each (two-barrier forward kernel: x wait, x product, cell + publish,
+ * barrier A, P2, P2 epilogue + P3a, accumulator read-back, barrier B, P3b, x push, -, with out16[10..13] = MMA issue time of the
+ * issuing thread, arrive A, arrive B, P3b loads + sums; backward: wait, B3, B3 epilogue, B2', barrier, -, gate gradients, B1'
+ * read-back, barrier, dx reduce + push, B1' relayout, with out16[11] = B1' MMA issue -> done) */
 int abcd_debug_dec_timing(unsigned long long* out16);
 /* measurement (bench.py "latency_roofline"): nanoseconds per round of the publish -> cluster barrier -> consume exchange that
  * every phase of the persistent recurrent kernels performs, on ONE cluster of `cluster_size` CTAs x 256 threads.
